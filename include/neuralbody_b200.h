@@ -1,0 +1,137 @@
+/* neuralbody_b200 -- C ABI of the B200-native volumetric-render hot path.
+ *
+ * The reference (zju3dv/neuralbody @ 3c516b9) is pure Python over PyTorch and has no FFI
+ * of its own; its plugin boundary for this path is
+ *     make_renderer(cfg, net).render(batch)       lib/networks/renderer/make_renderer.py:5-9
+ *                                                 lib/networks/renderer/if_clight_renderer.py:94-122
+ * This header is the C surface a binding for that boundary calls (the ctypes binding
+ * shipped in neuralbody_b200/capi.py is the one a reference maintainer would add;
+ * see INTEGRATION.md).  Conventions:
+ *   - plain C types only; every pointer marked `device` is caller-owned CUDA memory that
+ *     the library neither frees nor retains beyond the call;
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*); no
+ *     hidden synchronisation, no allocation;
+ *   - return value 0 = ok, <0 = error (see NB_ERR_*); nb_last_error() gives a thread-local
+ *     message.  No exceptions cross the boundary.
+ */
+#ifndef NEURALBODY_B200_H
+#define NEURALBODY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_ABI_VERSION 1
+
+#define NB_OK               0
+#define NB_ERR_BAD_ARG     (-1)
+#define NB_ERR_UNSUPPORTED (-2)
+#define NB_ERR_CUDA        (-3)
+
+/* element type of a packed feature volume */
+#define NB_DTYPE_F32 0
+#define NB_DTYPE_F16 1
+
+/* arithmetic of the decoder MLP inside nb_render_fwd */
+#define NB_PRECISION_FP32      0   /* exact: fp32 FFMA everywhere (GPU-side oracle, fallback)            */
+#define NB_PRECISION_TC_FP16   1   /* tcgen05 tensor cores: fp16 operands, fp32 accumulate in TMEM       */
+
+#define NB_NUM_LEVELS   4          /* SparseConvNet returns 4 dense volumes, latent_xyzc.py:179-204     */
+#define NB_FEAT_DIM     352        /* 32+64+128+128 channels, latent_xyzc.py:20                         */
+#define NB_XYZ_PE_DIM   63         /* embedder.py:53  (cfg.xyz_res = 10)                                */
+#define NB_VIEW_PE_DIM  27         /* embedder.py:54  (cfg.view_res = 4)                                */
+
+int         nb_abi_version(void);
+const char* nb_last_error(void);
+int         nb_has_precision(int precision);   /* 1 if nb_render_fwd implements NB_PRECISION_<precision> */
+
+/* ------------------------------------------------------------------------------------------
+ * Feature volumes.  Replaces the per-point F.grid_sample reads of NCDHW fp32 volumes in
+ * Network.interpolate_features (lib/networks/latent_xyzc.py:62-72): the volumes returned by
+ * net.encode_sparse_voxels (latent_xyzc.py:30-39) are re-laid-out ONCE per frame as
+ * channels-last [B][D][H][W][C] so one trilinear corner is one contiguous vector.
+ * Blob layout: level l starts at nb_packed_volume_level_offset(...), 256-byte aligned.
+ */
+typedef struct nb_volume_level {
+    const float* data;   /* device, (B, C, D, H, W) fp32 contiguous, as `.dense()` returns it */
+    int C, D, H, W;
+} nb_volume_level;
+
+size_t nb_packed_volume_bytes(const int dims[NB_NUM_LEVELS][4] /* C,D,H,W */, int batch, int dtype);
+size_t nb_packed_volume_level_offset(const int dims[NB_NUM_LEVELS][4], int batch, int dtype, int level);
+int    nb_pack_volume(const nb_volume_level levels[NB_NUM_LEVELS], int batch, int dtype,
+                      void* out_blob /* device */, size_t out_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decoder weights.  Replaces the eight nn.Conv1d(k=1) modules + nn.Embedding `latent` of
+ * Network (lib/networks/latent_xyzc.py:13-28) as consumed by calculate_density_color (:91-126).
+ * All pointers device fp32, Conv1d layout (out, in[, 1]).  The pack step performs the exact
+ * fold  view_fc[:, :256] o latent_fc o (feature_fc (+) latent[latent_index])  (no activation
+ * between those layers) in fp64, and emits fp32 K-major matrices for the exact kernel and fp16
+ * tcgen05-canonical (UMMA K-major, no-swizzle) matrices for the tensor-core kernel.
+ */
+typedef struct nb_decoder_weights {
+    const float *fc0_w, *fc0_b;         /* (256,352) (256) */
+    const float *fc1_w, *fc1_b;         /* (256,256) (256) */
+    const float *fc2_w, *fc2_b;         /* (256,256) (256) */
+    const float *alpha_w, *alpha_b;     /* (1,256)   (1)   */
+    const float *feature_w, *feature_b; /* (256,256) (256) */
+    const float *latent_w, *latent_b;   /* (256,384) (256) */
+    const float *view_w, *view_b;       /* (128,346) (128) */
+    const float *rgb_w, *rgb_b;         /* (3,128)   (3)   */
+    const float *latent;                /* (num_train_frame,128) embedding table */
+    const int64_t *latent_index;        /* device (batch) int64, sp_input['latent_index'] */
+    int num_train_frame;
+    int batch;
+} nb_decoder_weights;
+
+size_t nb_packed_weights_bytes(int batch);
+int    nb_pack_weights(const nb_decoder_weights* w, void* out_blob /* device */, size_t out_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused forward render.  One launch replaces the whole chunk loop of Renderer.render
+ * (if_clight_renderer.py:107-120): get_sampling_points (:11-27) -> viewdir (:68) ->
+ * Network.pts_to_can_pts / get_grid_coords / interpolate_features / calculate_density_color
+ * (latent_xyzc.py:41-126, embedder.py:5-50) -> raw2outputs (nerf_net_utils.py:6-51).
+ */
+typedef struct nb_render_args {
+    int batch;             /* B frames */
+    int n_rays;            /* n rays per frame */
+    int n_samples;         /* cfg.N_samples */
+    const float* ray_o;    /* device (B,n,3) */
+    const float* ray_d;    /* device (B,n,3), NOT normalised; near/far are parametric t */
+    const float* near;     /* device (B,n) */
+    const float* far;      /* device (B,n) */
+    const float* t_vals;   /* device (S) = torch.linspace(0,1,S); NULL -> computed in-kernel */
+    const float* t_rand;   /* device (B,n,S) uniform [0,1) jitter (cfg.perturb>0 and net.training), or NULL */
+    const float* R;        /* device (B,3,3)  sp_input['R']  */
+    const float* Th;       /* device (B,3)    sp_input['Th'] (either (B,1,3) or (B,3) upstream) */
+    const float* bounds;   /* device (B,2,3)  sp_input['bounds'] (SMPL-frame box, xyz) */
+    float voxel_size[3];   /* cfg.voxel_size, dhw order */
+    int   out_sh[3];       /* sp_input['out_sh'], dhw order */
+    int   level_dims[NB_NUM_LEVELS][4]; /* C,D,H,W of each packed level */
+    const void* volume_blob;  /* device, from nb_pack_volume */
+    int   volume_dtype;       /* NB_DTYPE_* of volume_blob */
+    const void* weights_blob; /* device, from nb_pack_weights (same batch) */
+    int   white_bkgd;      /* cfg.white_bkgd */
+    int   precision;       /* NB_PRECISION_* */
+    float* rgb_map;        /* device (B,n,3) */
+    float* disp_map;       /* device (B,n)   */
+    float* acc_map;        /* device (B,n)   */
+    float* weights;        /* device (B,n,S) or NULL to skip */
+    float* depth_map;      /* device (B,n)   */
+    float* raw;            /* device (B,n,S,4) decoder output (rgb logits, sigma) or NULL; debugging / parity */
+} nb_render_args;
+
+int nb_render_fwd(const nb_render_args* args, void* stream);
+
+/* number of kernels nb_render_fwd enqueues per call for the given precision (for launch accounting) */
+int nb_render_fwd_launches(int precision);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURALBODY_B200_H */

@@ -1,0 +1,90 @@
+"""ctypes binding of include/neuralbody_b200.h -- the binding a reference maintainer would
+add next to lib/networks/renderer/ (see INTEGRATION.md).  There is NO fallback: if the
+shared library is missing or does not load, importing/using the product path raises."""
+import ctypes as C
+import os
+
+from . import _build
+
+NB_OK = 0
+NB_DTYPE_F32, NB_DTYPE_F16 = 0, 1
+NB_PRECISION_FP32, NB_PRECISION_TC_FP16 = 0, 1
+NB_NUM_LEVELS = 4
+
+EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
+           "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
+           "nb_render_fwd_launches"]
+
+
+class nb_volume_level(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("C", C.c_int), ("D", C.c_int), ("H", C.c_int), ("W", C.c_int)]
+
+
+class nb_decoder_weights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "fc0_w", "fc0_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "alpha_w", "alpha_b", "feature_w", "feature_b",
+        "latent_w", "latent_b", "view_w", "view_b", "rgb_w", "rgb_b", "latent", "latent_index")] + \
+        [("num_train_frame", C.c_int), ("batch", C.c_int)]
+
+
+LevelDims = (C.c_int * 4) * NB_NUM_LEVELS
+
+
+class nb_render_args(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("n_rays", C.c_int), ("n_samples", C.c_int),
+        ("ray_o", C.c_void_p), ("ray_d", C.c_void_p), ("near", C.c_void_p), ("far", C.c_void_p),
+        ("t_vals", C.c_void_p), ("t_rand", C.c_void_p),
+        ("R", C.c_void_p), ("Th", C.c_void_p), ("bounds", C.c_void_p),
+        ("voxel_size", C.c_float * 3), ("out_sh", C.c_int * 3), ("level_dims", LevelDims),
+        ("volume_blob", C.c_void_p), ("volume_dtype", C.c_int),
+        ("weights_blob", C.c_void_p),
+        ("white_bkgd", C.c_int), ("precision", C.c_int),
+        ("rgb_map", C.c_void_p), ("disp_map", C.c_void_p), ("acc_map", C.c_void_p), ("weights", C.c_void_p),
+        ("depth_map", C.c_void_p), ("raw", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load(path=None):
+    """dlopen libneuralbody_b200.so and declare every prototype. Raises if absent."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "libneuralbody_b200.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU fallback for the render path" % path)
+    lib = C.CDLL(path)
+    lib.nb_abi_version.restype = C.c_int
+    lib.nb_last_error.restype = C.c_char_p
+    lib.nb_has_precision.restype = C.c_int
+    lib.nb_has_precision.argtypes = [C.c_int]
+    lib.nb_packed_volume_bytes.restype = C.c_size_t
+    lib.nb_packed_volume_bytes.argtypes = [LevelDims, C.c_int, C.c_int]
+    lib.nb_packed_volume_level_offset.restype = C.c_size_t
+    lib.nb_packed_volume_level_offset.argtypes = [LevelDims, C.c_int, C.c_int, C.c_int]
+    lib.nb_pack_volume.restype = C.c_int
+    lib.nb_pack_volume.argtypes = [nb_volume_level * NB_NUM_LEVELS, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.nb_packed_weights_bytes.restype = C.c_size_t
+    lib.nb_packed_weights_bytes.argtypes = [C.c_int]
+    lib.nb_pack_weights.restype = C.c_int
+    lib.nb_pack_weights.argtypes = [C.POINTER(nb_decoder_weights), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.nb_render_fwd.restype = C.c_int
+    lib.nb_render_fwd.argtypes = [C.POINTER(nb_render_args), C.c_void_p]
+    lib.nb_render_fwd_launches.restype = C.c_int
+    lib.nb_render_fwd_launches.argtypes = [C.c_int]
+    if lib.nb_abi_version() != 1:
+        raise RuntimeError("libneuralbody_b200.so ABI version mismatch")
+    if path == _build.LIB_PATH:
+        _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != NB_OK:
+        msg = load().nb_last_error().decode("utf-8", "replace")
+        raise RuntimeError("%s failed (status %d): %s" % (what, status, msg))

@@ -1,0 +1,277 @@
+// extern "C" entry points of libneuralbody_b200.so (see include/neuralbody_b200.h) and the
+// once-per-frame pack kernels (volume re-layout, decoder-weight fold + re-layout).
+#include <stdarg.h>
+#include <stdio.h>
+#include "nb_internal.h"
+
+namespace nb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// ------------------------------------------------------------------------------------------
+// Volume pack: (B,C,D,H,W) fp32 -> [B][D][H][W][C] fp32/fp16 through a shared-memory
+// transpose tile so that both the NCDHW reads (along W..DHW) and the channels-last writes
+// (along C) are coalesced.  HBM-bound: reads 4 B and writes 4 or 2 B per element.
+template <typename OT>
+__device__ __forceinline__ OT cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+
+template <typename OT>
+__global__ void __launch_bounds__(256) pack_volume_kernel(const float* __restrict__ src, OT* __restrict__ dst, int C,
+                                                          size_t nvox /* D*H*W */, int batch) {
+    // tile: 32 voxels x 32 channels
+    __shared__ float tile[32][33];
+    const size_t tiles_v = (nvox + 31) / 32;
+    const int tiles_c = (C + 31) / 32;
+    const size_t total = tiles_v * tiles_c * batch;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (size_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const int b = (int)(t / (tiles_v * tiles_c));
+        const size_t rem = t % (tiles_v * tiles_c);
+        const int tc = (int)(rem / tiles_v);
+        const size_t tv = rem % tiles_v;
+        const float* s = src + (size_t)b * C * nvox;
+        OT* d = dst + (size_t)b * C * nvox;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = tc * 32 + ty + 8 * j;
+            const size_t v = tv * 32 + tx;
+            tile[ty + 8 * j][tx] = (c < C && v < nvox) ? __ldg(s + (size_t)c * nvox + v) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t v = tv * 32 + ty + 8 * j;
+            const int c = tc * 32 + tx;
+            if (c < C && v < nvox) d[v * C + c] = cvt_out<OT>(tile[tx][ty + 8 * j]);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Weight pack.  fold_T: T = view_fc[:, :256] * latent_fc[:, :256] (128x256, fp64) and
+// u[b] = latent_fc[:, 256:] * latent[idx_b] + latent_fc.bias (256, fp64).
+__global__ void fold_T_kernel(nb_decoder_weights w, double* __restrict__ T, double* __restrict__ u) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < kColor * kHidden) {
+        const int n = idx / kHidden, k = idx % kHidden;
+        double acc = 0.0;
+        for (int j = 0; j < kHidden; ++j) acc += (double)w.view_w[n * 346 + j] * (double)w.latent_w[j * 384 + k];
+        T[idx] = acc;
+    } else if (idx < kColor * kHidden + w.batch * kHidden) {
+        const int r = idx - kColor * kHidden;
+        const int b = r / kHidden, j = r % kHidden;
+        long long li = w.latent_index[b];
+        if (li < 0) li = 0;
+        if (li >= w.num_train_frame) li = w.num_train_frame - 1;
+        double acc = (double)w.latent_b[j];
+        for (int i = 0; i < 128; ++i) acc += (double)w.latent_w[j * 384 + 256 + i] * (double)w.latent[li * 128 + i];
+        u[r] = acc;
+    }
+}
+
+// Wc = T * feature_fc.W (128x256); bc[b] = T feature_fc.b + view_fc[:, :256] u[b] + view_fc.b
+__global__ void fold_Wc_kernel(nb_decoder_weights w, const double* __restrict__ T, const double* __restrict__ u,
+                               float* __restrict__ f32, __half* __restrict__ f16, float* __restrict__ bc) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < kColor * kHidden) {
+        const int n = idx / kHidden, k = idx % kHidden;
+        double acc = 0.0;
+        for (int j = 0; j < kHidden; ++j) acc += T[n * kHidden + j] * (double)w.feature_w[j * kHidden + k];
+        const float v = (float)acc;
+        f32[oWct + (size_t)k * kColor + n] = v;
+        f16[hW3 + umma_kmajor_offset(n, k, kColor)] = __float2half_rn(v);
+    } else if (idx < kColor * kHidden + w.batch * kColor) {
+        const int r = idx - kColor * kHidden;
+        const int b = r / kColor, n = r % kColor;
+        double acc = (double)w.view_b[n];
+        for (int j = 0; j < kHidden; ++j)
+            acc += T[n * kHidden + j] * (double)w.feature_b[j] + (double)w.view_w[n * 346 + j] * u[b * kHidden + j];
+        bc[r] = (float)acc;
+    }
+}
+
+// Everything that is a plain copy / transpose / fp16 re-layout.
+__global__ void relayout_kernel(nb_decoder_weights w, float* __restrict__ f32, __half* __restrict__ f16) {
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int i = t0; i < kHidden * kFeat; i += stride) {          // fc_0 (256,352)
+        const int n = i / kFeat, k = i % kFeat;
+        const float v = w.fc0_w[i];
+        f32[oW0t + (size_t)k * kHidden + n] = v;
+        f16[hW0 + umma_kmajor_offset(n, k, kHidden)] = __float2half_rn(v);
+    }
+    for (int i = t0; i < kHidden * kHidden; i += stride) {        // fc_1, fc_2 (256,256)
+        const int n = i / kHidden, k = i % kHidden;
+        const float v1 = w.fc1_w[i], v2 = w.fc2_w[i];
+        f32[oW1t + (size_t)k * kHidden + n] = v1;
+        f32[oW2t + (size_t)k * kHidden + n] = v2;
+        f16[hW1 + umma_kmajor_offset(n, k, kHidden)] = __float2half_rn(v1);
+        f16[hW2 + umma_kmajor_offset(n, k, kHidden)] = __float2half_rn(v2);
+    }
+    for (int i = t0; i < kHidden; i += stride) {
+        f32[oB0 + i] = w.fc0_b[i]; f32[oB1 + i] = w.fc1_b[i]; f32[oB2 + i] = w.fc2_b[i];
+        f32[oAlphaW + i] = w.alpha_w[i];
+    }
+    if (t0 == 0) { f32[oAlphaB] = w.alpha_b[0]; f32[oAlphaB + 1] = 0.f; f32[oAlphaB + 2] = 0.f; f32[oAlphaB + 3] = 0.f; }
+    for (int i = t0; i < kColor * 64; i += stride) {              // Wx = view_fc[:, 283:346] (+ zero pad row 319)
+        const int n = i / 64, j = i % 64;
+        const float v = (j < kXyzPE) ? w.view_w[n * 346 + 283 + j] : 0.f;
+        f32[oWct + (size_t)(kHidden + j) * kColor + n] = v;
+        f16[hW3 + umma_kmajor_offset(n, kHidden + j, kColor)] = __float2half_rn(v);
+    }
+    for (int i = t0; i < kColor * 28; i += stride) {              // Wv = view_fc[:, 256:283]
+        const int n = i / 28, j = i % 28;
+        f32[oWvt + (size_t)j * kColor + n] = (j < kViewPE) ? w.view_w[n * 346 + 256 + j] : 0.f;
+    }
+    for (int i = t0; i < 3 * kColor; i += stride) f32[oRgbW + i] = w.rgb_w[i];
+    if (t0 < 4) f32[oRgbB + t0] = (t0 < 3) ? w.rgb_b[t0] : 0.f;
+}
+
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" {
+
+int nb_abi_version(void) { return NB_ABI_VERSION; }
+const char* nb_last_error(void) { return g_err; }
+int nb_has_precision(int precision) {
+    if (precision == NB_PRECISION_FP32) return 1;
+    if (precision == NB_PRECISION_TC_FP16) return tc_available() ? 1 : 0;
+    return 0;
+}
+
+static size_t dtype_size(int dtype) { return dtype == NB_DTYPE_F16 ? 2 : 4; }
+
+size_t nb_packed_volume_level_offset(const int dims[NB_NUM_LEVELS][4], int batch, int dtype, int level) {
+    size_t off = 0;
+    for (int l = 0; l < level && l < NB_NUM_LEVELS; ++l)
+        off += align256((size_t)batch * dims[l][0] * dims[l][1] * dims[l][2] * dims[l][3] * dtype_size(dtype));
+    return off;
+}
+
+size_t nb_packed_volume_bytes(const int dims[NB_NUM_LEVELS][4], int batch, int dtype) {
+    return nb_packed_volume_level_offset(dims, batch, dtype, NB_NUM_LEVELS);
+}
+
+int nb_pack_volume(const nb_volume_level levels[NB_NUM_LEVELS], int batch, int dtype, void* out_blob, size_t out_bytes,
+                   void* stream) {
+    if (!levels || !out_blob || batch <= 0) { set_error("nb_pack_volume: null argument or batch <= 0"); return NB_ERR_BAD_ARG; }
+    if (dtype != NB_DTYPE_F32 && dtype != NB_DTYPE_F16) { set_error("nb_pack_volume: unknown dtype %d", dtype); return NB_ERR_BAD_ARG; }
+    int dims[NB_NUM_LEVELS][4];
+    for (int l = 0; l < NB_NUM_LEVELS; ++l) {
+        if (!levels[l].data || levels[l].C <= 0 || levels[l].C % 8 || levels[l].D <= 0 || levels[l].H <= 0 || levels[l].W <= 0) {
+            set_error("nb_pack_volume: level %d has a null pointer or bad dims (C must be a multiple of 8)", l);
+            return NB_ERR_BAD_ARG;
+        }
+        dims[l][0] = levels[l].C; dims[l][1] = levels[l].D; dims[l][2] = levels[l].H; dims[l][3] = levels[l].W;
+    }
+    if (out_bytes < nb_packed_volume_bytes(dims, batch, dtype)) { set_error("nb_pack_volume: out_bytes too small"); return NB_ERR_BAD_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 0; l < NB_NUM_LEVELS; ++l) {
+        const size_t nvox = (size_t)levels[l].D * levels[l].H * levels[l].W;
+        const size_t tiles = ((nvox + 31) / 32) * ((levels[l].C + 31) / 32) * batch;
+        const int grid = (int)(tiles < 148 * 16 ? tiles : 148 * 16);
+        char* dst = (char*)out_blob + nb_packed_volume_level_offset(dims, batch, dtype, l);
+        if (dtype == NB_DTYPE_F16)
+            pack_volume_kernel<__half><<<grid, 256, 0, st>>>(levels[l].data, (__half*)dst, levels[l].C, nvox, batch);
+        else
+            pack_volume_kernel<float><<<grid, 256, 0, st>>>(levels[l].data, (float*)dst, levels[l].C, nvox, batch);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("nb_pack_volume: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
+    return NB_OK;
+}
+
+size_t nb_packed_weights_bytes(int batch) { return packed_weights_bytes(batch < 1 ? 1 : batch); }
+
+int nb_pack_weights(const nb_decoder_weights* w, void* out_blob, size_t out_bytes, void* stream) {
+    if (!w || !out_blob) { set_error("nb_pack_weights: null argument"); return NB_ERR_BAD_ARG; }
+    const void* ptrs[] = {w->fc0_w, w->fc0_b, w->fc1_w, w->fc1_b, w->fc2_w, w->fc2_b, w->alpha_w, w->alpha_b, w->feature_w,
+                          w->feature_b, w->latent_w, w->latent_b, w->view_w, w->view_b, w->rgb_w, w->rgb_b, w->latent,
+                          w->latent_index};
+    for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); ++i)
+        if (!ptrs[i]) { set_error("nb_pack_weights: weight pointer #%zu is null", i); return NB_ERR_BAD_ARG; }
+    if (w->batch <= 0 || w->num_train_frame <= 0) { set_error("nb_pack_weights: batch / num_train_frame must be > 0"); return NB_ERR_BAD_ARG; }
+    if (out_bytes < packed_weights_bytes(w->batch)) { set_error("nb_pack_weights: out_bytes too small"); return NB_ERR_BAD_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = (char*)out_blob;
+    float* f32 = (float*)base;
+    __half* f16 = (__half*)(base + kF16ByteOffset);
+    double* T = (double*)(base + kScratchByteOffset);
+    float* bc = (float*)(base + kBcByteOffset);
+    double* u = (double*)(base + u_byte_offset(w->batch));
+    const int n1 = kColor * kHidden + w->batch * kHidden;
+    fold_T_kernel<<<(n1 + 127) / 128, 128, 0, st>>>(*w, T, u);
+    const int n2 = kColor * kHidden + w->batch * kColor;
+    fold_Wc_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(*w, T, u, f32, f16, bc);
+    relayout_kernel<<<148, 256, 0, st>>>(*w, f32, f16);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("nb_pack_weights: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
+    return NB_OK;
+}
+
+int nb_render_fwd_launches(int precision) { (void)precision; return 1; }
+
+int nb_render_fwd(const nb_render_args* a, void* stream) {
+    if (!a) { set_error("nb_render_fwd: null args"); return NB_ERR_BAD_ARG; }
+    if (a->batch <= 0 || a->n_rays < 0 || a->n_samples <= 0) { set_error("nb_render_fwd: bad batch/n_rays/n_samples"); return NB_ERR_BAD_ARG; }
+    if (a->n_rays == 0) return NB_OK;
+    if (!a->ray_o || !a->ray_d || !a->near || !a->far || !a->R || !a->Th || !a->bounds || !a->volume_blob || !a->weights_blob ||
+        !a->rgb_map || !a->disp_map || !a->acc_map || !a->depth_map) {
+        set_error("nb_render_fwd: a required device pointer is null");
+        return NB_ERR_BAD_ARG;
+    }
+    if (a->volume_dtype != NB_DTYPE_F32 && a->volume_dtype != NB_DTYPE_F16) { set_error("nb_render_fwd: bad volume_dtype"); return NB_ERR_BAD_ARG; }
+    static const int expectC[4] = {32, 64, 128, 128};
+    for (int l = 0; l < NB_NUM_LEVELS; ++l) {
+        if (a->level_dims[l][0] != expectC[l]) {
+            set_error("nb_render_fwd: level %d has %d channels, decoder expects %d (fc_0 is 352-wide)", l, a->level_dims[l][0], expectC[l]);
+            return NB_ERR_UNSUPPORTED;
+        }
+        if (a->level_dims[l][1] <= 0 || a->level_dims[l][2] <= 0 || a->level_dims[l][3] <= 0) { set_error("nb_render_fwd: bad level dims"); return NB_ERR_BAD_ARG; }
+    }
+    for (int i = 0; i < 3; ++i)
+        if (!(a->voxel_size[i] > 0.f) || a->out_sh[i] <= 0) { set_error("nb_render_fwd: voxel_size/out_sh must be > 0"); return NB_ERR_BAD_ARG; }
+
+    RenderParams p;
+    p.batch = a->batch; p.n_rays = a->n_rays; p.n_samples = a->n_samples;
+    p.ray_o = a->ray_o; p.ray_d = a->ray_d; p.near = a->near; p.far = a->far; p.t_vals = a->t_vals; p.t_rand = a->t_rand;
+    p.R = a->R; p.Th = a->Th; p.bounds = a->bounds;
+    for (int i = 0; i < 3; ++i) { p.voxel_size[i] = a->voxel_size[i]; p.inv_voxel[i] = 1.f / a->voxel_size[i]; p.out_sh[i] = (float)a->out_sh[i]; }
+    for (int l = 0; l < NB_NUM_LEVELS; ++l) {
+        p.lvl_C[l] = a->level_dims[l][0]; p.lvl_D[l] = a->level_dims[l][1]; p.lvl_H[l] = a->level_dims[l][2]; p.lvl_W[l] = a->level_dims[l][3];
+        p.lvl_off[l] = nb_packed_volume_level_offset(a->level_dims, a->batch, a->volume_dtype, l);
+        p.lvl_bstride[l] = (size_t)p.lvl_C[l] * p.lvl_D[l] * p.lvl_H[l] * p.lvl_W[l];
+    }
+    p.volume = a->volume_blob;
+    const char* wb = (const char*)a->weights_blob;
+    p.wf32 = (const float*)wb;
+    p.wf16 = (const __half*)(wb + kF16ByteOffset);
+    p.bc = (const float*)(wb + kBcByteOffset);
+    p.white_bkgd = a->white_bkgd;
+    p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw;
+    p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    if (a->precision == NB_PRECISION_FP32) return launch_render_f32(p, a->volume_dtype, st);
+    if (a->precision == NB_PRECISION_TC_FP16) return launch_render_tc(p, a->volume_dtype, st);
+    set_error("nb_render_fwd: unknown precision %d", a->precision);
+    return NB_ERR_BAD_ARG;
+}
+
+}  // extern "C"

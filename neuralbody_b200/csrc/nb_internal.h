@@ -1,0 +1,40 @@
+// Internal declarations shared by the translation units of libneuralbody_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include "../../include/neuralbody_b200.h"
+#include "nb_layout.h"
+
+namespace nb {
+
+void set_error(const char* fmt, ...);
+
+// Kernel-side view of one nb_render_fwd call (passed by value as a __grid_constant__).
+struct RenderParams {
+    int batch, n_rays, n_samples;
+    const float *ray_o, *ray_d, *near, *far, *t_vals, *t_rand;
+    const float *R, *Th, *bounds;
+    float inv_voxel[3];        // not used for parity-critical math (we divide, as upstream does)
+    float voxel_size[3];       // dhw
+    float out_sh[3];           // dhw, as float (upstream: torch.tensor(out_sh).to(dhw))
+    int   lvl_C[4], lvl_D[4], lvl_H[4], lvl_W[4];
+    size_t lvl_off[4];         // byte offset of level l inside the volume blob
+    size_t lvl_bstride[4];     // ELEMENT stride between frames of level l
+    const void* volume;
+    const float* wf32;         // fp32 weight section
+    const __half* wf16;        // fp16 tcgen05-canonical section
+    const float* bc;           // [B][128]
+    int white_bkgd;
+    float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *raw;
+    int rays_per_group;        // rays handled together by one CTA work item
+    int tiles_per_group;       // point tiles per group
+    int n_groups;              // total work items = batch * ceil(n_rays / rays_per_group)
+    int groups_per_frame;
+};
+
+int launch_render_f32(const RenderParams& p, int volume_dtype, cudaStream_t stream);
+int launch_render_tc(const RenderParams& p, int volume_dtype, cudaStream_t stream);
+bool tc_available();
+
+}  // namespace nb

@@ -1,0 +1,273 @@
+"""Drop-in for the reference's Neural Body renderer.
+
+Replaces lib/networks/renderer/if_clight_renderer.py (the file every Neural Body config
+selects through `renderer_module/renderer_path`; BASELINE.json calls it
+if_nerf_renderer.py): same class name, constructor and `render(batch)` contract
+(:94-122), same five output keys/shapes/dtypes (:84-92), same config keys read inside
+(`N_samples, perturb, raw_noise_std, white_bkgd` :13,16,82; `voxel_size`
+latent_xyzc.py:54).  The body of the per-chunk loop -- get_sampling_points ->
+get_density_color -> Network.calculate_density_color -> raw2outputs -- is ONE fused
+CUDA launch through the C ABI (include/neuralbody_b200.h); no PyTorch op runs inside
+the ray loop and there is no CPU/eager fallback.
+"""
+import ctypes as C
+
+import torch
+
+from neuralbody_b200 import capi
+from neuralbody_b200.lib.config import get_active_cfg
+
+_PRECISIONS = {"fp32": capi.NB_PRECISION_FP32, "tc_fp16": capi.NB_PRECISION_TC_FP16}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _f32c(t, device):
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class Renderer:
+    def __init__(self, net):
+        self.net = net
+        self.lib = capi.load()
+        self._vol_key = None
+        self._vol_blob = None
+        self._vol_dims = None
+        self._vol_dtype = None
+        self._w_key = None
+        self._w_blob = None
+        self._tvals = {}
+        self.launches = 0          # render kernels enqueued so far (bench accounting)
+
+    # ------------------------------------------------------------------ options
+    def _opt(self, name, default):
+        cfg = get_active_cfg()
+        return cfg[name] if name in cfg else default
+
+    def _precision(self):
+        name = str(self._opt("render_precision", "tc_fp16"))
+        if name not in _PRECISIONS:
+            raise ValueError("cfg.render_precision must be one of %s" % sorted(_PRECISIONS))
+        return _PRECISIONS[name]
+
+    def _volume_dtype(self, precision):
+        name = str(self._opt("render_volume_dtype", "auto"))
+        if name == "auto":
+            return capi.NB_DTYPE_F32 if precision == capi.NB_PRECISION_FP32 else capi.NB_DTYPE_F16
+        return {"fp32": capi.NB_DTYPE_F32, "fp16": capi.NB_DTYPE_F16}[name]
+
+    # ------------------------------------------------------------------ a2 (host API parity)
+    def get_sampling_points(self, ray_o, ray_d, near, far, t_rand=None):
+        """if_clight_renderer.py:11-27, kept callable for subclasses.  `render` does not call
+        this: the fused kernel generates the same samples in registers."""
+        cfg = get_active_cfg()
+        t_vals = torch.linspace(0., 1., steps=cfg.N_samples).to(near)
+        z_vals = near[..., None] * (1. - t_vals) + far[..., None] * t_vals
+        if cfg.perturb > 0. and self.net.training:
+            mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+            upper = torch.cat([mids, z_vals[..., -1:]], -1)
+            lower = torch.cat([z_vals[..., :1], mids], -1)
+            if t_rand is None:
+                t_rand = torch.rand(z_vals.shape)
+            z_vals = lower + (upper - lower) * t_rand.to(upper)
+        pts = ray_o[:, :, None] + ray_d[:, :, None] * z_vals[..., None]
+        return pts, z_vals
+
+    # ------------------------------------------------------------------ a3
+    def prepare_sp_input(self, batch):
+        """if_clight_renderer.py:29-52, unchanged semantics (stays Python; `.tolist()` is the
+        one host sync per frame, exactly as upstream)."""
+        sp_input = {}
+        sh = batch['coord'].shape
+        idx = [torch.full([sh[1]], i) for i in range(sh[0])]
+        idx = torch.cat(idx).to(batch['coord'])
+        coord = batch['coord'].view(-1, sh[-1])
+        sp_input['coord'] = torch.cat([idx[:, None], coord], dim=1)
+        out_sh, _ = torch.max(batch['out_sh'], dim=0)
+        sp_input['out_sh'] = out_sh.tolist()
+        sp_input['batch_size'] = sh[0]
+        sp_input['bounds'] = batch['bounds']
+        sp_input['R'] = batch['R']
+        sp_input['Th'] = batch['Th']
+        sp_input['latent_index'] = batch['latent_index']
+        return sp_input
+
+    def get_density_color(self, wpts, viewdir, raw_decoder):
+        """if_clight_renderer.py:54-60 (host API parity for subclasses that pass their own decoder)."""
+        n_batch, n_pixel, n_sample = wpts.shape[:3]
+        wpts = wpts.view(n_batch, n_pixel * n_sample, -1)
+        viewdir = viewdir[:, :, None].repeat(1, 1, n_sample, 1).contiguous()
+        viewdir = viewdir.view(n_batch, n_pixel * n_sample, -1)
+        return raw_decoder(wpts, viewdir)
+
+    # ------------------------------------------------------------------ once-per-frame packs
+    def pack_volume(self, feature_volume, dtype):
+        """NCDHW fp32 volumes -> channels-last blob (nb_pack_volume); cached until the tensors change."""
+        key = (dtype,) + tuple((v.data_ptr(), tuple(v.shape), v._version) for v in feature_volume)
+        if key == self._vol_key:
+            return self._vol_blob, self._vol_dims
+        if len(feature_volume) != capi.NB_NUM_LEVELS:
+            raise ValueError("expected %d feature volumes" % capi.NB_NUM_LEVELS)
+        dev = feature_volume[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("feature volumes must live on a CUDA device (no CPU render path)")
+        B = feature_volume[0].shape[0]
+        dims = capi.LevelDims()
+        levels = (capi.nb_volume_level * capi.NB_NUM_LEVELS)()
+        keep = []
+        for l, v in enumerate(feature_volume):
+            v = v.detach()
+            if v.dtype != torch.float32 or not v.is_contiguous():
+                v = v.float().contiguous()
+            keep.append(v)
+            _, c, d, h, w = v.shape
+            dims[l][0], dims[l][1], dims[l][2], dims[l][3] = c, d, h, w
+            levels[l].data = v.data_ptr()
+            levels[l].C, levels[l].D, levels[l].H, levels[l].W = c, d, h, w
+        nbytes = self.lib.nb_packed_volume_bytes(dims, B, dtype)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        capi.check(self.lib.nb_pack_volume(levels, B, dtype, blob.data_ptr(), nbytes, C.c_void_p(stream)),
+                   "nb_pack_volume")
+        self._vol_key, self._vol_blob, self._vol_dims, self._vol_dtype = key, blob, dims, dtype
+        return blob, dims
+
+    def pack_weights(self, latent_index, device):
+        """Fold + re-lay-out the decoder (nb_pack_weights); cached on parameter versions."""
+        tensors = self.net.decoder_tensors()
+        key = tuple((t.data_ptr(), t._version) for t in tensors) + (latent_index.data_ptr(), latent_index._version,
+                                                                    tuple(latent_index.shape))
+        if key == self._w_key:
+            return self._w_blob
+        B = int(latent_index.shape[0])
+        w = capi.nb_decoder_weights()
+        names = [f[0] for f in capi.nb_decoder_weights._fields_][:17]
+        keep = []
+        for name, t in zip(names, tensors):
+            t = t.detach()
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            setattr(w, name, t.data_ptr())
+        li = latent_index.to(device=device, dtype=torch.int64).contiguous()
+        w.latent_index = li.data_ptr()
+        w.num_train_frame = int(self.net.latent.weight.shape[0])
+        w.batch = B
+        nbytes = self.lib.nb_packed_weights_bytes(B)
+        blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        capi.check(self.lib.nb_pack_weights(C.byref(w), blob.data_ptr(), nbytes, C.c_void_p(stream)), "nb_pack_weights")
+        self._w_key, self._w_blob = key, blob
+        return blob
+
+    def _t_vals(self, S, device):
+        k = (S, str(device))
+        if k not in self._tvals:
+            # upstream: torch.linspace(0., 1., steps=cfg.N_samples).to(near)  -- computed on the CPU, then moved
+            self._tvals[k] = torch.linspace(0., 1., steps=S).to(device)
+        return self._tvals[k]
+
+    def _draw_t_rand(self, B, n, S, device):
+        """The jitter draw of if_clight_renderer.py:22 (`torch.rand(z_vals.shape).to(upper)`, CPU
+        generator), issued per 2048-ray chunk like upstream so the RNG stream is identical."""
+        parts = [torch.rand((B, min(2048, n - i), S)) for i in range(0, n, 2048)]
+        return torch.cat(parts, dim=1).to(device).contiguous()
+
+    # ------------------------------------------------------------------ fused launch
+    def render_rays(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, want_raw=False,
+                    out=None):
+        """One nb_render_fwd launch for (B,n) rays.  Returns the dict of get_pixel_value."""
+        cfg = get_active_cfg()
+        if float(cfg.raw_noise_std) > 0.:
+            # upstream's branch draws CPU randn and would crash on GPU tensors (nerf_net_utils.py:33)
+            raise NotImplementedError("raw_noise_std > 0 is not supported (it is 0 in every reference config)")
+        dev = ray_o.device
+        if dev.type != "cuda":
+            raise RuntimeError("Renderer.render needs CUDA tensors: the render path has no CPU implementation")
+        B, n = int(ray_o.shape[0]), int(ray_o.shape[1])
+        S = int(cfg.N_samples)
+        precision = self._precision()
+        vdtype = self._volume_dtype(precision)
+        with torch.cuda.device(dev):
+            vol_blob, dims = self.pack_volume(feature_volume, vdtype)
+            w_blob = self.pack_weights(sp_input['latent_index'], dev)
+            if t_rand is None and float(cfg.perturb) > 0. and self.net.training:
+                t_rand = self._draw_t_rand(B, n, S, dev)
+            ray_o, ray_d = _f32c(ray_o, dev), _f32c(ray_d, dev)
+            near, far = _f32c(near, dev), _f32c(far, dev)
+            R = _f32c(sp_input['R'], dev)
+            Th = _f32c(sp_input['Th'], dev).reshape(B, 3)           # (B,1,3) multi-view / (B,3) monocular
+            bounds = _f32c(sp_input['bounds'], dev)
+            t_vals = self._t_vals(S, dev)
+            if t_rand is not None:
+                t_rand = _f32c(t_rand, dev)
+                assert tuple(t_rand.shape) == (B, n, S)
+            if out is None:
+                out = {
+                    'rgb_map': torch.empty((B, n, 3), dtype=torch.float32, device=dev),
+                    'disp_map': torch.empty((B, n), dtype=torch.float32, device=dev),
+                    'acc_map': torch.empty((B, n), dtype=torch.float32, device=dev),
+                    'depth_map': torch.empty((B, n), dtype=torch.float32, device=dev),
+                }
+                if bool(self._opt("render_return_weights", True)):
+                    out['weights'] = torch.empty((B, n, S), dtype=torch.float32, device=dev)
+            raw = torch.empty((B, n, S, 4), dtype=torch.float32, device=dev) if want_raw else None
+
+            a = capi.nb_render_args()
+            a.batch, a.n_rays, a.n_samples = B, n, S
+            a.ray_o, a.ray_d, a.near, a.far = ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(), far.data_ptr()
+            a.t_vals = t_vals.data_ptr()
+            a.t_rand = t_rand.data_ptr() if t_rand is not None else None
+            a.R, a.Th, a.bounds = R.data_ptr(), Th.data_ptr(), bounds.data_ptr()
+            vs = list(cfg.voxel_size)
+            for i in range(3):
+                a.voxel_size[i] = float(vs[i])
+                a.out_sh[i] = int(sp_input['out_sh'][i])
+            for l in range(capi.NB_NUM_LEVELS):
+                for j in range(4):
+                    a.level_dims[l][j] = dims[l][j]
+            a.volume_blob, a.volume_dtype = vol_blob.data_ptr(), vdtype
+            a.weights_blob = w_blob.data_ptr()
+            a.white_bkgd = 1 if bool(cfg.white_bkgd) else 0
+            a.precision = precision
+            a.rgb_map, a.disp_map = out['rgb_map'].data_ptr(), out['disp_map'].data_ptr()
+            a.acc_map, a.depth_map = out['acc_map'].data_ptr(), out['depth_map'].data_ptr()
+            a.weights = out['weights'].data_ptr() if 'weights' in out else None
+            a.raw = raw.data_ptr() if raw is not None else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            capi.check(self.lib.nb_render_fwd(C.byref(a), C.c_void_p(stream)), "nb_render_fwd")
+            self.launches += self.lib.nb_render_fwd_launches(precision)
+        if raw is not None:
+            out = dict(out)
+            out['raw'] = raw
+        return out
+
+    def get_pixel_value(self, ray_o, ray_d, near, far, feature_volume, sp_input, batch):
+        """if_clight_renderer.py:62-92: same signature, same returned dict."""
+        return self.render_rays(ray_o, ray_d, near, far, feature_volume, sp_input)
+
+    # ------------------------------------------------------------------ a1
+    def render(self, batch):
+        """if_clight_renderer.py:94-122.  `cfg.chunk` rays per launch (0 = everything in one
+        launch; upstream hard-codes 2048 to bound activation memory, which the fused kernel
+        never materialises)."""
+        ray_o = batch['ray_o']
+        ray_d = batch['ray_d']
+        near = batch['near']
+        far = batch['far']
+
+        sp_input = self.prepare_sp_input(batch)
+        feature_volume = self.net.encode_sparse_voxels(sp_input)
+
+        n_pixel = ray_o.shape[1]
+        chunk = int(self._opt("chunk", 0)) or n_pixel
+        if chunk >= n_pixel:
+            return self.get_pixel_value(ray_o, ray_d, near, far, feature_volume, sp_input, batch)
+        ret_list = []
+        for i in range(0, n_pixel, chunk):
+            ret_list.append(self.get_pixel_value(ray_o[:, i:i + chunk], ray_d[:, i:i + chunk], near[:, i:i + chunk],
+                                                 far[:, i:i + chunk], feature_volume, sp_input, batch))
+        keys = ret_list[0].keys()
+        return {k: torch.cat([r[k] for r in ret_list], dim=1) for k in keys}

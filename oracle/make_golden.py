@@ -1,0 +1,39 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (oracle/ref_harness.py)
+on the seeded synthetic cases of oracle/golden_cases.py.  Run in the build container:
+
+    python -m oracle.make_golden
+
+Each file holds the reference's five outputs (fp32) plus a sha256 of every input tensor, so a
+consumer on another machine can prove it rebuilt the identical inputs from the seeds.
+TEST INFRASTRUCTURE ONLY."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from neuralbody_b200 import synth
+    from oracle import ref_harness, golden_cases
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name in golden_cases.CASES:
+        scene, rkw = golden_cases.build_case(name)
+        ret = ref_harness.reference_render(scene, **rkw)
+        arrays = {k: v.numpy().astype(np.float32) for k, v in ret.items()}
+        arrays["input_sha256"] = np.frombuffer(synth.scene_checksum(scene).encode(), dtype=np.uint8)
+        arrays["torch_version"] = np.frombuffer(torch.__version__.encode(), dtype=np.uint8)
+        path = os.path.join(out_dir, name + ".npz")
+        np.savez_compressed(path, **arrays)
+        acc = ret["acc_map"]
+        print("%-22s rays=%-5d acc.mean=%.3f nan_disp=%d -> %s (%d KB)" % (
+            name, acc.numel(), float(acc.mean()), int(torch.isnan(ret["disp_map"]).sum()), path,
+            os.path.getsize(path) // 1024))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,172 @@
+"""ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+CPU fp32 restatement of neuralbody's volumetric-render hot path, function by
+function, each citing the reference file:line it follows (paths relative to the
+reference tree, commit 3c516b9).  Only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / `--impl reference` leg may import this module; the
+product path (neuralbody_b200/) never does and fails loudly without its CUDA
+library.
+
+Parity pinning: the reference ships no tests or golden vectors.
+This restatement is pinned instead against outputs of the UNMODIFIED reference
+executed in the build container (oracle/ref_harness.py) on the seeded synthetic
+scenes of neuralbody_b200/synth.py; the vectors are committed under tests/golden/
+together with the generating script oracle/make_golden.py, and
+tests/test_oracle.py re-checks the restatement against them on every run.
+
+Torch is used as the array library (F.grid_sample / conv1d are the third-party
+arithmetic the reference itself calls); nothing here touches CUDA.
+"""
+import torch
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------ a2 sampling
+def get_sampling_points(ray_o, ray_d, near, far, n_samples, perturb=0.0, training=False, t_rand=None):
+    """lib/networks/renderer/if_clight_renderer.py:11-27.
+    ray_o/ray_d (B,n,3), near/far (B,n) -> pts (B,n,S,3), z_vals (B,n,S).
+    `t_rand` stands for the `torch.rand(z_vals.shape)` draw at :22."""
+    t_vals = torch.linspace(0., 1., steps=n_samples).to(near)
+    z_vals = near[..., None] * (1. - t_vals) + far[..., None] * t_vals
+    if perturb > 0. and training:
+        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], -1)
+        lower = torch.cat([z_vals[..., :1], mids], -1)
+        if t_rand is None:
+            t_rand = torch.rand(z_vals.shape)
+        z_vals = lower + (upper - lower) * t_rand.to(upper)
+    pts = ray_o[:, :, None] + ray_d[:, :, None] * z_vals[..., None]
+    return pts, z_vals
+
+
+# ------------------------------------------------------------------ a5 / a6 / a7
+def pts_to_can_pts(pts, R, Th):
+    """lib/networks/latent_xyzc.py:41-47: (p - Th) @ R.  Th is (B,1,3) or (B,3)."""
+    Th = Th.reshape(Th.shape[0], 1, 3)
+    return torch.matmul(pts - Th, R)
+
+
+def get_grid_coords(pts, bounds, out_sh, voxel_size):
+    """lib/networks/latent_xyzc.py:49-60 (divides by out_sh, not out_sh-1; xyz order out)."""
+    dhw = pts[..., [2, 1, 0]]
+    min_dhw = bounds[:, 0, [2, 1, 0]]
+    dhw = dhw - min_dhw[:, None]
+    dhw = dhw / torch.tensor(voxel_size).to(dhw)
+    out_sh = torch.tensor(out_sh).to(dhw)
+    dhw = dhw / out_sh * 2 - 1
+    return dhw[..., [2, 1, 0]]
+
+
+def interpolate_features(grid_coords, feature_volume):
+    """lib/networks/latent_xyzc.py:62-72: 4x trilinear grid_sample, zeros padding,
+    align_corners=True; channel order [L1:32, L2:64, L3:128, L4:128] -> (B,352,P)."""
+    g = grid_coords[:, None, None]
+    feats = [F.grid_sample(v, g, padding_mode='zeros', align_corners=True) for v in feature_volume]
+    feats = torch.cat(feats, dim=1)
+    return feats.view(feats.size(0), -1, feats.size(4))
+
+
+# ------------------------------------------------------------------ a9 embedder
+def positional_embed(x, multires):
+    """lib/networks/embedder.py:5-50: [x, sin(2^0 x), cos(2^0 x), ..., sin(2^(L-1) x), cos(2^(L-1) x)]."""
+    freq_bands = 2. ** torch.linspace(0., multires - 1, steps=multires)
+    out = [x]
+    for freq in freq_bands:
+        out.append(torch.sin(x * freq))
+        out.append(torch.cos(x * freq))
+    return torch.cat(out, -1)
+
+
+# ------------------------------------------------------------------ a8 decoder
+def _conv(w, name, x):
+    return F.conv1d(x, w[name + ".weight"], w[name + ".bias"])
+
+
+def calculate_density_color(w, wpts, viewdir, feature_volume, sp_input, voxel_size, xyz_res=10, view_res=4):
+    """lib/networks/latent_xyzc.py:91-126. wpts, viewdir (B,P,3) -> raw (B,P,4) = (rgb logits, sigma)."""
+    ppts = pts_to_can_pts(wpts, sp_input['R'], sp_input['Th'])
+    grid_coords = get_grid_coords(ppts, sp_input['bounds'], sp_input['out_sh'], voxel_size)
+    xyzc_features = interpolate_features(grid_coords, feature_volume)
+
+    net = F.relu(_conv(w, "fc_0", xyzc_features))
+    net = F.relu(_conv(w, "fc_1", net))
+    net = F.relu(_conv(w, "fc_2", net))
+    alpha = _conv(w, "alpha_fc", net)
+
+    features = _conv(w, "feature_fc", net)
+    latent = w["latent.weight"][sp_input['latent_index']]
+    latent = latent[..., None].expand(*latent.shape, net.size(2))
+    features = torch.cat((features, latent), dim=1)
+    features = _conv(w, "latent_fc", features)
+
+    vd = positional_embed(viewdir, view_res).transpose(1, 2)
+    light_pts = positional_embed(wpts, xyz_res).transpose(1, 2)
+    features = torch.cat((features, vd, light_pts), dim=1)
+    net = F.relu(_conv(w, "view_fc", features))
+    rgb = _conv(w, "rgb_fc", net)
+    raw = torch.cat((rgb, alpha), dim=1)
+    return raw.transpose(1, 2)
+
+
+# ------------------------------------------------------------------ a10 composite
+def raw2outputs(raw, z_vals, rays_d, white_bkgd=False):
+    """lib/networks/renderer/nerf_net_utils.py:6-51 (raw_noise_std = 0 as in every config)."""
+    dists = z_vals[..., 1:] - z_vals[..., :-1]
+    dists = torch.cat([dists, torch.Tensor([1e10]).expand(dists[..., :1].shape).to(dists)], -1)
+    dists = dists * torch.norm(rays_d[..., None, :], dim=-1)
+    rgb = torch.sigmoid(raw[..., :3])
+    alpha = 1. - torch.exp(-F.relu(raw[..., 3]) * dists)
+    weights = alpha * torch.cumprod(
+        torch.cat([torch.ones((alpha.shape[0], 1)).to(alpha), 1. - alpha + 1e-10], -1), -1)[:, :-1]
+    rgb_map = torch.sum(weights[..., None] * rgb, -2)
+    depth_map = torch.sum(weights * z_vals, -1)
+    disp_map = 1. / torch.max(1e-10 * torch.ones_like(depth_map), depth_map / torch.sum(weights, -1))
+    acc_map = torch.sum(weights, -1)
+    if white_bkgd:
+        rgb_map = rgb_map + (1. - acc_map[..., None])
+    return rgb_map, disp_map, acc_map, weights, depth_map
+
+
+# ------------------------------------------------------------------ a3 / a4 / a1 driver
+def prepare_sp_input(batch):
+    """lib/networks/renderer/if_clight_renderer.py:29-52 (coord concat omitted: it only
+    feeds spconv, which stays on the reference path)."""
+    out_sh, _ = torch.max(batch['out_sh'], dim=0)
+    return {'out_sh': out_sh.tolist(), 'batch_size': batch['coord'].shape[0], 'bounds': batch['bounds'],
+            'R': batch['R'], 'Th': batch['Th'], 'latent_index': batch['latent_index']}
+
+
+def get_pixel_value(w, ray_o, ray_d, near, far, feature_volume, sp_input, voxel_size, n_samples,
+                    perturb=0.0, training=False, white_bkgd=False, t_rand=None):
+    """lib/networks/renderer/if_clight_renderer.py:62-92 (+ get_density_color :54-60)."""
+    wpts, z_vals = get_sampling_points(ray_o, ray_d, near, far, n_samples, perturb, training, t_rand)
+    viewdir = ray_d / torch.norm(ray_d, dim=2, keepdim=True)
+    n_batch, n_pixel, n_sample = wpts.shape[:3]
+    wpts_flat = wpts.view(n_batch, n_pixel * n_sample, -1)
+    vd = viewdir[:, :, None].repeat(1, 1, n_sample, 1).contiguous().view(n_batch, n_pixel * n_sample, -1)
+    raw = calculate_density_color(w, wpts_flat, vd, feature_volume, sp_input, voxel_size)
+    raw = raw.reshape(-1, n_sample, 4)
+    rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(
+        raw, z_vals.view(-1, n_sample), ray_d.reshape(-1, 3), white_bkgd)
+    return {'rgb_map': rgb_map.view(n_batch, n_pixel, -1), 'disp_map': disp_map.view(n_batch, n_pixel),
+            'acc_map': acc_map.view(n_batch, n_pixel), 'weights': weights.view(n_batch, n_pixel, -1),
+            'depth_map': depth_map.view(n_batch, n_pixel)}
+
+
+def render(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False, t_rand=None, chunk=2048,
+           max_rays=None):
+    """lib/networks/renderer/if_clight_renderer.py:94-122 with the dense volumes supplied
+    (scene['volumes']) in place of net.encode_sparse_voxels."""
+    ray_o, ray_d, near, far = scene['ray_o'], scene['ray_d'], scene['near'], scene['far']
+    if max_rays is not None:
+        ray_o, ray_d, near, far = ray_o[:, :max_rays], ray_d[:, :max_rays], near[:, :max_rays], far[:, :max_rays]
+    sp_input = prepare_sp_input(scene)
+    n_pixel = ray_o.shape[1]
+    ret_list = []
+    for i in range(0, n_pixel, chunk):
+        tr = None if t_rand is None else t_rand[:, i:i + chunk]
+        ret_list.append(get_pixel_value(
+            scene['weights'], ray_o[:, i:i + chunk], ray_d[:, i:i + chunk], near[:, i:i + chunk],
+            far[:, i:i + chunk], scene['volumes'], sp_input, scene['voxel_size'], n_samples,
+            perturb, training, white_bkgd, tr))
+    return {k: torch.cat([r[k] for r in ret_list], dim=1) for k in ret_list[0]}

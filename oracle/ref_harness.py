@@ -1,0 +1,148 @@
+"""TEST INFRASTRUCTURE ONLY -- imports the UNMODIFIED reference (zju3dv/neuralbody)
+from /root/reference so that the oracle restatement (oracle/neuralbody_oracle.py)
+can be pinned against it and golden vectors can be generated (oracle/make_golden.py).
+
+/root/reference only exists in the build container, never on the GPU box: nothing in
+`tests -m gpu`, `__graft_entry__.smoke()` or `bench.py` may import this module.
+
+Recipe: three module stubs make the render path importable
+on CPU without touching the reference sources:
+  * `open3d`  -- imported at lib/config/config.py:1, never used on the render path;
+  * `imp`     -- removed in Python 3.12; lib/networks/make_network.py:2 and
+                 lib/networks/renderer/make_renderer.py:2 use `imp.load_source`;
+  * `spconv`  -- lib/networks/latent_xyzc.py:2; the SparseConvNet is built but never
+                 run: the dense feature volumes are supplied by the caller.
+`lib.config` parses sys.argv and opens the yaml relative to CWD at import time
+(lib/config/config.py:176-187), hence the chdir/argv dance below.
+"""
+import importlib.machinery
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("NB_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "lib", "networks"))
+
+
+def _install_stubs():
+    import torch.nn as nn
+
+    if "open3d" not in sys.modules:
+        sys.modules["open3d"] = types.ModuleType("open3d")
+
+    if "imp" not in sys.modules:
+        imp = types.ModuleType("imp")
+
+        def load_source(name, path):
+            return importlib.machinery.SourceFileLoader(name, path).load_module()
+
+        imp.load_source = load_source
+        sys.modules["imp"] = imp
+
+    if "spconv" not in sys.modules:
+        sp = types.ModuleType("spconv")
+
+        class _Inert(nn.Module):
+            def __init__(self, *a, **k):
+                super().__init__()
+
+        class SparseSequential(nn.Sequential):
+            def __init__(self, *mods):
+                super().__init__(*[m for m in mods if isinstance(m, nn.Module)])
+
+        class SparseConvTensor:  # never constructed: volumes are supplied
+            def __init__(self, *a, **k):
+                raise RuntimeError("spconv is stubbed; supply dense volumes")
+
+        sp.SubMConv3d = _Inert
+        sp.SparseConv3d = _Inert
+        sp.SparseSequential = SparseSequential
+        sp.SparseConvTensor = SparseConvTensor
+        sys.modules["spconv"] = sp
+
+
+_loaded = None
+
+
+def load_reference(cfg_file="configs/snapshot_exp/snapshot_f3c.yaml"):
+    """Return (cfg, latent_xyzc module, if_clight_renderer module, nerf_net_utils module)."""
+    global _loaded
+    if _loaded is not None:
+        return _loaded
+    if not reference_available():
+        raise RuntimeError("reference tree not found at %s" % REFERENCE_ROOT)
+    _install_stubs()
+    old_cwd, old_argv = os.getcwd(), list(sys.argv)
+    os.chdir(REFERENCE_ROOT)
+    sys.argv = ["x", "--cfg_file", cfg_file]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        from lib.config import cfg  # noqa
+        from lib.networks import latent_xyzc  # noqa
+        from lib.networks.renderer import if_clight_renderer, nerf_net_utils  # noqa
+    finally:
+        os.chdir(old_cwd)
+        sys.argv = old_argv
+    _loaded = (cfg, latent_xyzc, if_clight_renderer, nerf_net_utils)
+    return _loaded
+
+
+def reference_render(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False,
+                     t_rand=None, chunk=2048, num_train_frame=None, grad=False):
+    """Run the reference renderer on a synthetic scene dict (neuralbody_b200.synth).
+
+    Follows Renderer.render (if_clight_renderer.py:94-122) literally, except that
+    net.encode_sparse_voxels (spconv) is replaced by the supplied dense volumes.
+    `t_rand` (B, n, S): when given, torch.rand is patched for the duration of the
+    call so the reference's own jitter line (if_clight_renderer.py:22) consumes
+    exactly these numbers, chunk by chunk.
+    """
+    import torch
+    cfg, latent_xyzc, if_clight_renderer, _ = load_reference()
+    cfg.N_samples = int(n_samples)
+    cfg.perturb = float(perturb)
+    cfg.white_bkgd = bool(white_bkgd)
+    cfg.raw_noise_std = 0
+    cfg.voxel_size = [float(v) for v in scene["voxel_size"]]
+    if num_train_frame is None:
+        num_train_frame = int(scene["weights"]["latent.weight"].shape[0])
+    cfg.num_train_frame = int(num_train_frame)
+
+    net = latent_xyzc.Network()
+    missing, unexpected = net.load_state_dict(scene["weights"], strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("xyzc_net") or k.startswith("c.") for k in missing), missing
+    net.train(training)
+    volumes = [v.clone().requires_grad_(grad) for v in scene["volumes"]]
+    net.encode_sparse_voxels = lambda sp_input: volumes
+    renderer = if_clight_renderer.Renderer(net)
+    batch = {k: scene[k] for k in ("coord", "out_sh", "bounds", "R", "Th", "latent_index",
+                                   "ray_o", "ray_d", "near", "far")}
+
+    state = {"ofs": 0}
+    real_rand = torch.rand
+
+    def fake_rand(shape, *a, **k):
+        # the reference draws (B, chunk, S) per chunk
+        b, n, s = tuple(shape)
+        out = t_rand[:, state["ofs"]:state["ofs"] + n, :].clone()
+        state["ofs"] += n
+        assert out.shape == (b, n, s)
+        return out
+
+    # the reference hard-codes chunk = 2048 (if_clight_renderer.py:107)
+    assert chunk == 2048
+    ctx = torch.enable_grad() if grad else torch.no_grad()
+    try:
+        if t_rand is not None:
+            torch.rand = fake_rand
+        with ctx:
+            ret = renderer.render(batch)
+    finally:
+        torch.rand = real_rand
+    if grad:
+        return ret, net, volumes
+    return {k: v.detach() for k, v in ret.items()}
