@@ -131,6 +131,15 @@ int nb_render_fwd(const nb_render_args* args, void* stream);
 /* number of kernels nb_render_fwd enqueues per call for the given precision (for launch accounting) */
 int nb_render_fwd_launches(int precision);
 
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics.  A two-layer tcgen05 micro-pipeline on one 128-row tile (see csrc/nb_tc_probe.cu):
+ * validates descriptor layouts, TMEM-resident activations and the bias-as-K-step trick in
+ * isolation.  a0: device fp16 [128][64] row-major; w0_packed: device fp16 128x80 in the packed
+ * K-major layout (columns 64/65 = bias hi/lo); w1_packed: 64x128 packed; d0_out fp32 [128][128];
+ * d1_out fp32 [128][64].  variant bit0 swaps the descriptor's LBO/SBO, bit1 the fp16 pair order. */
+int nb_debug_tc_probe(const void* a0, const void* w0_packed, const void* w1_packed, float* d0_out, float* d1_out,
+                      int variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ NB_NUM_LEVELS = 4
 
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
-           "nb_render_fwd_launches"]
+           "nb_render_fwd_launches", "nb_debug_tc_probe"]
 
 
 class nb_volume_level(C.Structure):
@@ -77,6 +77,8 @@ def load(path=None):
     lib.nb_render_fwd.argtypes = [C.POINTER(nb_render_args), C.c_void_p]
     lib.nb_render_fwd_launches.restype = C.c_int
     lib.nb_render_fwd_launches.argtypes = [C.c_int]
+    lib.nb_debug_tc_probe.restype = C.c_int
+    lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     if lib.nb_abi_version() != 1:
         raise RuntimeError("libneuralbody_b200.so ABI version mismatch")
     if path == _build.LIB_PATH:

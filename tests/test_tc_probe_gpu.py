@@ -1,0 +1,60 @@
+"""GPU: the tcgen05 building blocks in isolation (csrc/nb_tc_probe.cu) against fp32 matmuls of the
+same fp16-rounded operands.  Pins the descriptor / TMEM-operand conventions the fused kernel uses."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def pack_kmajor(w):
+    """(N,K) fp16 -> the packed K-major no-swizzle layout of csrc/nb_layout.h::umma_kmajor_offset."""
+    N, K = w.shape
+    out = torch.empty(N * K, dtype=w.dtype)
+    n = torch.arange(N)[:, None].expand(N, K)
+    k = torch.arange(K)[None, :].expand(N, K)
+    off = ((k // 8) * (N // 8) + n // 8) * 64 + (n % 8) * 8 + (k % 8)
+    out[off.reshape(-1)] = w.reshape(-1)
+    return out
+
+
+def run_probe(variant, seed=0):
+    from neuralbody_b200 import capi
+    lib = capi.load()
+    g = torch.Generator().manual_seed(seed)
+    a0 = (torch.randn((128, 64), generator=g)).half()
+    w0 = (torch.randn((128, 64), generator=g) * 0.2).half()
+    bias = torch.randn((128,), generator=g)
+    b_hi = bias.half()
+    b_lo = (bias - b_hi.float()).half()
+    w0p = torch.zeros((128, 80), dtype=torch.float16)
+    w0p[:, :64] = w0
+    w0p[:, 64] = b_hi
+    w0p[:, 65] = b_lo
+    w1 = (torch.randn((64, 128), generator=g) * 0.2).half()
+    dev = "cuda:0"
+    a0d, w0d, w1d = a0.to(dev), pack_kmajor(w0p).to(dev), pack_kmajor(w1).to(dev)
+    d0 = torch.zeros((128, 128), dtype=torch.float32, device=dev)
+    d1 = torch.zeros((128, 64), dtype=torch.float32, device=dev)
+    st = lib.nb_debug_tc_probe(a0d.data_ptr(), w0d.data_ptr(), w1d.data_ptr(), d0.data_ptr(), d1.data_ptr(),
+                               variant, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    capi.check(st, "nb_debug_tc_probe")
+    torch.cuda.synchronize()
+    ref0 = a0.float() @ w0.float().t() + b_hi.float() + b_lo.float()
+    h = torch.relu(d0.cpu()).half().float()          # the kernel rounds ITS OWN layer-0 output
+    ref1 = h @ w1.float().t()
+    e0 = float((d0.cpu() - ref0).abs().max())
+    e1 = float((d1.cpu() - ref1).abs().max())
+    ebias = float((d0.cpu() - ref0 - 0).abs().max())
+    return e0, e1, float(ref0.abs().max()), float(ref1.abs().max())
+
+
+def test_tc_probe_default_variant():
+    table = {v: run_probe(v) for v in range(4)}
+    for v, r in table.items():
+        print("variant %d: max|d0-ref|=%.3e max|d1-ref|=%.3e (|ref0|max %.2f, |ref1|max %.2f)" % ((v,) + r))
+    e0, e1, _, _ = table[0]
+    assert e0 < 2e-4, "SS MMA / smem descriptor / bias-as-K-step mismatch: %s" % (table,)
+    assert e1 < 2e-3, "TS MMA / TMEM A operand mismatch: %s" % (table,)
