@@ -93,7 +93,6 @@ __global__ void fold_Wc_kernel(nb_decoder_weights w, const double* __restrict__ 
         for (int j = 0; j < kHidden; ++j) acc += T[n * kHidden + j] * (double)w.feature_w[j * kHidden + k];
         const float v = (float)acc;
         f32[oWct + (size_t)k * kColor + n] = v;
-        f16[hW3 + umma_kmajor_offset(n, k, kColor)] = __float2half_rn(v);
     } else if (idx < kColor * kHidden + w.batch * kColor) {
         const int r = idx - kColor * kHidden;
         const int b = r / kColor, n = r % kColor;
@@ -112,15 +111,12 @@ __global__ void relayout_kernel(nb_decoder_weights w, float* __restrict__ f32, _
         const int n = i / kFeat, k = i % kFeat;
         const float v = w.fc0_w[i];
         f32[oW0t + (size_t)k * kHidden + n] = v;
-        f16[hW0 + umma_kmajor_offset(n, k, kHidden)] = __float2half_rn(v);
     }
     for (int i = t0; i < kHidden * kHidden; i += stride) {        // fc_1, fc_2 (256,256)
         const int n = i / kHidden, k = i % kHidden;
         const float v1 = w.fc1_w[i], v2 = w.fc2_w[i];
         f32[oW1t + (size_t)k * kHidden + n] = v1;
         f32[oW2t + (size_t)k * kHidden + n] = v2;
-        f16[hW1 + umma_kmajor_offset(n, k, kHidden)] = __float2half_rn(v1);
-        f16[hW2 + umma_kmajor_offset(n, k, kHidden)] = __float2half_rn(v2);
     }
     for (int i = t0; i < kHidden; i += stride) {
         f32[oB0 + i] = w.fc0_b[i]; f32[oB1 + i] = w.fc1_b[i]; f32[oB2 + i] = w.fc2_b[i];
@@ -131,7 +127,6 @@ __global__ void relayout_kernel(nb_decoder_weights w, float* __restrict__ f32, _
         const int n = i / 64, j = i % 64;
         const float v = (j < kXyzPE) ? w.view_w[n * 346 + 283 + j] : 0.f;
         f32[oWct + (size_t)(kHidden + j) * kColor + n] = v;
-        f16[hW3 + umma_kmajor_offset(n, kHidden + j, kColor)] = __float2half_rn(v);
     }
     for (int i = t0; i < kColor * 28; i += stride) {              // Wv = view_fc[:, 256:283]
         const int n = i / 28, j = i % 28;
@@ -139,6 +134,74 @@ __global__ void relayout_kernel(nb_decoder_weights w, float* __restrict__ f32, _
     }
     for (int i = t0; i < 3 * kColor; i += stride) f32[oRgbW + i] = w.rgb_w[i];
     if (t0 < 4) f32[oRgbB + t0] = (t0 < 3) ? w.rgb_b[t0] : 0.f;
+}
+
+// fp16 split of an fp32 value: hi = fp16(x), lo = fp16(x - hi): hi + lo carries ~21 mantissa bits.
+__device__ __forceinline__ __half f16_hi(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ __half f16_lo(float x) { return __float2half_rn(x - __half2float(__float2half_rn(x))); }
+
+// The tensor-core kernel's weight stream (layout in nb_layout.h).  Runs after fold_Wc_kernel
+// (reads the folded Wc from the fp32 section and the per-frame bias bc).
+__global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f32, const float* __restrict__ bc,
+                              __half* __restrict__ seq, __half* __restrict__ frame_steps) {
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // L0 / L1 / L2: N = 256
+    for (int layer = 0; layer < 3; ++layer) {
+        const int K = layer == 0 ? kFeat : kHidden;
+        const int steps = K / 16 + 1;
+        const float* W = layer == 0 ? w.fc0_w : layer == 1 ? w.fc1_w : w.fc2_w;
+        const float* Bv = layer == 0 ? w.fc0_b : layer == 1 ? w.fc1_b : w.fc2_b;
+        __half* dst = seq + (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
+        for (int i = t0; i < steps * 256 * 16; i += stride) {
+            const int st = i / 4096, n = (i / 16) % 256, kk = i % 16;
+            __half v;
+            if (st < steps - 1) v = __float2half_rn(W[(size_t)n * K + st * 16 + kk]);
+            else v = kk == 0 ? f16_hi(Bv[n]) : kk == 1 ? f16_lo(Bv[n]) : __float2half_rn(0.f);
+            dst[(size_t)st * kStepHalves256 + step_offset(n, kk, 256)] = v;
+        }
+    }
+    // L3: N = 144.  common steps 0..20 -> seq, per-frame step 21 -> frame_steps[b]
+    for (int i = t0; i < (kStepsL3 - 1 + w.batch) * kN3 * 16; i += stride) {
+        int st = i / (kN3 * 16);
+        const int n = (i / 16) % kN3, kk = i % 16;
+        int b = 0;
+        __half* dst;
+        if (st >= kStepsL3 - 1) { b = st - (kStepsL3 - 1); st = kStepsL3 - 1; dst = frame_steps + (size_t)b * kStepHalves3; }
+        else dst = seq + sL3 + (size_t)st * kStepHalves3;
+        float v = 0.f;
+        bool lo = false;
+        if (st < 16) {
+            const int k = st * 16 + kk;
+            if (n < kColor) v = f32[oWct + (size_t)k * kColor + n];
+            else if (n == 128) v = w.alpha_w[k];
+            else if (n == 129) { v = w.alpha_w[k]; lo = true; }
+        } else {
+            const int k2 = (st - 16) * 16 + kk;      // column of the per-point tile
+            if (n < kColor) {
+                if (k2 < kXyzPE) v = w.view_w[n * 346 + 283 + k2];
+                else if (k2 >= 64 && k2 < 64 + kViewPE) v = w.view_w[n * 346 + 256 + (k2 - 64)];
+                else if (k2 == 92) v = bc[b * kColor + n];
+                else if (k2 == 93) { v = bc[b * kColor + n]; lo = true; }
+            } else if (n == 128 && k2 == 92) v = w.alpha_b[0];
+            else if (n == 129 && k2 == 92) { v = w.alpha_b[0]; lo = true; }
+        }
+        dst[step_offset(n, kk, kN3)] = lo ? f16_lo(v) : f16_hi(v);
+    }
+    // L4: N = 16
+    for (int i = t0; i < kStepsL4 * kN4 * 16; i += stride) {
+        const int st = i / (kN4 * 16), n = (i / 16) % kN4, kk = i % 16;
+        float v = 0.f;
+        bool lo = false;
+        if (n < 6) {
+            const int c = n % 3;
+            lo = n >= 3;
+            if (st < 8) v = w.rgb_w[c * kColor + st * 16 + kk];
+            else if (kk == 0) v = w.rgb_b[c];
+            else { v = 0.f; }
+        }
+        seq[sL4 + (size_t)st * kStepHalves4 + step_offset(n, kk, kN4)] = lo ? f16_lo(v) : f16_hi(v);
+    }
 }
 
 }  // namespace nb
@@ -220,6 +283,7 @@ int nb_pack_weights(const nb_decoder_weights* w, void* out_blob, size_t out_byte
     const int n2 = kColor * kHidden + w->batch * kColor;
     fold_Wc_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(*w, T, u, f32, f16, bc);
     relayout_kernel<<<148, 256, 0, st>>>(*w, f32, f16);
+    stream_kernel<<<148, 256, 0, st>>>(*w, f32, bc, f16, (__half*)(base + frame_step_byte_offset(w->batch)));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("nb_pack_weights: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
     return NB_OK;
@@ -263,6 +327,7 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     p.wf32 = (const float*)wb;
     p.wf16 = (const __half*)(wb + kF16ByteOffset);
     p.bc = (const float*)(wb + kBcByteOffset);
+    p.wframe = (const __half*)(wb + frame_step_byte_offset(a->batch));
     p.white_bkgd = a->white_bkgd;
     p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw;
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;

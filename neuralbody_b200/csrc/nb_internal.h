@@ -23,7 +23,8 @@ struct RenderParams {
     size_t lvl_bstride[4];     // ELEMENT stride between frames of level l
     const void* volume;
     const float* wf32;         // fp32 weight section
-    const __half* wf16;        // fp16 tcgen05-canonical section
+    const __half* wf16;        // fp16 weight stream (common steps)
+    const __half* wframe;      // per-frame L3 step [B][144*16]
     const float* bc;           // [B][128]
     int white_bkgd;
     float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *raw;

@@ -34,33 +34,52 @@ constexpr size_t oRgbW = oWvt + (size_t)28 * kColor;        // [3][128]
 constexpr size_t oRgbB = oRgbW + 3 * kColor;                // [3] (+1 pad)
 constexpr size_t kF32Floats = oRgbB + 4;
 
-// ---- fp16 section: tcgen05 canonical K-major no-swizzle operand tiles.
-// Element (n, k) of an N x K matrix lives at half-offset
-//     ((k/8) * (N/8) + n/8) * 64 + (n%8) * 8 + (k%8)
-// i.e. 8x8 "core matrices" (8 rows x 16 bytes, 128 B contiguous), core matrices of one
-// 8-wide K chunk contiguous over N (stride-byte-offset 128 B), K chunks N*16 B apart
-// (leading-byte-offset).  A K=16 MMA step is therefore one contiguous N*32-byte slab.
+// ---- fp16 section: the tensor-core kernel's weight STREAM, in consumption order.
+// One "step" = the B operand of one K=16 tcgen05.mma: an N x 16 tile in the canonical K-major
+// no-swizzle layout: element (n, kk) at half-offset ((kk/8) * (N/8) + n/8) * 64 + (n%8) * 8 + (kk%8),
+// i.e. 8x8 core matrices (8 rows x 16 B = 128 B contiguous); stride-byte-offset (next 8 rows) = 128 B,
+// leading-byte-offset (next 8-wide K chunk) = N*16 B.  Each step is one contiguous bulk copy.
+//   L0  : 22 steps of fc_0 (N=256) + 1 bias step (A column of ones x [hi(b), lo(b)])
+//   L1,2: 16 steps + 1 bias step
+//   L3  : N=144 = 128 colour rows (Wc) + rows 128/129 = hi/lo(alpha_fc) + 14 zero rows;
+//         16 steps over h2, then 6 steps over the per-point tile
+//         [PE(xyz) 63 | 0 | PE(view) 27 | 0 | 1 | 1 | 0 | 0]  (weights Wx | 0 | Wv | 0 | hi(bc) | lo(bc))
+//         the last of those steps carries the per-frame bias bc => stored once per frame
+//   L4  : N=16: rows 0-2 hi(rgb_fc), rows 3-5 lo(rgb_fc); 8 steps + 1 bias step
 constexpr size_t kF16ByteOffset = ((kF32Floats * 4 + 255) / 256) * 256;
-constexpr size_t hW0 = 0;                                   // N=256, K=352
-constexpr size_t hW1 = hW0 + (size_t)kHidden * kFeat;       // N=256, K=256
-constexpr size_t hW2 = hW1 + (size_t)kHidden * kHidden;     // N=256, K=256
-constexpr size_t hW3 = hW2 + (size_t)kHidden * kHidden;     // N=128, K=320  (Wc | Wx | 0)
-constexpr size_t kF16Halves = hW3 + (size_t)kColor * kColorK;
+constexpr int kStepsL0 = 23, kStepsL1 = 17, kStepsL2 = 17, kStepsL3 = 22, kStepsL4 = 9;
+constexpr int kStepsPerTile = kStepsL0 + kStepsL1 + kStepsL2 + kStepsL3 + kStepsL4;   // 88
+constexpr int kN3 = 144, kN4 = 16;
+constexpr int kPeK = 96;                                   // per-point tile width of L3
+constexpr size_t kStepHalves256 = 256 * 16, kStepHalves3 = kN3 * 16, kStepHalves4 = kN4 * 16;
+constexpr size_t sL0 = 0;
+constexpr size_t sL1 = sL0 + kStepsL0 * kStepHalves256;
+constexpr size_t sL2 = sL1 + kStepsL1 * kStepHalves256;
+constexpr size_t sL3 = sL2 + kStepsL2 * kStepHalves256;
+constexpr size_t sL4 = sL3 + kStepsL3 * kStepHalves3;      // (the common copy of L3's last step is unused)
+constexpr size_t kF16Halves = sL4 + kStepsL4 * kStepHalves4;
 
-// ---- scratch for the fp64 fold (doubles), then per-frame bias bc (floats)
+// ---- scratch for the fp64 fold (doubles), then per-frame data
 constexpr size_t kScratchByteOffset = ((kF16ByteOffset + kF16Halves * 2 + 255) / 256) * 256;
 constexpr size_t kScratchDoubles = (size_t)kColor * kHidden;   // T = view_fc[:, :256] * latent_fc[:, :256]
 constexpr size_t kBcByteOffset = kScratchByteOffset + kScratchDoubles * 8;
-// after bc[B][128] floats: u[B][256] doubles (fold scratch)
+// after bc[B][128] floats: u[B][256] doubles (fold scratch), then the per-frame L3 step [B][144*16] halves
 
-__host__ __device__ inline size_t packed_weights_bytes(int batch) {
-    size_t b = kBcByteOffset + (size_t)batch * kColor * 4;
-    b = (b + 255) / 256 * 256;
-    return b + (size_t)batch * kHidden * 8;
-}
 __host__ __device__ inline size_t u_byte_offset(int batch) {
     size_t b = kBcByteOffset + (size_t)batch * kColor * 4;
     return (b + 255) / 256 * 256;
+}
+__host__ __device__ inline size_t frame_step_byte_offset(int batch) {
+    size_t b = u_byte_offset(batch) + (size_t)batch * kHidden * 8;
+    return (b + 255) / 256 * 256;
+}
+__host__ __device__ inline size_t packed_weights_bytes(int batch) {
+    return frame_step_byte_offset(batch) + (size_t)batch * kStepHalves3 * 2;
+}
+
+// element (n, kk) of an N x 16 step tile
+__host__ __device__ inline size_t step_offset(int n, int kk, int N) {
+    return ((size_t)(kk >> 3) * (N >> 3) + (n >> 3)) * 64 + (size_t)(n & 7) * 8 + (kk & 7);
 }
 
 __host__ __device__ inline size_t umma_kmajor_offset(int n, int k, int N) {

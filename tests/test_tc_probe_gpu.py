@@ -52,9 +52,17 @@ def run_probe(variant, seed=0):
 
 
 def test_tc_probe_default_variant():
-    table = {v: run_probe(v) for v in range(4)}
-    for v, r in table.items():
-        print("variant %d: max|d0-ref|=%.3e max|d1-ref|=%.3e (|ref0|max %.2f, |ref1|max %.2f)" % ((v,) + r))
-    e0, e1, _, _ = table[0]
-    assert e0 < 2e-4, "SS MMA / smem descriptor / bias-as-K-step mismatch: %s" % (table,)
-    assert e1 < 2e-3, "TS MMA / TMEM A operand mismatch: %s" % (table,)
+    """Variant 0 is the convention the fused kernel uses.  (Other variants can fault by reading
+    shared memory out of bounds; probe them one per process: `python tests/test_tc_probe_gpu.py <v>`.)"""
+    e0, e1, m0, m1 = run_probe(0)
+    print("variant 0: max|d0-ref|=%.3e max|d1-ref|=%.3e (|ref0|max %.2f, |ref1|max %.2f)" % (e0, e1, m0, m1))
+    assert e0 < 2e-4, "SS MMA / smem descriptor / bias-as-K-step mismatch: %.3e" % e0
+    assert e1 < 2e-3, "TS MMA / TMEM A operand mismatch: %.3e" % e1
+
+
+if __name__ == "__main__":
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    v = int(sys.argv[1])
+    print("variant %d: max|d0-ref|=%.3e max|d1-ref|=%.3e (|ref0|max %.2f, |ref1|max %.2f)" % ((v,) + run_probe(v)))
