@@ -38,6 +38,7 @@ extern "C" {
 /* arithmetic of the decoder MLP inside nb_render_fwd */
 #define NB_PRECISION_FP32      0   /* exact: fp32 FFMA everywhere (GPU-side oracle, fallback)            */
 #define NB_PRECISION_TC_FP16   1   /* tcgen05 tensor cores: fp16 operands, fp32 accumulate in TMEM       */
+#define NB_PRECISION_TC_FP16X3 2   /* tcgen05, density path as hi+lo fp16 pairs, 3 MMA passes: ~fp32-accurate */
 
 #define NB_NUM_LEVELS   4          /* SparseConvNet returns 4 dense volumes, latent_xyzc.py:179-204     */
 #define NB_FEAT_DIM     352        /* 32+64+128+128 channels, latent_xyzc.py:20                         */

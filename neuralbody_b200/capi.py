@@ -8,7 +8,7 @@ from . import _build
 
 NB_OK = 0
 NB_DTYPE_F32, NB_DTYPE_F16 = 0, 1
-NB_PRECISION_FP32, NB_PRECISION_TC_FP16 = 0, 1
+NB_PRECISION_FP32, NB_PRECISION_TC_FP16, NB_PRECISION_TC_FP16X3 = 0, 1, 2
 NB_NUM_LEVELS = 4
 
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",

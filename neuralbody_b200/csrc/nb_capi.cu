@@ -146,19 +146,21 @@ __global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f3
                               __half* __restrict__ seq, __half* __restrict__ frame_steps) {
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    // L0 / L1 / L2: N = 256
+    // L0 / L1 / L2: N = 256; slot 2*ks = hi(W[:, 16ks..]), slot 2*ks+1 = lo(...), last slot = bias step
     for (int layer = 0; layer < 3; ++layer) {
         const int K = layer == 0 ? kFeat : kHidden;
-        const int steps = K / 16 + 1;
+        const int slots = (K / 16) * 2 + 1;
         const float* W = layer == 0 ? w.fc0_w : layer == 1 ? w.fc1_w : w.fc2_w;
         const float* Bv = layer == 0 ? w.fc0_b : layer == 1 ? w.fc1_b : w.fc2_b;
         __half* dst = seq + (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
-        for (int i = t0; i < steps * 256 * 16; i += stride) {
-            const int st = i / 4096, n = (i / 16) % 256, kk = i % 16;
+        for (int i = t0; i < slots * 256 * 16; i += stride) {
+            const int sl = i / 4096, n = (i / 16) % 256, kk = i % 16;
             __half v;
-            if (st < steps - 1) v = __float2half_rn(W[(size_t)n * K + st * 16 + kk]);
-            else v = kk == 0 ? f16_hi(Bv[n]) : kk == 1 ? f16_lo(Bv[n]) : __float2half_rn(0.f);
-            dst[(size_t)st * kStepHalves256 + step_offset(n, kk, 256)] = v;
+            if (sl < slots - 1) {
+                const float x = W[(size_t)n * K + (sl >> 1) * 16 + kk];
+                v = (sl & 1) ? f16_lo(x) : f16_hi(x);
+            } else v = kk == 0 ? f16_hi(Bv[n]) : kk == 1 ? f16_lo(Bv[n]) : __float2half_rn(0.f);
+            dst[(size_t)sl * kStepHalves256 + step_offset(n, kk, 256)] = v;
         }
     }
     // L3: N = 144.  common steps 0..20 -> seq, per-frame step 21 -> frame_steps[b]
@@ -214,7 +216,7 @@ int nb_abi_version(void) { return NB_ABI_VERSION; }
 const char* nb_last_error(void) { return g_err; }
 int nb_has_precision(int precision) {
     if (precision == NB_PRECISION_FP32) return 1;
-    if (precision == NB_PRECISION_TC_FP16) return tc_available() ? 1 : 0;
+    if (precision == NB_PRECISION_TC_FP16 || precision == NB_PRECISION_TC_FP16X3) return tc_available() ? 1 : 0;
     return 0;
 }
 
@@ -334,7 +336,8 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
 
     cudaStream_t st = (cudaStream_t)stream;
     if (a->precision == NB_PRECISION_FP32) return launch_render_f32(p, a->volume_dtype, st);
-    if (a->precision == NB_PRECISION_TC_FP16) return launch_render_tc(p, a->volume_dtype, st);
+    if (a->precision == NB_PRECISION_TC_FP16) return launch_render_tc(p, a->volume_dtype, 1, st);
+    if (a->precision == NB_PRECISION_TC_FP16X3) return launch_render_tc(p, a->volume_dtype, 3, st);
     set_error("nb_render_fwd: unknown precision %d", a->precision);
     return NB_ERR_BAD_ARG;
 }

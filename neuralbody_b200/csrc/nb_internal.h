@@ -35,7 +35,7 @@ struct RenderParams {
 };
 
 int launch_render_f32(const RenderParams& p, int volume_dtype, cudaStream_t stream);
-int launch_render_tc(const RenderParams& p, int volume_dtype, cudaStream_t stream);
+int launch_render_tc(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
 bool tc_available();
 
 }  // namespace nb

@@ -39,23 +39,26 @@ constexpr size_t kF32Floats = oRgbB + 4;
 // no-swizzle layout: element (n, kk) at half-offset ((kk/8) * (N/8) + n/8) * 64 + (n%8) * 8 + (kk%8),
 // i.e. 8x8 core matrices (8 rows x 16 B = 128 B contiguous); stride-byte-offset (next 8 rows) = 128 B,
 // leading-byte-offset (next 8-wide K chunk) = N*16 B.  Each step is one contiguous bulk copy.
-//   L0  : 22 steps of fc_0 (N=256) + 1 bias step (A column of ones x [hi(b), lo(b)])
-//   L1,2: 16 steps + 1 bias step
-//   L3  : N=144 = 128 colour rows (Wc) + rows 128/129 = hi/lo(alpha_fc) + 14 zero rows;
+// Layers 0-2 (the density path) carry every weight as hi = fp16(w) and lo = fp16(w - hi) in two
+// consecutive steps, so the 3-pass mode (A_hi W_hi + A_lo W_hi + A_hi W_lo) is ~fp32-accurate; the
+// 1-pass mode simply skips the lo steps.
+//   L0  : 22 x (hi, lo) steps of fc_0 (N=256) + 1 bias step (A column of ones x [hi(b), lo(b)])
+//   L1,2: 16 x (hi, lo) steps + 1 bias step
+//   L3  : N=144 = 128 colour rows (Wc, fp16) + rows 128/129 = hi/lo(alpha_fc) + 14 zero rows;
 //         16 steps over h2, then 6 steps over the per-point tile
 //         [PE(xyz) 63 | 0 | PE(view) 27 | 0 | 1 | 1 | 0 | 0]  (weights Wx | 0 | Wv | 0 | hi(bc) | lo(bc))
 //         the last of those steps carries the per-frame bias bc => stored once per frame
 //   L4  : N=16: rows 0-2 hi(rgb_fc), rows 3-5 lo(rgb_fc); 8 steps + 1 bias step
 constexpr size_t kF16ByteOffset = ((kF32Floats * 4 + 255) / 256) * 256;
-constexpr int kStepsL0 = 23, kStepsL1 = 17, kStepsL2 = 17, kStepsL3 = 22, kStepsL4 = 9;
-constexpr int kStepsPerTile = kStepsL0 + kStepsL1 + kStepsL2 + kStepsL3 + kStepsL4;   // 88
+constexpr int kSlotsL0 = 22 * 2 + 1, kSlotsL1 = 16 * 2 + 1, kSlotsL2 = 16 * 2 + 1;   // stream slots incl. lo steps
+constexpr int kStepsL3 = 22, kStepsL4 = 9;
 constexpr int kN3 = 144, kN4 = 16;
 constexpr int kPeK = 96;                                   // per-point tile width of L3
 constexpr size_t kStepHalves256 = 256 * 16, kStepHalves3 = kN3 * 16, kStepHalves4 = kN4 * 16;
 constexpr size_t sL0 = 0;
-constexpr size_t sL1 = sL0 + kStepsL0 * kStepHalves256;
-constexpr size_t sL2 = sL1 + kStepsL1 * kStepHalves256;
-constexpr size_t sL3 = sL2 + kStepsL2 * kStepHalves256;
+constexpr size_t sL1 = sL0 + kSlotsL0 * kStepHalves256;
+constexpr size_t sL2 = sL1 + kSlotsL1 * kStepHalves256;
+constexpr size_t sL3 = sL2 + kSlotsL2 * kStepHalves256;
 constexpr size_t sL4 = sL3 + kStepsL3 * kStepHalves3;      // (the common copy of L3's last step is unused)
 constexpr size_t kF16Halves = sL4 + kStepsL4 * kStepHalves4;
 

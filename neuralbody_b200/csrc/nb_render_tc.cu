@@ -1,23 +1,30 @@
-// Tensor-core fused render kernel (NB_PRECISION_TC_FP16) for sm_100a.
+// Tensor-core fused render kernel for sm_100a (NB_PRECISION_TC_FP16 = 1 pass, NB_PRECISION_TC_FP16X3 = 3 passes).
 //
-// One persistent CTA per SM walks 128-point tiles (= 128/S whole rays) and does, per tile, everything
+// One persistent CTA per SM walks 128-point tiles (= floor(128/S) whole rays) and does, per tile, everything
 // Renderer.render's chunk loop does upstream (if_clight_renderer.py:107-120): sampling, world->SMPL->grid,
 // 4-level trilinear gather, decoder MLP (latent_xyzc.py:99-121, folded as in nb_layout.h), PE, composite.
+// Nothing per-point touches global memory between the gather and the 24-byte per-ray result.
 //
-// Data flow (nothing per-point ever touches global memory between the gather and the 24-byte result):
-//   producer warps (8)  : geometry + trilinear gather from the fp16 channels-last volume -> fp16 A tile "F"
-//                         in shared memory, in the tcgen05 K-major no-swizzle operand layout
-//   loader warp         : streams the decoder weights (fp16, pre-packed per K=16 step, consumption order)
-//                         from L2 into a 12-slot shared-memory ring with bulk async copies (TMA engine)
-//   MMA warp (1 thread) : tcgen05.mma kind::f16, fp32 accumulators in TMEM.  Layer 0 reads A from smem (F);
-//                         layers 1..4 read A straight from TMEM, where the previous layer's epilogue left it
-//   epilogue warps (4)  : tcgen05.ld accumulator -> cvt.rn.relu.f16x2 -> tcgen05.st next layer's A operand
-//                         (activations never visit shared memory); PE(xyz) / PE(view) tile; sigma / rgb
-//                         read-out; warp-scan alpha composite; 24 B/ray written to HBM
-// Biases ride in the GEMMs as an extra K=16 step against a constant column of ones (hi+lo fp16 split, so
-// they stay fp32-accurate); so do alpha_fc (2 extra N rows of layer 3) and rgb_fc (a 16-wide layer 4).
+//   producer warps (12) : geometry, then the trilinear gather from the channels-last volume into the fp16 A
+//                         operand of layer 0, written in the tcgen05 K-major no-swizzle layout into a 2-deep
+//                         ring of 64-channel K SEGMENTS (layer 0 is K-pipelined against the gather)
+//   loader warp         : streams the decoder weights (fp16, one pre-packed K=16 step per bulk copy, in
+//                         consumption order) from L2 into a 12-slot shared-memory ring (TMA engine, UBLKCP)
+//   MMA warp (1 thread) : tcgen05.mma kind::f16, fp32 accumulator in TMEM.  Layer 0 reads A from shared memory;
+//                         layers 1..4 read A straight from TMEM, where the previous epilogue left it
+//   epilogue warps (4)  : tcgen05.ld accumulator -> relu -> fp16 (hi [+ lo]) -> tcgen05.st as the next layer's
+//                         A operand (activations never visit shared memory); PE tile; sigma / rgb read-out;
+//                         warp-scan alpha composite
+// Biases ride in the GEMMs as an extra K=16 step against a constant column of ones (hi+lo fp16 split => fp32
+// accurate); so do alpha_fc (2 extra N rows of layer 3) and rgb_fc (a 16-wide layer 4).
 //
-// TMEM (512 columns): [0,256) fp32 accumulator | [256,384) hA | [384,512) hB  (fp16 activations, 2 per column)
+// Precision.  fp16 has an 11-bit significand; on a trained-like decoder one fp16 rounding of ANY density-path
+// operand (volume, features, weights, h0, h1, h2) moves depth_map by ~1e-3, the whole parity budget.  The
+// 3-pass mode therefore carries every density-path operand as hi + lo fp16 (22 bits) and issues
+//   A_hi W_hi + A_lo W_hi + A_hi W_lo      (the A_lo W_lo term is 2^-22 relative and dropped)
+// for layers 0-2 and the alpha rows, gathering from an fp32 volume; the colour tail stays single fp16.
+//
+// TMEM (512 columns): [0,256) fp32 accumulator | [256,384) h_hi | [384,512) h_lo  (fp16 pairs, in place)
 #include "nb_device.cuh"
 #include "nb_tc_ptx.cuh"
 
@@ -28,49 +35,45 @@ constexpr int TP = 128;                       // points per tile = UMMA M
 constexpr int NUM_SLOTS = 12;
 constexpr int SLOT_BYTES = 8192;              // one K=16 step of an N=256 layer
 constexpr int CHUNK_BYTES = 2048;             // one 8-wide K chunk of a 128-row A tile
-constexpr int F_CHUNKS = 46;                  // 44 feature chunks + the "ones" K-step (chunks 44,45)
+constexpr int SEG_CHUNKS = 8;                 // 64 channels per segment
+constexpr int NUM_SEGS = 6;                   // 44 feature chunks = 5 x 8 + 4
+constexpr int SEG_BYTES = 2 * SEG_CHUNKS * CHUNK_BYTES;   // hi plane + lo plane = 32 KB
 constexpr int PE_CHUNKS = 12;                 // 96-wide per-point tile of layer 3
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 8;
-constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;   // 448
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 12;
+constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;   // 576
 constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int NSUB = PROD_WARPS / 4;          // lanes sharing one point (each takes chunks j % NSUB == sub)
 
 // shared-memory map (bytes)
-constexpr int OFF_F = 0;
-constexpr int OFF_PE = OFF_F + F_CHUNKS * CHUNK_BYTES;            //  94208
-constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;        // 118784
-constexpr int OFF_GEOM = OFF_RING + NUM_SLOTS * SLOT_BYTES;       // 217088  float4[128] (wx,wy,wz,z)   producer-owned
-constexpr int OFF_GRID = OFF_GEOM + TP * 16;                      // 219136  float4[128] (gx,gy,gz,-)   producer-owned
-constexpr int OFF_RAW = OFF_GRID + TP * 16;                       // 221184  float4[128] (r,g,b,sigma)  epilogue-owned
-constexpr int OFF_Z = OFF_RAW + TP * 16;                          // 223232  float[128] z               epilogue-owned
-constexpr int OFF_XF = OFF_Z + TP * 4;                            // 223744  FrameXf (producer-owned)
-constexpr int OFF_BAR = OFF_XF + 128;                             // 223872
-constexpr int NUM_BARS = 2 * NUM_SLOTS + 6;
-constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;                  // 224112
+constexpr int OFF_SEG = 0;                                         // 2 x 32 KB
+constexpr int OFF_ONES = OFF_SEG + 2 * SEG_BYTES;                  //  65536: constant (1,1,0..) K-step, 2 chunks
+constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;                 //  69632
+constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;         //  94208
+constexpr int OFF_GEOM = OFF_RING + NUM_SLOTS * SLOT_BYTES;        // 192512  float4[128] (wx,wy,wz,z)   producer-owned
+constexpr int OFF_GRID = OFF_GEOM + TP * 16;                       // float4[128] (gx,gy,gz,-)           producer-owned
+constexpr int OFF_RAW = OFF_GRID + TP * 16;                        // float4[128] (r,g,b,sigma)          epilogue-owned
+constexpr int OFF_Z = OFF_RAW + TP * 16;                           // float[128] z                       epilogue-owned
+constexpr int OFF_XF = OFF_Z + TP * 4;                             // FrameXf (producer-owned)
+constexpr int OFF_BAR = OFF_XF + 128;
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + 2,
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 4, BAR_H_READY, BAR_GEOM_FULL, BAR_GEOM_FREE, NUM_BARS };
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_F_FULL = 2 * NUM_SLOTS, BAR_F_EMPTY, BAR_ACC_FULL, BAR_H_READY,
-       BAR_GEOM_FREE, BAR_SPARE };
-
-constexpr uint32_t TM_ACC = 0, TM_HA = 256, TM_HB = 384;
+constexpr uint32_t TM_ACC = 0, TM_HI = 256, TM_LO = 384;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
 __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     uint4 r;
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-
-__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& v, float w) {
-    const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h[i]);
-        acc[2 * i] = fmaf(f.x, w, acc[2 * i]);
-        acc[2 * i + 1] = fmaf(f.y, w, acc[2 * i + 1]);
-    }
+__device__ __forceinline__ float f16lo_of(float x, uint32_t hi_pair, int which) {
+    // x - float(hi) for one element of a packed fp16 pair
+    const __half2 h = *reinterpret_cast<const __half2*>(&hi_pair);
+    return x - (which ? __high2float(h) : __low2float(h));
 }
 
 struct TileCoord { int b, r0, nr; };
@@ -82,6 +85,31 @@ __device__ __forceinline__ TileCoord tile_coord(const RenderParams& P, int tile)
     return t;
 }
 
+// One gather unit: 8 corners x 16 bytes -> NCH channels accumulated in fp32.
+template <typename VT> struct Unit;
+template <> struct Unit<__half> {
+    static constexpr int NCH = 8;
+    static __device__ __forceinline__ void fma(float (&acc)[8], const uint4& v, float w) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            acc[2 * i] = fmaf(f.x, w, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(f.y, w, acc[2 * i + 1]);
+        }
+    }
+};
+template <> struct Unit<float> {
+    static constexpr int NCH = 4;
+    static __device__ __forceinline__ void fma(float (&acc)[4], const uint4& v, float w) {
+        acc[0] = fmaf(__uint_as_float(v.x), w, acc[0]);
+        acc[1] = fmaf(__uint_as_float(v.y), w, acc[1]);
+        acc[2] = fmaf(__uint_as_float(v.z), w, acc[2]);
+        acc[3] = fmaf(__uint_as_float(v.w), w, acc[3]);
+    }
+};
+
+template <int NP, typename VT>
 __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -93,19 +121,19 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == LOAD_WARP * 32) {
         for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], 1); }
-        tc::mbar_init(&bars[BAR_F_FULL], PROD_WARPS);
-        tc::mbar_init(&bars[BAR_F_EMPTY], 1);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
         tc::mbar_init(&bars[BAR_H_READY], EPI_WARPS * 32);
+        tc::mbar_init(&bars[BAR_GEOM_FULL], PROD_WARPS);
         tc::mbar_init(&bars[BAR_GEOM_FREE], EPI_WARPS * 32);
         tc::fence_mbar_init();
     }
-    if (warp >= PROD_WARP0) {   // constant "ones" K-step of the A operand: chunk 44 = (1,1,0,..), chunk 45 = 0
+    if (warp >= PROD_WARP0) {   // constant "ones" K-step of the A operand: chunk 0 = (1,1,0,..), chunk 1 = 0
         const int pt = tid - PROD_WARP0 * 32;
         if (pt < TP) {
-            unsigned char* f = smem + OFF_F;
-            *reinterpret_cast<uint4*>(f + (44 * 16 + (pt >> 3)) * 128 + (pt & 7) * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(f + (45 * 16 + (pt >> 3)) * 128 + (pt & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            unsigned char* o = smem + OFF_ONES;
+            *reinterpret_cast<uint4*>(o + (pt >> 3) * 128 + (pt & 7) * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(o + CHUNK_BYTES + (pt >> 3) * 128 + (pt & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
         tc::fence_proxy_async();
     }
@@ -113,25 +141,25 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-
     const int n_tiles = P.n_groups;
 
     // ================================================================== PRODUCERS: geometry + gather
     if (warp >= PROD_WARP0) {
-        const int pt = tid - PROD_WARP0 * 32;          // 0..255
+        const int pt = tid - PROD_WARP0 * 32;
         const int pw = warp - PROD_WARP0;
         float4* geom = reinterpret_cast<float4*>(smem + OFF_GEOM);
         float4* grid = reinterpret_cast<float4*>(smem + OFF_GRID);
         FrameXf* xf = reinterpret_cast<FrameXf*>(smem + OFF_XF);
-        unsigned char* F = smem + OFF_F;
         const unsigned char* volbase = reinterpret_cast<const unsigned char*>(P.volume);
+        // this lane's fixed point and chunk residue: quarter-warps = 8 consecutive points of one chunk
+        const int gid = pw * 4 + (lane >> 3);
+        const int p = (gid & 15) * 8 + (lane & 7);
+        const int sub = gid >> 4;
+        constexpr int NCH = Unit<VT>::NCH;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc_ = tile_coord(P, tile);
-            // F and grid are free once layer 0 of the previous tile has been consumed; geom once the
-            // epilogue has copied what it needs from the previous tile
-            tc::mbar_wait(&bars[BAR_F_EMPTY], (it & 1) ^ 1);
-            tc::mbar_wait(&bars[BAR_GEOM_FREE], (it & 1) ^ 1);
+            tc::mbar_wait(&bars[BAR_GEOM_FREE], (it & 1) ^ 1);    // epilogue has copied the previous tile's geometry
             if (pt < 9) xf->R[pt] = __ldg(P.R + tc_.b * 9 + pt);
             if (pt < 3) {
                 xf->Th[pt] = __ldg(P.Th + tc_.b * 3 + pt);
@@ -159,46 +187,73 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 grid[pt] = gr;
             }
             named_bar_sync(1, PROD_THREADS);
-            // gather: a warp-iteration covers 8 points x 4 consecutive 8-channel chunks (lane%8 = point,
-            // lane/8 = chunk): every quarter-warp stores 128 contiguous bytes of one chunk (conflict-free),
-            // every point reads 64 contiguous bytes per corner.
-            const int lp = lane & 7, lj = lane >> 3;
-            for (int blk = pw; blk < 16 * 11; blk += PROD_WARPS) {
-                const int p = (blk & 15) * 8 + lp;
-                const int j = (blk >> 4) * 4 + lj;           // chunk 0..43
-                int lvl, c0;
-                if (j < 4) { lvl = 0; c0 = j * 8; }
-                else if (j < 12) { lvl = 1; c0 = (j - 4) * 8; }
-                else if (j < 28) { lvl = 2; c0 = (j - 12) * 8; }
-                else { lvl = 3; c0 = (j - 28) * 8; }
-                const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
-                const float4 g = grid[p];
-                Corners cn;
-                corner_setup(unnormalize(g.x, W), unnormalize(g.y, H), unnormalize(g.z, D), W, H, D, cn);
-                const __half* vol = reinterpret_cast<const __half*>(volbase + P.lvl_off[lvl]) + (size_t)tc_.b * P.lvl_bstride[lvl];
-                float acc[8];
+            if (lane == 0) tc::mbar_arrive(&bars[BAR_GEOM_FULL]);
+
+            const float4 g = grid[p];
+            int cur_lvl = -1;
+            uint32_t coff[8];    // element offset of each corner's voxel inside the level (0 when out of range)
+            float cw[8];         // corner weight (0 when out of range)
+            const VT* vol = nullptr;
+            for (int seg = 0; seg < NUM_SEGS; ++seg) {
+                const uint32_t gseg = (uint32_t)it * NUM_SEGS + seg;
+                const uint32_t buf = gseg & 1;
+                tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg >> 1) & 1) ^ 1);
+                unsigned char* hi_plane = smem + OFF_SEG + buf * SEG_BYTES;
+                unsigned char* lo_plane = hi_plane + SEG_CHUNKS * CHUNK_BYTES;
+                const int nchunks = (seg == NUM_SEGS - 1) ? 4 : SEG_CHUNKS;
+                for (int jj = sub; jj < nchunks; jj += NSUB) {
+                    const int j = seg * SEG_CHUNKS + jj;          // feature chunk 0..43
+                    int lvl, c0;
+                    if (j < 4) { lvl = 0; c0 = j * 8; }
+                    else if (j < 12) { lvl = 1; c0 = (j - 4) * 8; }
+                    else if (j < 28) { lvl = 2; c0 = (j - 12) * 8; }
+                    else { lvl = 3; c0 = (j - 28) * 8; }
+                    if (lvl != cur_lvl) {
+                        cur_lvl = lvl;
+                        const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+                        Corners cn;
+                        corner_setup(unnormalize(g.x, W), unnormalize(g.y, H), unnormalize(g.z, D), W, H, D, cn);
+                        vol = reinterpret_cast<const VT*>(volbase + P.lvl_off[lvl]) + (size_t)tc_.b * P.lvl_bstride[lvl];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                uint4 v[8];
-                float wgt[8];
+                        for (int c = 0; c < 8; ++c) {
+                            const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+                            const bool ok = corner_valid(cn, dx, dy, dz, W, H, D);
+                            cw[c] = ok ? corner_weight(cn, dx, dy, dz) : 0.f;
+                            coff[c] = ok ? (uint32_t)((((cn.z0 + dz) * H + (cn.y0 + dy)) * W + (cn.x0 + dx)) * C) : 0u;
+                        }
+                    }
+                    float acc[8];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
-                    const bool ok = corner_valid(cn, dx, dy, dz, W, H, D);
-                    wgt[c] = ok ? corner_weight(cn, dx, dy, dz) : 0.f;
-                    const size_t vox = ok ? ((size_t)(cn.z0 + dz) * H + (cn.y0 + dy)) * W + (cn.x0 + dx) : 0;
-                    v[c] = ok ? ldg_nc_v4(vol + vox * C + c0) : make_uint4(0u, 0u, 0u, 0u);
+                    for (int u = 0; u < 8 / NCH; ++u) {
+                        uint4 v[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) v[c] = ldg_nc_v4(vol + coff[c] + c0 + u * NCH);
+                        float a[NCH];
+#pragma unroll
+                        for (int i = 0; i < NCH; ++i) a[i] = 0.f;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) Unit<VT>::fma(a, v[c], cw[c]);   // ATen order: x fastest
+#pragma unroll
+                        for (int i = 0; i < NCH; ++i) acc[u * NCH + i] = a[i];
+                    }
+                    uint4 hi;
+                    hi.x = tc::cvt_f16x2(acc[0], acc[1]); hi.y = tc::cvt_f16x2(acc[2], acc[3]);
+                    hi.z = tc::cvt_f16x2(acc[4], acc[5]); hi.w = tc::cvt_f16x2(acc[6], acc[7]);
+                    const int so = (jj * 16 + (p >> 3)) * 128 + (p & 7) * 16;
+                    *reinterpret_cast<uint4*>(hi_plane + so) = hi;
+                    if (NP == 3) {
+                        uint4 lo;
+                        lo.x = tc::cvt_f16x2(f16lo_of(acc[0], hi.x, 0), f16lo_of(acc[1], hi.x, 1));
+                        lo.y = tc::cvt_f16x2(f16lo_of(acc[2], hi.y, 0), f16lo_of(acc[3], hi.y, 1));
+                        lo.z = tc::cvt_f16x2(f16lo_of(acc[4], hi.z, 0), f16lo_of(acc[5], hi.z, 1));
+                        lo.w = tc::cvt_f16x2(f16lo_of(acc[6], hi.w, 0), f16lo_of(acc[7], hi.w, 1));
+                        *reinterpret_cast<uint4*>(lo_plane + so) = lo;
+                    }
                 }
-#pragma unroll
-                for (int c = 0; c < 8; ++c) fma8(acc, v[c], wgt[c]);
-                uint4 o;
-                o.x = tc::cvt_f16x2(acc[0], acc[1]); o.y = tc::cvt_f16x2(acc[2], acc[3]);
-                o.z = tc::cvt_f16x2(acc[4], acc[5]); o.w = tc::cvt_f16x2(acc[6], acc[7]);
-                *reinterpret_cast<uint4*>(F + (j * 16 + (p >> 3)) * 128 + (p & 7) * 16) = o;
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars[BAR_SEG_FULL + buf]);
             }
-            tc::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&bars[BAR_F_FULL]);
         }
     }
     // ================================================================== LOADER: weight stream -> ring
@@ -206,27 +261,31 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         if (lane == 0) {
             uint32_t cnt = 0;
             const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
+            auto push = [&](const unsigned char* src, uint32_t bytes) {
+                const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
+                tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes);
+                tc::bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_W_FULL + slot]);
+                ++cnt;
+            };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int b = tile / P.groups_per_frame;
-                for (int st = 0; st < kStepsPerTile; ++st, ++cnt) {
-                    const unsigned char* src;
-                    uint32_t bytes;
-                    if (st < kStepsL0 + kStepsL1 + kStepsL2) { src = seq + (size_t)st * SLOT_BYTES; bytes = SLOT_BYTES; }
-                    else if (st < kStepsL0 + kStepsL1 + kStepsL2 + kStepsL3) {
-                        const int s3 = st - (kStepsL0 + kStepsL1 + kStepsL2);
-                        bytes = kStepHalves3 * 2;
-                        src = (s3 == kStepsL3 - 1) ? reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)b * bytes
-                                                   : seq + sL3 * 2 + (size_t)s3 * bytes;
-                    } else {
-                        const int s4 = st - (kStepsL0 + kStepsL1 + kStepsL2 + kStepsL3);
-                        bytes = kStepHalves4 * 2;
-                        src = seq + sL4 * 2 + (size_t)s4 * bytes;
+                // layers 0-2: (hi, lo) pairs + bias step; the 1-pass mode skips the lo steps
+                for (int layer = 0; layer < 3; ++layer) {
+                    const int ksteps = layer == 0 ? 22 : 16;
+                    const unsigned char* base = seq + 2 * (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        push(base + (size_t)(2 * ks) * SLOT_BYTES, SLOT_BYTES);
+                        if (NP == 3) push(base + (size_t)(2 * ks + 1) * SLOT_BYTES, SLOT_BYTES);
                     }
-                    const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
-                    tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);
-                    tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes);
-                    tc::bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_W_FULL + slot]);
+                    push(base + (size_t)(2 * ksteps) * SLOT_BYTES, SLOT_BYTES);
                 }
+                for (int s3 = 0; s3 < kStepsL3; ++s3) {
+                    const uint32_t bytes = kStepHalves3 * 2;
+                    push((s3 == kStepsL3 - 1) ? reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)b * bytes
+                                              : seq + sL3 * 2 + (size_t)s3 * bytes, bytes);
+                }
+                for (int s4 = 0; s4 < kStepsL4; ++s4) push(seq + sL4 * 2 + (size_t)s4 * kStepHalves4 * 2, kStepHalves4 * 2);
             }
         }
     }
@@ -235,8 +294,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         if (lane == 0) {
             uint32_t cnt = 0, hcnt = 0;
             int it = 0;
-            const uint32_t f_addr = tc::smem_u32(smem + OFF_F), pe_addr = tc::smem_u32(smem + OFF_PE);
-            const uint32_t ring_addr = tc::smem_u32(smem + OFF_RING);
+            const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
+            const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
             constexpr uint32_t ID256 = tc::make_idesc_f16(128, 256), ID3 = tc::make_idesc_f16(128, kN3),
                                ID4 = tc::make_idesc_f16(128, kN4);
             auto wait_slot = [&](uint32_t& slot) {
@@ -251,36 +310,59 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
 
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 uint32_t slot;
-                // ---- layer 0: A = F (smem), 22 feature steps + ones step
-                tc::mbar_wait(&bars[BAR_F_FULL], it & 1);
                 if (it > 0) wait_h();                 // previous tile's last epilogue has drained the accumulator
-                tc::tc_fence_after();
-                for (int ks = 0; ks < kStepsL0; ++ks) {
-                    wait_slot(slot);
-                    tc::mma_ss(tmem + TM_ACC, a_desc(f_addr, ks), b_desc(slot, 256), ID256, ks > 0);
-                    release_slot(slot);
+                // ---- layer 0: A = gathered features, K-pipelined over 6 segments of the smem ring
+                bool first = true;
+                for (int seg = 0; seg < NUM_SEGS; ++seg) {
+                    const uint32_t gseg = (uint32_t)it * NUM_SEGS + seg;
+                    const uint32_t buf = gseg & 1;
+                    tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg >> 1) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * CHUNK_BYTES;
+                    const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        wait_slot(slot);
+                        tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, 256), ID256, !first);
+                        first = false;
+                        if (NP == 3) tc::mma_ss(tmem + TM_ACC, a_desc(lo_addr, ks), b_desc(slot, 256), ID256, true);
+                        release_slot(slot);
+                        if (NP == 3) {
+                            wait_slot(slot);
+                            tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, 256), ID256, true);
+                            release_slot(slot);
+                        }
+                    }
+                    tc::mma_commit(&bars[BAR_SEG_EMPTY + buf]);
                 }
-                tc::mma_commit(&bars[BAR_F_EMPTY]);
+                wait_slot(slot);
+                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 256), ID256, true);
+                release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
-                // ---- layers 1, 2: A = h (TMEM), 16 steps + ones step (A from smem chunk pair 22)
+                // ---- layers 1, 2: A = h (TMEM, in place), 16 steps (x passes) + ones step
                 for (int layer = 1; layer <= 2; ++layer) {
                     wait_h();
-                    const uint32_t hin = (layer == 1) ? TM_HA : TM_HB;
                     for (int ks = 0; ks < 16; ++ks) {
                         wait_slot(slot);
-                        tc::mma_ts(tmem + TM_ACC, tmem + hin + ks * 8, b_desc(slot, 256), ID256, ks > 0);
+                        tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, 256), ID256, ks > 0);
+                        if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + ks * 8, b_desc(slot, 256), ID256, true);
                         release_slot(slot);
+                        if (NP == 3) {
+                            wait_slot(slot);
+                            tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, 256), ID256, true);
+                            release_slot(slot);
+                        }
                     }
                     wait_slot(slot);
-                    tc::mma_ss(tmem + TM_ACC, a_desc(f_addr, 22), b_desc(slot, 256), ID256, true);
+                    tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 256), ID256, true);
                     release_slot(slot);
                     tc::mma_commit(&bars[BAR_ACC_FULL]);
                 }
-                // ---- layer 3: N = 144: A = h2 (hA), then the per-point tile (PE | ones) from smem
+                // ---- layer 3: N = 144: A = h2 (hi [+ lo]), then the per-point tile (PE | ones) from smem
                 wait_h();
                 for (int ks = 0; ks < 16; ++ks) {
                     wait_slot(slot);
-                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HA + ks * 8, b_desc(slot, kN3), ID3, ks > 0);
+                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, kN3), ID3, ks > 0);
+                    if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + ks * 8, b_desc(slot, kN3), ID3, true);
                     release_slot(slot);
                 }
                 for (int ks = 0; ks < kPeK / 16; ++ks) {
@@ -289,15 +371,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                     release_slot(slot);
                 }
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
-                // ---- layer 4: N = 16: A = relu(w) (hB, K = 128) + ones step
+                // ---- layer 4: N = 16: A = relu(w) (fp16 in h_hi[0:64), K = 128) + ones step
                 wait_h();
                 for (int ks = 0; ks < 8; ++ks) {
                     wait_slot(slot);
-                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HB + ks * 8, b_desc(slot, kN4), ID4, ks > 0);
+                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, kN4), ID4, ks > 0);
                     release_slot(slot);
                 }
                 wait_slot(slot);
-                tc::mma_ss(tmem + TM_ACC, a_desc(f_addr, 22), b_desc(slot, kN4), ID4, true);
+                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, kN4), ID4, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
             }
@@ -314,8 +396,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         uint32_t acnt = 0;
         int it = 0;
         auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
-        // accumulator columns [0, ncols) -> relu -> fp16 pairs -> TMEM h buffer
-        auto relu_to_h = [&](uint32_t hout, int ncols) {
+        // accumulator columns [0, ncols) -> relu -> fp16 hi (+ lo) pairs -> TMEM h (in place: the layer's MMAs are done)
+        auto relu_to_h = [&](int ncols, bool with_lo) {
             for (int c = 0; c < ncols / 32; ++c) {
                 uint32_t v[32];
                 tc::tmem_ld32(lane_base + TM_ACC + c * 32, v);
@@ -323,7 +405,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 uint32_t h[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                tc::tmem_st16(lane_base + hout + c * 16, h);
+                tc::tmem_st16(lane_base + TM_HI + c * 16, h);
+                if (NP == 3 && with_lo) {
+                    uint32_t l[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        l[i] = tc::cvt_f16x2(f16lo_of(fmaxf(__uint_as_float(v[2 * i]), 0.f), h[i], 0),
+                                             f16lo_of(fmaxf(__uint_as_float(v[2 * i + 1]), 0.f), h[i], 1));
+                    tc::tmem_st16(lane_base + TM_LO + c * 16, l);
+                }
             }
             tc::tmem_st_wait();
         };
@@ -335,16 +425,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             const bool valid = ry < tc_.nr;
             const size_t ri = (size_t)tc_.b * P.n_rays + tc_.r0 + (valid ? ry : 0);
             // copy what this thread needs from the producer-owned geometry, then hand it back
-            tc::mbar_wait(&bars[BAR_F_FULL], it & 1);
+            tc::mbar_wait(&bars[BAR_GEOM_FULL], it & 1);
             const float4 gm = geom[row];
             zbuf[row] = gm.w;
             tc::mbar_arrive(&bars[BAR_GEOM_FREE]);
-
-            // ---- layer 0 epilogue -> hA
-            wait_acc();
-            relu_to_h(TM_HA, 256);
-            h_done();
             // ---- per-point tile of layer 3: [PE10(world xyz) 63 | 0 | PE4(viewdir) 27 | 0 | 1 | 1 | 0 | 0]
+            // (written while the producers gather; read by the MMA only after three more h_ready hand-offs;
+            //  the previous tile's layer-3 MMAs were complete before its last accumulator hand-off)
             {
                 auto store8 = [&](int j, const float* f) {
                     uint4 o;
@@ -370,14 +457,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 }
                 tc::fence_proxy_async();
             }
-            // ---- layer 1 -> hB, layer 2 -> hA
-            wait_acc();
-            relu_to_h(TM_HB, 256);
-            h_done();
-            wait_acc();
-            relu_to_h(TM_HA, 256);
-            h_done();
-            // ---- layer 3: colour hidden -> hB (fp16), sigma = acc[128] + acc[129]
+            // ---- layers 0, 1, 2 -> h (hi [+ lo]) in place
+            for (int layer = 0; layer < 3; ++layer) {
+                wait_acc();
+                relu_to_h(256, true);
+                h_done();
+            }
+            // ---- layer 3: sigma = acc[128] + acc[129]; colour hidden -> fp16 in h_hi[0:64)
             wait_acc();
             float sigma;
             {
@@ -386,7 +472,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 tc::tmem_ld_wait();
                 sigma = __uint_as_float(v[0]) + __uint_as_float(v[1]);
             }
-            relu_to_h(TM_HB, 128);
+            relu_to_h(128, false);
             h_done();
             // ---- layer 4: rgb logits = hi rows + lo rows
             wait_acc();
@@ -397,7 +483,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 rawbuf[row] = make_float4(__uint_as_float(v[0]) + __uint_as_float(v[3]), __uint_as_float(v[1]) + __uint_as_float(v[4]),
                                           __uint_as_float(v[2]) + __uint_as_float(v[5]), sigma);
             }
-            h_done();                                  // accumulator drained: next tile's layer 0 may start
+            h_done();                                  // accumulator drained: the next tile's layer 0 may start
             named_bar_sync(2, EPI_WARPS * 32);
             // ---- composite (a10): one warp per ray
             for (int g = warp; g < tc_.nr; g += EPI_WARPS) {
@@ -420,7 +506,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                     P.disp_map[rg] = disparity(o.depth, o.acc);
                 }
             }
-            named_bar_sync(2, EPI_WARPS * 32);     // rawbuf / zbuf reused by the next tile
+            named_bar_sync(2, EPI_WARPS * 32);     // rawbuf / zbuf are reused by the next tile
         }
     }
 
@@ -433,16 +519,23 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     }
 }
 
+template <int NP, typename VT>
+static cudaError_t launch(const RenderParams& p, int grid, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(render_tc_kernel<NP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    render_tc_kernel<NP, VT><<<grid, NT, SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
 }  // namespace tcr
 
 bool tc_available() { return true; }
 
-int launch_render_tc(const RenderParams& p_in, int volume_dtype, cudaStream_t stream) {
+int launch_render_tc(const RenderParams& p_in, int volume_dtype, int passes, cudaStream_t stream) {
     RenderParams p = p_in;
     const int S = p.n_samples;
-    if (volume_dtype != NB_DTYPE_F16) { set_error("NB_PRECISION_TC_FP16 needs an fp16-packed volume (NB_DTYPE_F16)"); return NB_ERR_UNSUPPORTED; }
     if (S > tcr::TP) {
-        set_error("NB_PRECISION_TC_FP16 supports n_samples <= 128 (got %d); use NB_PRECISION_FP32", S);
+        set_error("the tensor-core render kernel supports n_samples <= 128 (got %d); use NB_PRECISION_FP32", S);
         return NB_ERR_UNSUPPORTED;
     }
     p.rays_per_group = tcr::TP / S;
@@ -454,11 +547,9 @@ int launch_render_tc(const RenderParams& p_in, int volume_dtype, cudaStream_t st
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = p.n_groups < sms ? p.n_groups : sms;
     if (grid == 0) return NB_OK;
-    cudaError_t e = cudaFuncSetAttribute(tcr::render_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcr::SMEM_BYTES);
-    if (e == cudaSuccess) {
-        tcr::render_tc_kernel<<<grid, tcr::NT, tcr::SMEM_BYTES, stream>>>(p);
-        e = cudaGetLastError();
-    }
+    cudaError_t e;
+    if (passes == 3) e = (volume_dtype == NB_DTYPE_F32) ? tcr::launch<3, float>(p, grid, stream) : tcr::launch<3, __half>(p, grid, stream);
+    else e = (volume_dtype == NB_DTYPE_F32) ? tcr::launch<1, float>(p, grid, stream) : tcr::launch<1, __half>(p, grid, stream);
     if (e != cudaSuccess) { set_error("render_tc launch failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
     return NB_OK;
 }

@@ -17,7 +17,8 @@ import torch
 from neuralbody_b200 import capi
 from neuralbody_b200.lib.config import get_active_cfg
 
-_PRECISIONS = {"fp32": capi.NB_PRECISION_FP32, "tc_fp16": capi.NB_PRECISION_TC_FP16}
+_PRECISIONS = {"fp32": capi.NB_PRECISION_FP32, "tc_fp16": capi.NB_PRECISION_TC_FP16,
+               "tc_fp16x3": capi.NB_PRECISION_TC_FP16X3}
 
 
 def _ptr(t):
@@ -47,7 +48,7 @@ class Renderer:
         return cfg[name] if name in cfg else default
 
     def _precision(self):
-        name = str(self._opt("render_precision", "tc_fp16"))
+        name = str(self._opt("render_precision", "tc_fp16x3"))
         if name not in _PRECISIONS:
             raise ValueError("cfg.render_precision must be one of %s" % sorted(_PRECISIONS))
         return _PRECISIONS[name]
@@ -55,7 +56,8 @@ class Renderer:
     def _volume_dtype(self, precision):
         name = str(self._opt("render_volume_dtype", "auto"))
         if name == "auto":
-            return capi.NB_DTYPE_F32 if precision == capi.NB_PRECISION_FP32 else capi.NB_DTYPE_F16
+            # the fp16 volume alone costs ~1e-3 of depth_map parity: only the 1-pass mode gathers from it
+            return capi.NB_DTYPE_F16 if precision == capi.NB_PRECISION_TC_FP16 else capi.NB_DTYPE_F32
         return {"fp32": capi.NB_DTYPE_F32, "fp16": capi.NB_DTYPE_F16}[name]
 
     # ------------------------------------------------------------------ a2 (host API parity)

@@ -2,7 +2,9 @@
 nb_render_fwd) against (1) the golden vectors made by the unmodified reference and (2) the CPU
 oracle on seeded inputs; plus size-independent properties at full size.
 Tolerance (BASELINE.json north_star): <= 1e-3 abs on rgb_map / depth_map for the tensor-core
-path; the exact-fp32 kernel is held to 1e-4."""
+path (tc_fp16x3, the default); the exact-fp32 kernel is held to 1e-4.  The 1-pass fp16 mode
+(tc_fp16) is an opt-in speed mode that does NOT meet the gate on depth_map (one fp16 rounding of
+any density-path operand costs ~1e-3); it is only checked against a documented 6e-3 envelope."""
 import numpy as np
 import pytest
 import torch
@@ -13,28 +15,29 @@ import gpu_utils as G
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "tc_fp16": 1e-3}
+TOL = {"fp32": 1e-4, "tc_fp16x3": 1e-3, "tc_fp16": 6e-3}
+ALL_PREC = ["fp32", "tc_fp16x3", "tc_fp16"]
 
 
 def _precisions():
     from neuralbody_b200 import capi
     lib = capi.load()
-    return ["fp32"] + (["tc_fp16"] if lib.nb_has_precision(capi.NB_PRECISION_TC_FP16) else [])
+    return ["fp32"] + (["tc_fp16", "tc_fp16x3"] if lib.nb_has_precision(capi.NB_PRECISION_TC_FP16X3) else [])
 
 
 @pytest.mark.parametrize("name", list(golden_cases.CASES))
-@pytest.mark.parametrize("precision", ["fp32", "tc_fp16"])
+@pytest.mark.parametrize("precision", ALL_PREC)
 def test_golden_parity(name, precision):
     if precision not in _precisions():
         pytest.skip("precision %s not built" % precision)
     scene, rkw, gold = golden_case(name)
     out = G.render_product(scene, precision=precision, **rkw)
-    rep = G.compare(out, gold, TOL[precision], nan_mismatch_frac=0.0 if precision == "fp32" else 0.01,
+    rep = G.compare(out, gold, TOL[precision], nan_mismatch_frac=0.0 if precision != "tc_fp16" else 0.01,
                     label="%s/%s" % (name, precision))
     print(name, precision, rep)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tc_fp16"])
+@pytest.mark.parametrize("precision", ALL_PREC)
 def test_raw_decoder_output_vs_oracle(precision):
     """Per-sample (rgb logits, sigma) against calculate_density_color of the oracle."""
     if precision not in _precisions():
@@ -49,7 +52,9 @@ def test_raw_decoder_output_vs_oracle(precision):
                                     vd[:, :, None].repeat(1, 1, S, 1).view(B, n * S, 3), scene["volumes"], sp,
                                     scene["voxel_size"]).view(B, n, S, 4)
     d = (out["raw"] - raw).abs()
-    tol = 2e-4 if precision == "fp32" else 8e-2   # sigma reaches +-30, logits +-8
+    tol = {"fp32": 2e-4, "tc_fp16x3": 2e-2, "tc_fp16": 8e-2}[precision]   # sigma reaches +-30, logits +-8
+    if precision == "tc_fp16x3":   # the density path is ~fp32-accurate in the 3-pass mode
+        assert float(d[..., 3].max()) < 5e-4, float(d[..., 3].max())
     assert float(d.max()) < tol, float(d.max())
 
 
