@@ -1,0 +1,66 @@
+"""CPU, gloo, world_size 2: the ray-sharding + one-all-gather host logic of neuralbody_b200/dist.py.
+The per-rank render function is the oracle (tests may use it as a checker/stand-in); the check is the
+one SURVEY 4(v) asks for: the sharded result equals the single-process result BIT FOR BIT."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n_rays, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from neuralbody_b200 import synth, dist as nbdist
+        from oracle import neuralbody_oracle as O
+        torch.set_num_threads(1)
+        scene = synth.make_scene(H=16, W=16, scale=0.25, all_hit=True, n_rays=n_rays)
+
+        def render_fn(batch):
+            sc = dict(scene)
+            sc.update({k: batch[k] for k in ("ray_o", "ray_d", "near", "far")})
+            return O.render(sc, n_samples=16)
+
+        batch = {k: scene[k] for k in ("coord", "out_sh", "bounds", "R", "Th", "latent_index", "ray_o", "ray_d", "near", "far")}
+        full = nbdist.render_sharded(render_fn, batch)
+        torch.save({k: v.clone() for k, v in full.items()}, os.path.join(out_dir, "rank%d.pt" % rank))
+        if rank == 0:
+            torch.save(render_fn(batch), os.path.join(out_dir, "single.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_rays", [40, 37])     # even split and a ragged last slab (padding dropped)
+def test_ray_sharded_render_equals_single_process(tmp_path, n_rays):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), n_rays, str(tmp_path)), nprocs=world, join=True)
+    single = torch.load(os.path.join(tmp_path, "single.pt"))
+    for r in range(world):
+        got = torch.load(os.path.join(tmp_path, "rank%d.pt" % r))
+        for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
+            assert got[k].shape == single[k].shape, k
+            assert torch.equal(torch.nan_to_num(got[k]), torch.nan_to_num(single[k])), (r, k)
+
+
+def test_shard_bounds_cover_all_rays_once():
+    from neuralbody_b200.dist import shard_bounds
+    for n in (0, 1, 7, 262144, 262145):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                a, b, per = shard_bounds(n, r, world)
+                assert b - a <= per
+                seen += list(range(a, b))
+            assert seen == list(range(n))
