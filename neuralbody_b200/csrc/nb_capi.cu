@@ -30,9 +30,11 @@ __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half
 
 template <typename OT>
 __global__ void __launch_bounds__(256) pack_volume_kernel(const float* __restrict__ src, OT* __restrict__ dst, int C,
-                                                          size_t nvox /* D*H*W */, int batch) {
-    // tile: 32 voxels x 32 channels
+                                                          size_t nvox /* D*H*W */, int batch,
+                                                          unsigned* __restrict__ voxbits, size_t voxwords) {
+    // tile: 32 voxels x 32 channels.  Also ORs "this voxel has a non-zero channel" into voxbits.
     __shared__ float tile[32][33];
+    __shared__ unsigned tilemask;
     const size_t tiles_v = (nvox + 31) / 32;
     const int tiles_c = (C + 31) / 32;
     const size_t total = tiles_v * tiles_c * batch;
@@ -44,13 +46,18 @@ __global__ void __launch_bounds__(256) pack_volume_kernel(const float* __restric
         const size_t tv = rem % tiles_v;
         const float* s = src + (size_t)b * C * nvox;
         OT* d = dst + (size_t)b * C * nvox;
+        if (threadIdx.x == 0) tilemask = 0u;
+        bool nz = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = tc * 32 + ty + 8 * j;
             const size_t v = tv * 32 + tx;
-            tile[ty + 8 * j][tx] = (c < C && v < nvox) ? __ldg(s + (size_t)c * nvox + v) : 0.f;
+            const float val = (c < C && v < nvox) ? __ldg(s + (size_t)c * nvox + v) : 0.f;
+            nz |= (val != 0.f);
+            tile[ty + 8 * j][tx] = val;
         }
         __syncthreads();
+        if (nz) atomicOr(&tilemask, 1u << tx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const size_t v = tv * 32 + ty + 8 * j;
@@ -58,6 +65,37 @@ __global__ void __launch_bounds__(256) pack_volume_kernel(const float* __restric
             if (c < C && v < nvox) d[v * C + c] = cvt_out<OT>(tile[tx][ty + 8 * j]);
         }
         __syncthreads();
+        if (threadIdx.x == 0 && tilemask) atomicOr(voxbits + (size_t)b * voxwords + tv, tilemask);
+    }
+}
+
+// Cell occupancy: cell (cx,cy,cz), cx in [0,W] etc., is the trilinear cell whose low corner is voxel
+// (cx-1, cy-1, cz-1); its bit is the OR of its (in-range) 8 corner voxels.  A sample whose cell bit is 0
+// interpolates EXACT zeros at this level (SparseConvNet's .dense() is exactly 0 off the active set), so the
+// gather can skip its 8 corner loads without changing a single bit of the result.
+__global__ void cell_occupancy_kernel(const unsigned* __restrict__ voxbits, unsigned* __restrict__ cellbits, int D, int H,
+                                      int W, size_t voxwords, size_t cellwords, int batch) {
+    const size_t ncell = (size_t)(D + 1) * (H + 1) * (W + 1);
+    const size_t padded = (ncell + 31) / 32 * 32;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < padded * batch; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / padded);
+        const size_t c = i % padded;
+        bool occ = false;
+        if (c < ncell) {
+            const int cx = (int)(c % (W + 1)), cy = (int)((c / (W + 1)) % (H + 1)), cz = (int)(c / ((size_t)(W + 1) * (H + 1)));
+            const unsigned* vb = voxbits + (size_t)b * voxwords;
+            for (int dz = -1; dz <= 0; ++dz)
+                for (int dy = -1; dy <= 0; ++dy)
+                    for (int dx = -1; dx <= 0; ++dx) {
+                        const int x = cx + dx, y = cy + dy, z = cz + dz;
+                        if (x >= 0 && x < W && y >= 0 && y < H && z >= 0 && z < D) {
+                            const size_t v = ((size_t)z * H + y) * W + x;
+                            occ |= (vb[v >> 5] >> (v & 31)) & 1u;
+                        }
+                    }
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, occ);
+        if ((threadIdx.x & 31) == 0) cellbits[(size_t)b * cellwords + (c >> 5)] = word;
     }
 }
 
@@ -229,8 +267,22 @@ size_t nb_packed_volume_level_offset(const int dims[NB_NUM_LEVELS][4], int batch
     return off;
 }
 
+static size_t vox_words(const int d[4]) { return ((size_t)d[1] * d[2] * d[3] + 31) / 32; }
+static size_t cell_words(const int d[4]) { return ((size_t)(d[1] + 1) * (d[2] + 1) * (d[3] + 1) + 31) / 32; }
+// occupancy region after the four levels: per level [voxel bits (scratch)][cell bits], 256-B aligned each
+static size_t occ_offset(const int dims[NB_NUM_LEVELS][4], int batch, int dtype, int level, int cell) {
+    size_t off = nb_packed_volume_level_offset(dims, batch, dtype, NB_NUM_LEVELS);
+    for (int l = 0; l < NB_NUM_LEVELS; ++l) {
+        if (l == level && !cell) return off;
+        off += align256((size_t)batch * vox_words(dims[l]) * 4);
+        if (l == level && cell) return off;
+        off += align256((size_t)batch * cell_words(dims[l]) * 4);
+    }
+    return off;
+}
+
 size_t nb_packed_volume_bytes(const int dims[NB_NUM_LEVELS][4], int batch, int dtype) {
-    return nb_packed_volume_level_offset(dims, batch, dtype, NB_NUM_LEVELS);
+    return occ_offset(dims, batch, dtype, NB_NUM_LEVELS, 0);
 }
 
 int nb_pack_volume(const nb_volume_level levels[NB_NUM_LEVELS], int batch, int dtype, void* out_blob, size_t out_bytes,
@@ -247,15 +299,23 @@ int nb_pack_volume(const nb_volume_level levels[NB_NUM_LEVELS], int batch, int d
     }
     if (out_bytes < nb_packed_volume_bytes(dims, batch, dtype)) { set_error("nb_pack_volume: out_bytes too small"); return NB_ERR_BAD_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
+    const size_t occ0 = occ_offset(dims, batch, dtype, 0, 0);
+    cudaMemsetAsync((char*)out_blob + occ0, 0, nb_packed_volume_bytes(dims, batch, dtype) - occ0, st);
     for (int l = 0; l < NB_NUM_LEVELS; ++l) {
         const size_t nvox = (size_t)levels[l].D * levels[l].H * levels[l].W;
         const size_t tiles = ((nvox + 31) / 32) * ((levels[l].C + 31) / 32) * batch;
         const int grid = (int)(tiles < 148 * 16 ? tiles : 148 * 16);
         char* dst = (char*)out_blob + nb_packed_volume_level_offset(dims, batch, dtype, l);
+        unsigned* vb = (unsigned*)((char*)out_blob + occ_offset(dims, batch, dtype, l, 0));
+        unsigned* cb = (unsigned*)((char*)out_blob + occ_offset(dims, batch, dtype, l, 1));
         if (dtype == NB_DTYPE_F16)
-            pack_volume_kernel<__half><<<grid, 256, 0, st>>>(levels[l].data, (__half*)dst, levels[l].C, nvox, batch);
+            pack_volume_kernel<__half><<<grid, 256, 0, st>>>(levels[l].data, (__half*)dst, levels[l].C, nvox, batch, vb, vox_words(dims[l]));
         else
-            pack_volume_kernel<float><<<grid, 256, 0, st>>>(levels[l].data, (float*)dst, levels[l].C, nvox, batch);
+            pack_volume_kernel<float><<<grid, 256, 0, st>>>(levels[l].data, (float*)dst, levels[l].C, nvox, batch, vb, vox_words(dims[l]));
+        const size_t ncellp = cell_words(dims[l]) * 32 * batch;
+        const int cgrid = (int)((ncellp + 255) / 256 < 148 * 8 ? (ncellp + 255) / 256 : 148 * 8);
+        cell_occupancy_kernel<<<cgrid, 256, 0, st>>>(vb, cb, levels[l].D, levels[l].H, levels[l].W, vox_words(dims[l]),
+                                                     cell_words(dims[l]), batch);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("nb_pack_volume: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
@@ -323,6 +383,8 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
         p.lvl_C[l] = a->level_dims[l][0]; p.lvl_D[l] = a->level_dims[l][1]; p.lvl_H[l] = a->level_dims[l][2]; p.lvl_W[l] = a->level_dims[l][3];
         p.lvl_off[l] = nb_packed_volume_level_offset(a->level_dims, a->batch, a->volume_dtype, l);
         p.lvl_bstride[l] = (size_t)p.lvl_C[l] * p.lvl_D[l] * p.lvl_H[l] * p.lvl_W[l];
+        p.occ_off[l] = occ_offset(a->level_dims, a->batch, a->volume_dtype, l, 1);
+        p.occ_bstride[l] = cell_words(a->level_dims[l]);
     }
     p.volume = a->volume_blob;
     const char* wb = (const char*)a->weights_blob;

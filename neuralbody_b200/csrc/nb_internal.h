@@ -21,6 +21,8 @@ struct RenderParams {
     int   lvl_C[4], lvl_D[4], lvl_H[4], lvl_W[4];
     size_t lvl_off[4];         // byte offset of level l inside the volume blob
     size_t lvl_bstride[4];     // ELEMENT stride between frames of level l
+    size_t occ_off[4];         // byte offset of level l's cell-occupancy bitmap inside the volume blob
+    size_t occ_bstride[4];     // 32-bit words per frame of that bitmap
     const void* volume;
     const float* wf32;         // fp32 weight section
     const __half* wf16;        // fp16 weight stream (common steps)

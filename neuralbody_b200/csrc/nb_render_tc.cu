@@ -5,7 +5,7 @@
 // 4-level trilinear gather, decoder MLP (latent_xyzc.py:99-121, folded as in nb_layout.h), PE, composite.
 // Nothing per-point touches global memory between the gather and the 24-byte per-ray result.
 //
-//   producer warps (12) : geometry, then the trilinear gather from the channels-last volume into the fp16 A
+//   producer warps (16) : geometry, then the trilinear gather from the channels-last volume into the fp16 A
 //                         operand of layer 0, written in the tcgen05 K-major no-swizzle layout into a 2-deep
 //                         ring of 64-channel K SEGMENTS (layer 0 is K-pipelined against the gather)
 //   loader warp         : streams the decoder weights (fp16, one pre-packed K=16 step per bulk copy, in
@@ -39,10 +39,10 @@ constexpr int SEG_CHUNKS = 8;                 // 64 channels per segment
 constexpr int NUM_SEGS = 6;                   // 44 feature chunks = 5 x 8 + 4
 constexpr int SEG_BYTES = 2 * SEG_CHUNKS * CHUNK_BYTES;   // hi plane + lo plane = 32 KB
 constexpr int PE_CHUNKS = 12;                 // 96-wide per-point tile of layer 3
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 12;
-constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;   // 576
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
+constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;   // 704
 constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int NSUB = PROD_WARPS / 4;          // lanes sharing one point (each takes chunks j % NSUB == sub)
+constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);   // an 8-lane group owns points g, g+64
 
 // shared-memory map (bytes)
 constexpr int OFF_SEG = 0;                                         // 2 x 32 KB
@@ -85,27 +85,32 @@ __device__ __forceinline__ TileCoord tile_coord(const RenderParams& P, int tile)
     return t;
 }
 
-// One gather unit: 8 corners x 16 bytes -> NCH channels accumulated in fp32.
-template <typename VT> struct Unit;
-template <> struct Unit<__half> {
-    static constexpr int NCH = 8;
-    static __device__ __forceinline__ void fma(float (&acc)[8], const uint4& v, float w) {
-        const __half2* h = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h[i]);
-            acc[2 * i] = fmaf(f.x, w, acc[2 * i]);
-            acc[2 * i + 1] = fmaf(f.y, w, acc[2 * i + 1]);
-        }
+// Gather granule: one lane accumulates 4 consecutive channels of one corner vector; the 8 lanes of a group
+// cover a 32-channel unit, so a group's load of one corner is one contiguous 128-byte (fp32) / 64-byte (fp16)
+// run = a single L1 wavefront, instead of 8 scattered 16-byte pieces.
+template <typename VT> struct Quad;
+template <> struct Quad<float> {
+    using raw = uint4;
+    static __device__ __forceinline__ raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    static __device__ __forceinline__ raw load(const float* p) { return ldg_nc_v4(p); }
+    static __device__ __forceinline__ void fma(float (&a)[4], const raw& v, float w) {
+        a[0] = fmaf(__uint_as_float(v.x), w, a[0]); a[1] = fmaf(__uint_as_float(v.y), w, a[1]);
+        a[2] = fmaf(__uint_as_float(v.z), w, a[2]); a[3] = fmaf(__uint_as_float(v.w), w, a[3]);
     }
 };
-template <> struct Unit<float> {
-    static constexpr int NCH = 4;
-    static __device__ __forceinline__ void fma(float (&acc)[4], const uint4& v, float w) {
-        acc[0] = fmaf(__uint_as_float(v.x), w, acc[0]);
-        acc[1] = fmaf(__uint_as_float(v.y), w, acc[1]);
-        acc[2] = fmaf(__uint_as_float(v.z), w, acc[2]);
-        acc[3] = fmaf(__uint_as_float(v.w), w, acc[3]);
+template <> struct Quad<__half> {
+    using raw = uint2;
+    static __device__ __forceinline__ raw zero() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ raw load(const __half* p) {
+        uint2 r;
+        asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        return r;
+    }
+    static __device__ __forceinline__ void fma(float (&a)[4], const raw& v, float w) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        a[0] = fmaf(f0.x, w, a[0]); a[1] = fmaf(f0.y, w, a[1]);
+        a[2] = fmaf(f1.x, w, a[2]); a[3] = fmaf(f1.y, w, a[3]);
     }
 };
 
@@ -151,11 +156,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         float4* grid = reinterpret_cast<float4*>(smem + OFF_GRID);
         FrameXf* xf = reinterpret_cast<FrameXf*>(smem + OFF_XF);
         const unsigned char* volbase = reinterpret_cast<const unsigned char*>(P.volume);
-        // this lane's fixed point and chunk residue: quarter-warps = 8 consecutive points of one chunk
-        const int gid = pw * 4 + (lane >> 3);
-        const int p = (gid & 15) * 8 + (lane & 7);
-        const int sub = gid >> 4;
-        constexpr int NCH = Unit<VT>::NCH;
+        // an 8-lane group owns the tile rows {grp, grp + 64}; lane t of the group owns channels 4t..4t+3 of
+        // every 32-channel unit.  Units in K order: u0 = L1, u1-2 = L2, u3-6 = L3, u7-10 = L4; segment s = units 2s, 2s+1.
+        const int grp = pw * 4 + (lane >> 3);
+        const int t = lane & 7;
+        const uint32_t* occ_base = reinterpret_cast<const uint32_t*>(volbase);
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc_ = tile_coord(P, tile);
@@ -189,65 +194,73 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             named_bar_sync(1, PROD_THREADS);
             if (lane == 0) tc::mbar_arrive(&bars[BAR_GEOM_FULL]);
 
-            const float4 g = grid[p];
-            int cur_lvl = -1;
-            uint32_t coff[8];    // element offset of each corner's voxel inside the level (0 when out of range)
-            float cw[8];         // corner weight (0 when out of range)
+            float4 g[PTS_PER_GROUP];
+#pragma unroll
+            for (int pp = 0; pp < PTS_PER_GROUP; ++pp) g[pp] = grid[grp + 64 * pp];
+            uint32_t coff[PTS_PER_GROUP][8];   // element offset of each corner voxel inside the level
+            float cw[PTS_PER_GROUP][8];        // corner weight (0 when out of range)
+            bool occupied[PTS_PER_GROUP];      // cell-occupancy bit: false => this level interpolates exact zeros
             const VT* vol = nullptr;
+            int cur_lvl = -1;
             for (int seg = 0; seg < NUM_SEGS; ++seg) {
                 const uint32_t gseg = (uint32_t)it * NUM_SEGS + seg;
                 const uint32_t buf = gseg & 1;
                 tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg >> 1) & 1) ^ 1);
                 unsigned char* hi_plane = smem + OFF_SEG + buf * SEG_BYTES;
                 unsigned char* lo_plane = hi_plane + SEG_CHUNKS * CHUNK_BYTES;
-                const int nchunks = (seg == NUM_SEGS - 1) ? 4 : SEG_CHUNKS;
-                for (int jj = sub; jj < nchunks; jj += NSUB) {
-                    const int j = seg * SEG_CHUNKS + jj;          // feature chunk 0..43
+                const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
+                for (int uu = 0; uu < nunits; ++uu) {
+                    const int unit = 2 * seg + uu;
                     int lvl, c0;
-                    if (j < 4) { lvl = 0; c0 = j * 8; }
-                    else if (j < 12) { lvl = 1; c0 = (j - 4) * 8; }
-                    else if (j < 28) { lvl = 2; c0 = (j - 12) * 8; }
-                    else { lvl = 3; c0 = (j - 28) * 8; }
+                    if (unit < 1) { lvl = 0; c0 = 0; }
+                    else if (unit < 3) { lvl = 1; c0 = (unit - 1) * 32; }
+                    else if (unit < 7) { lvl = 2; c0 = (unit - 3) * 32; }
+                    else { lvl = 3; c0 = (unit - 7) * 32; }
                     if (lvl != cur_lvl) {
                         cur_lvl = lvl;
                         const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
-                        Corners cn;
-                        corner_setup(unnormalize(g.x, W), unnormalize(g.y, H), unnormalize(g.z, D), W, H, D, cn);
                         vol = reinterpret_cast<const VT*>(volbase + P.lvl_off[lvl]) + (size_t)tc_.b * P.lvl_bstride[lvl];
+                        const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)tc_.b * P.occ_bstride[lvl];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
-                            const bool ok = corner_valid(cn, dx, dy, dz, W, H, D);
-                            cw[c] = ok ? corner_weight(cn, dx, dy, dz) : 0.f;
-                            coff[c] = ok ? (uint32_t)((((cn.z0 + dz) * H + (cn.y0 + dy)) * W + (cn.x0 + dx)) * C) : 0u;
+                        for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
+                            Corners cn;
+                            corner_setup(unnormalize(g[pp].x, W), unnormalize(g[pp].y, H), unnormalize(g[pp].z, D), W, H, D, cn);
+                            occupied[pp] = false;
+                            if (cn.x0 != -2) {
+                                const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
+                                occupied[pp] = (__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u;
+                            }
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const int dx = c & 1, dy = (c >> 1) & 1, dz = c >> 2;
+                                const bool ok = occupied[pp] && corner_valid(cn, dx, dy, dz, W, H, D);
+                                cw[pp][c] = ok ? corner_weight(cn, dx, dy, dz) : 0.f;
+                                coff[pp][c] = ok ? (uint32_t)((((cn.z0 + dz) * H + (cn.y0 + dy)) * W + (cn.x0 + dx)) * C) : 0u;
+                            }
                         }
                     }
-                    float acc[8];
 #pragma unroll
-                    for (int u = 0; u < 8 / NCH; ++u) {
-                        uint4 v[8];
+                    for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
+                        const int p = grp + 64 * pp;
+                        float a[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (occupied[pp]) {
+                            typename Quad<VT>::raw v[8];
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) v[c] = ldg_nc_v4(vol + coff[c] + c0 + u * NCH);
-                        float a[NCH];
+                            for (int c = 0; c < 8; ++c)
+                                v[c] = (cw[pp][c] != 0.f) ? Quad<VT>::load(vol + coff[pp][c] + c0 + 4 * t) : Quad<VT>::zero();
 #pragma unroll
-                        for (int i = 0; i < NCH; ++i) a[i] = 0.f;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) Unit<VT>::fma(a, v[c], cw[c]);   // ATen order: x fastest
-#pragma unroll
-                        for (int i = 0; i < NCH; ++i) acc[u * NCH + i] = a[i];
-                    }
-                    uint4 hi;
-                    hi.x = tc::cvt_f16x2(acc[0], acc[1]); hi.y = tc::cvt_f16x2(acc[2], acc[3]);
-                    hi.z = tc::cvt_f16x2(acc[4], acc[5]); hi.w = tc::cvt_f16x2(acc[6], acc[7]);
-                    const int so = (jj * 16 + (p >> 3)) * 128 + (p & 7) * 16;
-                    *reinterpret_cast<uint4*>(hi_plane + so) = hi;
-                    if (NP == 3) {
-                        uint4 lo;
-                        lo.x = tc::cvt_f16x2(f16lo_of(acc[0], hi.x, 0), f16lo_of(acc[1], hi.x, 1));
-                        lo.y = tc::cvt_f16x2(f16lo_of(acc[2], hi.y, 0), f16lo_of(acc[3], hi.y, 1));
-                        lo.z = tc::cvt_f16x2(f16lo_of(acc[4], hi.z, 0), f16lo_of(acc[5], hi.z, 1));
-                        lo.w = tc::cvt_f16x2(f16lo_of(acc[6], hi.w, 0), f16lo_of(acc[7], hi.w, 1));
-                        *reinterpret_cast<uint4*>(lo_plane + so) = lo;
+                            for (int c = 0; c < 8; ++c) Quad<VT>::fma(a, v[c], cw[pp][c]);   // ATen order: x fastest
+                        }
+                        uint2 hi;
+                        hi.x = tc::cvt_f16x2(a[0], a[1]); hi.y = tc::cvt_f16x2(a[2], a[3]);
+                        const int so = ((uu * 4 + (t >> 1)) * 16 + (p >> 3)) * 128 + (p & 7) * 16 + (t & 1) * 8;
+                        *reinterpret_cast<uint2*>(hi_plane + so) = hi;
+                        if (NP == 3) {
+                            uint2 lo;
+                            lo.x = tc::cvt_f16x2(f16lo_of(a[0], hi.x, 0), f16lo_of(a[1], hi.x, 1));
+                            lo.y = tc::cvt_f16x2(f16lo_of(a[2], hi.y, 0), f16lo_of(a[3], hi.y, 1));
+                            *reinterpret_cast<uint2*>(lo_plane + so) = lo;
+                        }
                     }
                 }
                 tc::fence_proxy_async();
@@ -398,21 +411,21 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
         // accumulator columns [0, ncols) -> relu -> fp16 hi (+ lo) pairs -> TMEM h (in place: the layer's MMAs are done)
         auto relu_to_h = [&](int ncols, bool with_lo) {
-            for (int c = 0; c < ncols / 32; ++c) {
-                uint32_t v[32];
-                tc::tmem_ld32(lane_base + TM_ACC + c * 32, v);
+            for (int c = 0; c < ncols / 16; ++c) {
+                uint32_t v[16];
+                tc::tmem_ld16(lane_base + TM_ACC + c * 16, v);
                 tc::tmem_ld_wait();
-                uint32_t h[16];
+                uint32_t h[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                tc::tmem_st16(lane_base + TM_HI + c * 16, h);
+                for (int i = 0; i < 8; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                tc::tmem_st8(lane_base + TM_HI + c * 8, h);
                 if (NP == 3 && with_lo) {
-                    uint32_t l[16];
+                    uint32_t l[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
+                    for (int i = 0; i < 8; ++i)
                         l[i] = tc::cvt_f16x2(f16lo_of(fmaxf(__uint_as_float(v[2 * i]), 0.f), h[i], 0),
                                              f16lo_of(fmaxf(__uint_as_float(v[2 * i + 1]), 0.f), h[i], 1));
-                    tc::tmem_st16(lane_base + TM_LO + c * 16, l);
+                    tc::tmem_st8(lane_base + TM_LO + c * 8, l);
                 }
             }
             tc::tmem_st_wait();
@@ -433,28 +446,17 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             // (written while the producers gather; read by the MMA only after three more h_ready hand-offs;
             //  the previous tile's layer-3 MMAs were complete before its last accumulator hand-off)
             {
-                auto store8 = [&](int j, const float* f) {
-                    uint4 o;
-                    o.x = tc::cvt_f16x2(f[0], f[1]); o.y = tc::cvt_f16x2(f[2], f[3]);
-                    o.z = tc::cvt_f16x2(f[4], f[5]); o.w = tc::cvt_f16x2(f[6], f[7]);
-                    *reinterpret_cast<uint4*>(PE + (j * 16 + (row >> 3)) * 128 + (row & 7) * 16) = o;
+                __half* peh = reinterpret_cast<__half*>(PE);
+                // element (row, k) of the 96-wide tile: chunk k/8, 8x8 core matrix (row/8), row%8, k%8
+                auto put = [&](int k, float v) {
+                    peh[((k >> 3) * 16 + (row >> 3)) * 64 + (row & 7) * 8 + (k & 7)] = __float2half_rn(v);
                 };
-                {
-                    float pf[64];
-                    positional_embed<10>(gm.x, gm.y, gm.z, [&](int j, float v) { pf[j] = v; });
-                    pf[63] = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) store8(j, pf + 8 * j);
-                }
-                {
-                    float pf[32];
-                    const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
-                    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-                    positional_embed<4>(__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm), [&](int j, float v) { pf[j] = v; });
-                    pf[27] = 0.f; pf[28] = 1.f; pf[29] = 1.f; pf[30] = 0.f; pf[31] = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) store8(8 + j, pf + 8 * j);
-                }
+                positional_embed<10>(gm.x, gm.y, gm.z, [&](int j, float v) { put(j, v); });
+                put(63, 0.f);
+                const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
+                const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                positional_embed<4>(__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm), [&](int j, float v) { put(64 + j, v); });
+                put(91, 0.f); put(92, 1.f); put(93, 1.f); put(94, 0.f); put(95, 0.f);
                 tc::fence_proxy_async();
             }
             // ---- layers 0, 1, 2 -> h (hi [+ lo]) in place
