@@ -125,6 +125,8 @@ typedef struct nb_render_args {
     float* weights;        /* device (B,n,S) or NULL to skip */
     float* depth_map;      /* device (B,n)   */
     float* raw;            /* device (B,n,S,4) decoder output (rgb logits, sigma) or NULL; debugging / parity */
+    unsigned long long* trace; /* device, 4 x 4096 u64, or NULL: per-role (code<<48 | SM clock) timeline of CTA 0
+                                  (tensor-core kernel only; diagnostics, see tools/trace_timeline.py) */
 } nb_render_args;
 
 int nb_render_fwd(const nb_render_args* args, void* stream);

@@ -393,7 +393,7 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     p.bc = (const float*)(wb + kBcByteOffset);
     p.wframe = (const __half*)(wb + frame_step_byte_offset(a->batch));
     p.white_bkgd = a->white_bkgd;
-    p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw;
+    p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace;
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
 
     cudaStream_t st = (cudaStream_t)stream;

@@ -76,6 +76,19 @@ __device__ __forceinline__ float f16lo_of(float x, uint32_t hi_pair, int which) 
     return x - (which ? __high2float(h) : __low2float(h));
 }
 
+// Diagnostics: CTA 0 records (code << 48 | clock) per role into P.trace[role * 4096 + n] (first ~40 tiles).
+struct Tracer {
+    unsigned long long* buf;
+    int n;
+    __device__ __forceinline__ void init(unsigned long long* base, int role) {
+        buf = (base && blockIdx.x == 0) ? base + role * 4096 : nullptr;
+        n = 0;
+    }
+    __device__ __forceinline__ void ev(int code) {
+        if (buf && n < 4096) buf[n++] = ((unsigned long long)code << 48) | ((unsigned long long)clock64() & 0xFFFFFFFFFFFFull);
+    }
+};
+
 struct TileCoord { int b, r0, nr; };
 __device__ __forceinline__ TileCoord tile_coord(const RenderParams& P, int tile) {
     TileCoord t;
@@ -161,6 +174,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         const int grp = pw * 4 + (lane >> 3);
         const int t = lane & 7;
         const uint32_t* occ_base = reinterpret_cast<const uint32_t*>(volbase);
+        Tracer tr;
+        tr.init((pw == 0 && lane == 0) ? P.trace : nullptr, 0);
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const TileCoord tc_ = tile_coord(P, tile);
@@ -193,6 +208,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             }
             named_bar_sync(1, PROD_THREADS);
             if (lane == 0) tc::mbar_arrive(&bars[BAR_GEOM_FULL]);
+            tr.ev(1);                                            // geometry done
 
             float4 g[PTS_PER_GROUP];
 #pragma unroll
@@ -206,6 +222,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 const uint32_t gseg = (uint32_t)it * NUM_SEGS + seg;
                 const uint32_t buf = gseg & 1;
                 tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg >> 1) & 1) ^ 1);
+                tr.ev(10 + seg);                                 // segment buffer free
                 unsigned char* hi_plane = smem + OFF_SEG + buf * SEG_BYTES;
                 unsigned char* lo_plane = hi_plane + SEG_CHUNKS * CHUNK_BYTES;
                 const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
@@ -266,6 +283,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 tc::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&bars[BAR_SEG_FULL + buf]);
+                tr.ev(20 + seg);                                 // segment gathered (this warp)
             }
         }
     }
@@ -307,6 +325,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         if (lane == 0) {
             uint32_t cnt = 0, hcnt = 0;
             int it = 0;
+            Tracer tr;
+            tr.init(P.trace, 1);
             const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
             const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
             constexpr uint32_t ID256 = tc::make_idesc_f16(128, 256), ID3 = tc::make_idesc_f16(128, kN3),
@@ -324,6 +344,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 uint32_t slot;
                 if (it > 0) wait_h();                 // previous tile's last epilogue has drained the accumulator
+                tr.ev(1);                             // tile begin
                 // ---- layer 0: A = gathered features, K-pipelined over 6 segments of the smem ring
                 bool first = true;
                 for (int seg = 0; seg < NUM_SEGS; ++seg) {
@@ -331,6 +352,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                     const uint32_t buf = gseg & 1;
                     tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg >> 1) & 1);
                     tc::tc_fence_after();
+                    tr.ev(10 + seg);                  // segment available
                     const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * CHUNK_BYTES;
                     const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
                     for (int ks = 0; ks < nks; ++ks) {
@@ -351,9 +373,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 256), ID256, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(20);                            // layer 0 issued
                 // ---- layers 1, 2: A = h (TMEM, in place), 16 steps (x passes) + ones step
                 for (int layer = 1; layer <= 2; ++layer) {
                     wait_h();
+                    tr.ev(30 + layer);                // h ready for this layer
                     for (int ks = 0; ks < 16; ++ks) {
                         wait_slot(slot);
                         tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, 256), ID256, ks > 0);
@@ -369,9 +393,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                     tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 256), ID256, true);
                     release_slot(slot);
                     tc::mma_commit(&bars[BAR_ACC_FULL]);
+                    tr.ev(20 + layer);                // layer issued
                 }
                 // ---- layer 3: N = 144: A = h2 (hi [+ lo]), then the per-point tile (PE | ones) from smem
                 wait_h();
+                tr.ev(33);
                 for (int ks = 0; ks < 16; ++ks) {
                     wait_slot(slot);
                     tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, kN3), ID3, ks > 0);
@@ -384,8 +410,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                     release_slot(slot);
                 }
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(23);
                 // ---- layer 4: N = 16: A = relu(w) (fp16 in h_hi[0:64), K = 128) + ones step
                 wait_h();
+                tr.ev(34);
                 for (int ks = 0; ks < 8; ++ks) {
                     wait_slot(slot);
                     tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, kN4), ID4, ks > 0);
@@ -408,6 +436,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         unsigned char* PE = smem + OFF_PE;
         uint32_t acnt = 0;
         int it = 0;
+        Tracer tr;
+        tr.init(tid == 0 ? P.trace : nullptr, 2);
         auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
         // accumulator columns [0, ncols) -> relu -> fp16 hi (+ lo) pairs -> TMEM h (in place: the layer's MMAs are done)
         auto relu_to_h = [&](int ncols, bool with_lo) {
@@ -439,6 +469,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             const size_t ri = (size_t)tc_.b * P.n_rays + tc_.r0 + (valid ? ry : 0);
             // copy what this thread needs from the producer-owned geometry, then hand it back
             tc::mbar_wait(&bars[BAR_GEOM_FULL], it & 1);
+            tr.ev(1);                                  // geometry available
             const float4 gm = geom[row];
             zbuf[row] = gm.w;
             tc::mbar_arrive(&bars[BAR_GEOM_FREE]);
@@ -460,13 +491,17 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 tc::fence_proxy_async();
             }
             // ---- layers 0, 1, 2 -> h (hi [+ lo]) in place
+            tr.ev(2);                                  // PE tile written
             for (int layer = 0; layer < 3; ++layer) {
                 wait_acc();
+                tr.ev(10 + layer);                     // accumulator of this layer complete
                 relu_to_h(256, true);
                 h_done();
+                tr.ev(20 + layer);                     // epilogue of this layer done
             }
             // ---- layer 3: sigma = acc[128] + acc[129]; colour hidden -> fp16 in h_hi[0:64)
             wait_acc();
+            tr.ev(13);
             float sigma;
             {
                 uint32_t v[16];
@@ -476,8 +511,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             }
             relu_to_h(128, false);
             h_done();
+            tr.ev(23);
             // ---- layer 4: rgb logits = hi rows + lo rows
             wait_acc();
+            tr.ev(14);
             {
                 uint32_t v[16];
                 tc::tmem_ld16(lane_base + TM_ACC, v);
@@ -509,6 +546,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 }
             }
             named_bar_sync(2, EPI_WARPS * 32);     // rawbuf / zbuf are reused by the next tile
+            tr.ev(30);                                 // composite done
         }
     }
 

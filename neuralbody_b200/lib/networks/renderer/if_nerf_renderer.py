@@ -179,7 +179,7 @@ class Renderer:
 
     # ------------------------------------------------------------------ fused launch
     def render_rays(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, want_raw=False,
-                    out=None):
+                    out=None, trace=None):
         """One nb_render_fwd launch for (B,n) rays.  Returns the dict of get_pixel_value."""
         cfg = get_active_cfg()
         if float(cfg.raw_noise_std) > 0.:
@@ -238,6 +238,7 @@ class Renderer:
             a.acc_map, a.depth_map = out['acc_map'].data_ptr(), out['depth_map'].data_ptr()
             a.weights = out['weights'].data_ptr() if 'weights' in out else None
             a.raw = raw.data_ptr() if raw is not None else None
+            a.trace = trace.data_ptr() if trace is not None else None   # diagnostics (tools/trace_timeline.py)
             stream = torch.cuda.current_stream(dev).cuda_stream
             capi.check(self.lib.nb_render_fwd(C.byref(a), C.c_void_p(stream)), "nb_render_fwd")
             self.launches += self.lib.nb_render_fwd_launches(precision)

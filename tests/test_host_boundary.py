@@ -59,7 +59,7 @@ def test_size_queries_without_gpu(built_lib):
     n32 = lib.nb_packed_volume_bytes(dims, 1, capi.NB_DTYPE_F32)
     n16 = lib.nb_packed_volume_bytes(dims, 1, capi.NB_DTYPE_F16)
     # 137 MB fp32 / 69 MB fp16 of features (+ ~0.3 MB of occupancy bitmaps in both)
-    assert n32 >= 137 * 10 ** 6 and abs((n32 - n16) - 137297920 // 2) < 4096 and n16 < 70 * 10 ** 6
+    assert n32 >= 137 * 10 ** 6 and abs((n32 - n16) - 68530176) < 4096 and n16 < 70 * 10 ** 6
     assert lib.nb_packed_volume_level_offset(dims, 1, capi.NB_DTYPE_F16, 0) == 0
     assert lib.nb_packed_weights_bytes(2) > lib.nb_packed_weights_bytes(1) > 15 * 10 ** 5
     # argument validation happens before any CUDA call
