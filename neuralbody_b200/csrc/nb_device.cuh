@@ -114,6 +114,31 @@ __device__ __forceinline__ void positional_embed(float x, float y, float z, Stor
     }
 }
 
+// Same layout, cheaper: an accurate sincosf only every ANCHOR-th octave, the octaves in between by the
+// double-angle recurrence (sin 2a = 2 sin a cos a, cos 2a = 1 - 2 sin^2 a).  Each doubling at most doubles the
+// absolute error, so with ANCHOR <= 5 the values stay within ~2e-6 of sincosf -- far below the fp16 rounding
+// (2^-11) they get as tensor-core operands.  Used by the tensor-core kernel only (colour path).
+template <int L, int ANCHOR, typename Store>
+__device__ __forceinline__ void positional_embed_anchored(float x, float y, float z, Store&& store) {
+    store(0, x); store(1, y); store(2, z);
+    float f = 1.f;
+    float sx = 0.f, cx = 1.f, sy = 0.f, cy = 1.f, sz = 0.f, cz = 1.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+        if (l % ANCHOR == 0) {
+            sincosf(x * f, &sx, &cx); sincosf(y * f, &sy, &cy); sincosf(z * f, &sz, &cz);
+        } else {
+            float t;
+            t = 2.f * sx * cx; cx = fmaf(-2.f * sx, sx, 1.f); sx = t;
+            t = 2.f * sy * cy; cy = fmaf(-2.f * sy, sy, 1.f); sy = t;
+            t = 2.f * sz * cz; cz = fmaf(-2.f * sz, sz, 1.f); sz = t;
+        }
+        store(3 + 6 * l + 0, sx); store(3 + 6 * l + 1, sy); store(3 + 6 * l + 2, sz);
+        store(3 + 6 * l + 3, cx); store(3 + 6 * l + 4, cy); store(3 + 6 * l + 5, cz);
+        f *= 2.f;
+    }
+}
+
 // ---------------------------------------------------------------- a10: raw2outputs
 // nerf_net_utils.py:6-51, one warp per ray.  raw = (rgb logits x3, sigma) per sample in smem,
 // z = perturbed z_vals in smem.  All lanes return the same reduced values.

@@ -43,6 +43,7 @@ constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_W
 constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;   // 704
 constexpr int PROD_THREADS = PROD_WARPS * 32;
 constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);   // an 8-lane group owns points g, g+64
+constexpr int CLUSTER = 2;                    // CTAs sharing one weight stream through TMA multicast
 
 // shared-memory map (bytes)
 constexpr int OFF_SEG = 0;                                         // 2 x 32 KB
@@ -92,6 +93,7 @@ struct Tracer {
 struct TileCoord { int b, r0, nr; };
 __device__ __forceinline__ TileCoord tile_coord(const RenderParams& P, int tile) {
     TileCoord t;
+    if (tile >= P.n_groups) { t.b = 0; t.r0 = 0; t.nr = 0; return t; }   // padding tile (keeps a cluster in lockstep)
     t.b = tile / P.groups_per_frame;
     t.r0 = (tile % P.groups_per_frame) * P.rays_per_group;
     t.nr = min(P.rays_per_group, P.n_rays - t.r0);
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     // ------------------------------------------------------------------ one-time set-up
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == LOAD_WARP * 32) {
-        for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], 1); }
+        for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], CLUSTER); }
         for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
         tc::mbar_init(&bars[BAR_H_READY], EPI_WARPS * 32);
@@ -157,9 +159,14 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     }
     tc::tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) tc::cluster_sync_all();      // peers' mbarriers are initialised before any multicast lands
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const int n_tiles = P.n_groups;
+    // every CTA of a cluster walks the same number of tiles (the weight stream is shared in lockstep)
+    const int n_iters = (P.n_groups + gridDim.x - 1) / gridDim.x;
+    const int n_tiles = n_iters * gridDim.x;
+    const uint32_t crank = CLUSTER > 1 ? tc::cluster_ctarank() : 0u;
+    constexpr uint16_t CMASK = (1u << CLUSTER) - 1;
 
     // ================================================================== PRODUCERS: geometry + gather
     if (warp >= PROD_WARP0) {
@@ -294,13 +301,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
             auto push = [&](const unsigned char* src, uint32_t bytes) {
                 const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
-                tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);
-                tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes);
-                tc::bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_W_FULL + slot]);
+                tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);     // every CTA of the cluster has consumed it
+                tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes);    // arm OUR barrier (a peer may issue the copy)
+                if (CLUSTER == 1) tc::bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_W_FULL + slot]);
+                else if (cnt % CLUSTER == crank)
+                    tc::bulk_g2s_multicast(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_W_FULL + slot], CMASK);
                 ++cnt;
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int b = tile / P.groups_per_frame;
+                const int b = tile < P.n_groups ? tile / P.groups_per_frame : 0;
                 // layers 0-2: (hi, lo) pairs + bias step; the 1-pass mode skips the lo steps
                 for (int layer = 0; layer < 3; ++layer) {
                     const int ksteps = layer == 0 ? 22 : 16;
@@ -336,7 +345,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
                 tc::tc_fence_after();
             };
-            auto release_slot = [&](uint32_t slot) { tc::mma_commit(&bars[BAR_W_EMPTY + slot]); ++cnt; };
+            auto release_slot = [&](uint32_t slot) {
+                if (CLUSTER == 1) tc::mma_commit(&bars[BAR_W_EMPTY + slot]);
+                else tc::mma_commit_multicast(&bars[BAR_W_EMPTY + slot], CMASK);
+                ++cnt;
+            };
             auto a_desc = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * CHUNK_BYTES, CHUNK_BYTES, 128); };
             auto b_desc = [&](uint32_t slot, int N) { return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES, N * 16, 128); };
             auto wait_h = [&]() { tc::mbar_wait(&bars[BAR_H_READY], hcnt & 1); ++hcnt; tc::tc_fence_after(); };
@@ -482,11 +495,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 auto put = [&](int k, float v) {
                     peh[((k >> 3) * 16 + (row >> 3)) * 64 + (row & 7) * 8 + (k & 7)] = __float2half_rn(v);
                 };
-                positional_embed<10>(gm.x, gm.y, gm.z, [&](int j, float v) { put(j, v); });
+                positional_embed_anchored<10, 5>(gm.x, gm.y, gm.z, [&](int j, float v) { put(j, v); });
                 put(63, 0.f);
                 const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
                 const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-                positional_embed<4>(__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm), [&](int j, float v) { put(64 + j, v); });
+                positional_embed_anchored<4, 4>(__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm), [&](int j, float v) { put(64 + j, v); });
                 put(91, 0.f); put(92, 1.f); put(93, 1.f); put(94, 0.f); put(95, 0.f);
                 tc::fence_proxy_async();
             }
@@ -553,6 +566,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     // ------------------------------------------------------------------ teardown
     tc::tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) tc::cluster_sync_all();      // no CTA exits while a peer may still multicast into it
     if (warp == MMA_WARP) {
         __syncwarp();
         tc::tmem_dealloc<512>(tmem);
@@ -563,8 +577,17 @@ template <int NP, typename VT>
 static cudaError_t launch(const RenderParams& p, int grid, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(render_tc_kernel<NP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    render_tc_kernel<NP, VT><<<grid, NT, SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, render_tc_kernel<NP, VT>, p);
 }
 
 }  // namespace tcr
@@ -585,8 +608,10 @@ int launch_render_tc(const RenderParams& p_in, int volume_dtype, int passes, cud
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = p.n_groups < sms ? p.n_groups : sms;
-    if (grid == 0) return NB_OK;
+    int grid = p.n_groups < sms ? p.n_groups : sms;
+    if (p.n_groups == 0) return NB_OK;
+    grid = (grid + tcr::CLUSTER - 1) / tcr::CLUSTER * tcr::CLUSTER;     // whole clusters; padding tiles are no-ops
+    if (grid > sms) grid = sms / tcr::CLUSTER * tcr::CLUSTER;
     cudaError_t e;
     if (passes == 3) e = (volume_dtype == NB_DTYPE_F32) ? tcr::launch<3, float>(p, grid, stream) : tcr::launch<3, __half>(p, grid, stream);
     else e = (volume_dtype == NB_DTYPE_F32) ? tcr::launch<1, float>(p, grid, stream) : tcr::launch<1, __half>(p, grid, stream);
