@@ -184,21 +184,23 @@ __global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f3
                               __half* __restrict__ seq, __half* __restrict__ frame_steps) {
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    // L0 / L1 / L2: N = 256; slot 2*ks = hi(W[:, 16ks..]), slot 2*ks+1 = lo(...), last slot = bias step
+    // L0 / L1 / L2: N = 256; (hi, lo) planes grouped by 4 K-steps, then the bias step (see nb_layout.h)
     for (int layer = 0; layer < 3; ++layer) {
         const int K = layer == 0 ? kFeat : kHidden;
-        const int slots = (K / 16) * 2 + 1;
+        const int nks = K / 16;
         const float* W = layer == 0 ? w.fc0_w : layer == 1 ? w.fc1_w : w.fc2_w;
         const float* Bv = layer == 0 ? w.fc0_b : layer == 1 ? w.fc1_b : w.fc2_b;
         __half* dst = seq + (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
-        for (int i = t0; i < slots * 256 * 16; i += stride) {
+        for (int i = t0; i < (2 * nks + 1) * 256 * 16; i += stride) {
             const int sl = i / 4096, n = (i / 16) % 256, kk = i % 16;
-            __half v;
-            if (sl < slots - 1) {
-                const float x = W[(size_t)n * K + (sl >> 1) * 16 + kk];
-                v = (sl & 1) ? f16_lo(x) : f16_hi(x);
-            } else v = kk == 0 ? f16_hi(Bv[n]) : kk == 1 ? f16_lo(Bv[n]) : __float2half_rn(0.f);
-            dst[(size_t)sl * kStepHalves256 + step_offset(n, kk, 256)] = v;
+            if (sl < 2 * nks) {
+                const int ks = sl >> 1, lo = sl & 1;
+                const float x = W[(size_t)n * K + ks * 16 + kk];
+                dst[step256_offset(ks, lo, nks) + step_offset(n, kk, 256)] = lo ? f16_lo(x) : f16_hi(x);
+            } else {
+                dst[bias256_offset(nks) + step_offset(n, kk, 256)] =
+                    kk == 0 ? f16_hi(Bv[n]) : kk == 1 ? f16_lo(Bv[n]) : __float2half_rn(0.f);
+            }
         }
     }
     // L3: N = 144.  common steps 0..20 -> seq, per-frame step 21 -> frame_steps[b]

@@ -38,29 +38,40 @@ constexpr size_t kF32Floats = oRgbB + 4;
 // One "step" = the B operand of one K=16 tcgen05.mma: an N x 16 tile in the canonical K-major
 // no-swizzle layout: element (n, kk) at half-offset ((kk/8) * (N/8) + n/8) * 64 + (n%8) * 8 + (kk%8),
 // i.e. 8x8 core matrices (8 rows x 16 B = 128 B contiguous); stride-byte-offset (next 8 rows) = 128 B,
-// leading-byte-offset (next 8-wide K chunk) = N*16 B.  Each step is one contiguous bulk copy.
-// Layers 0-2 (the density path) carry every weight as hi = fp16(w) and lo = fp16(w - hi) in two
-// consecutive steps, so the 3-pass mode (A_hi W_hi + A_lo W_hi + A_hi W_lo) is ~fp32-accurate; the
-// 1-pass mode simply skips the lo steps.
-//   L0  : 22 x (hi, lo) steps of fc_0 (N=256) + 1 bias step (A column of ones x [hi(b), lo(b)])
-//   L1,2: 16 x (hi, lo) steps + 1 bias step
+// leading-byte-offset (next 8-wide K chunk) = N*16 B.
+// Steps are stored in GROUPS of up to 4 consecutive K-steps (one bulk copy / one ring slot / one mbarrier
+// hand-off per group: the single MMA-issuing thread pays ~300 cycles of wait+commit latency per hand-off).
+// Layers 0-2 (the density path) carry every weight as hi = fp16(w) and lo = fp16(w - hi): group g is stored as
+// [hi steps of g][lo steps of g]; the 3-pass mode (A_hi W_hi + A_lo W_hi + A_hi W_lo) is ~fp32-accurate, the
+// 1-pass mode skips the lo halves.
+//   L0  : 22 K-steps of fc_0 (N=256) in groups 4,4,4,4,4,2 (= the gather's 64-channel segments), then 1 bias
+//         step (A column of ones x [hi(b), lo(b)])
+//   L1,2: 16 K-steps in 4 groups, then 1 bias step
 //   L3  : N=144 = 128 colour rows (Wc, fp16) + rows 128/129 = hi/lo(alpha_fc) + 14 zero rows;
 //         16 steps over h2, then 6 steps over the per-point tile
-//         [PE(xyz) 63 | 0 | PE(view) 27 | 0 | 1 | 1 | 0 | 0]  (weights Wx | 0 | Wv | 0 | hi(bc) | lo(bc))
-//         the last of those steps carries the per-frame bias bc => stored once per frame
-//   L4  : N=16: rows 0-2 hi(rgb_fc), rows 3-5 lo(rgb_fc); 8 steps + 1 bias step
+//         [PE(xyz) 63 | 0 | PE(view) 27 | 0 | 1 | 1 | 0 | 0]  (weights Wx | 0 | Wv | 0 | hi(bc) | lo(bc));
+//         the last step carries the per-frame bias bc => stored once per frame, outside the common stream
+//   L4  : N=16: rows 0-2 hi(rgb_fc), rows 3-5 lo(rgb_fc); 8 steps + 1 bias step (one group)
 constexpr size_t kF16ByteOffset = ((kF32Floats * 4 + 255) / 256) * 256;
-constexpr int kSlotsL0 = 22 * 2 + 1, kSlotsL1 = 16 * 2 + 1, kSlotsL2 = 16 * 2 + 1;   // stream slots incl. lo steps
+constexpr int kKsL0 = 22, kKsL12 = 16;                     // K-steps of layers 0 and 1/2 (without the bias step)
 constexpr int kStepsL3 = 22, kStepsL4 = 9;
 constexpr int kN3 = 144, kN4 = 16;
 constexpr int kPeK = 96;                                   // per-point tile width of L3
 constexpr size_t kStepHalves256 = 256 * 16, kStepHalves3 = kN3 * 16, kStepHalves4 = kN4 * 16;
 constexpr size_t sL0 = 0;
-constexpr size_t sL1 = sL0 + kSlotsL0 * kStepHalves256;
-constexpr size_t sL2 = sL1 + kSlotsL1 * kStepHalves256;
-constexpr size_t sL3 = sL2 + kSlotsL2 * kStepHalves256;
+constexpr size_t sL1 = sL0 + (2 * kKsL0 + 1) * kStepHalves256;
+constexpr size_t sL2 = sL1 + (2 * kKsL12 + 1) * kStepHalves256;
+constexpr size_t sL3 = sL2 + (2 * kKsL12 + 1) * kStepHalves256;
 constexpr size_t sL4 = sL3 + kStepsL3 * kStepHalves3;      // (the common copy of L3's last step is unused)
 constexpr size_t kF16Halves = sL4 + kStepsL4 * kStepHalves4;
+
+// N=256 layers: half-offset (from the layer base) of K-step ks, hi or lo plane, with nks K-steps in the layer
+__host__ __device__ inline size_t step256_offset(int ks, int lo, int nks) {
+    const int g = ks >> 2;
+    const int gsteps = (nks - 4 * g) < 4 ? (nks - 4 * g) : 4;
+    return ((size_t)8 * g + (lo ? gsteps : 0) + (ks & 3)) * kStepHalves256;
+}
+__host__ __device__ inline size_t bias256_offset(int nks) { return (size_t)2 * nks * kStepHalves256; }
 
 // ---- scratch for the fp64 fold (doubles), then per-frame data
 constexpr size_t kScratchByteOffset = ((kF16ByteOffset + kF16Halves * 2 + 255) / 256) * 256;

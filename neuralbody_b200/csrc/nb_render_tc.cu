@@ -8,8 +8,9 @@
 //   producer warps (16) : geometry, then the trilinear gather from the channels-last volume into the fp16 A
 //                         operand of layer 0, written in the tcgen05 K-major no-swizzle layout into a 2-deep
 //                         ring of 64-channel K SEGMENTS (layer 0 is K-pipelined against the gather)
-//   loader warp         : streams the decoder weights (fp16, one pre-packed K=16 step per bulk copy, in
-//                         consumption order) from L2 into a 12-slot shared-memory ring (TMA engine, UBLKCP)
+//   loader warp         : streams the decoder weights (fp16, pre-packed groups of 4 K=16 steps per bulk copy, in
+//                         consumption order) from L2 into a 3 x 32 KB shared-memory ring (TMA engine, UBLKCP),
+//                         multicast to both CTAs of a cluster pair
 //   MMA warp (1 thread) : tcgen05.mma kind::f16, fp32 accumulator in TMEM.  Layer 0 reads A from shared memory;
 //                         layers 1..4 read A straight from TMEM, where the previous epilogue left it
 //   epilogue warps (4)  : tcgen05.ld accumulator -> relu -> fp16 (hi [+ lo]) -> tcgen05.st as the next layer's
@@ -32,12 +33,14 @@ namespace nb {
 namespace tcr {
 
 constexpr int TP = 128;                       // points per tile = UMMA M
-constexpr int NUM_SLOTS = 12;
-constexpr int SLOT_BYTES = 8192;              // one K=16 step of an N=256 layer
+constexpr int NUM_SLOTS = 3;
+constexpr int STEP_BYTES = 8192;              // one K=16 step of an N=256 layer
+constexpr int SLOT_BYTES = 4 * STEP_BYTES;    // one group of up to 4 K-steps per ring slot / bulk copy / mbarrier hand-off
 constexpr int CHUNK_BYTES = 2048;             // one 8-wide K chunk of a 128-row A tile
 constexpr int SEG_CHUNKS = 8;                 // 64 channels per segment
 constexpr int NUM_SEGS = 6;                   // 44 feature chunks = 5 x 8 + 4
 constexpr int SEG_BYTES = 2 * SEG_CHUNKS * CHUNK_BYTES;   // hi plane + lo plane = 32 KB
+constexpr int NUM_SEG_BUFS = 3;               // segment ring depth (producers may run this far ahead of layer 0)
 constexpr int PE_CHUNKS = 12;                 // 96-wide per-point tile of layer 3
 constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
 constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;   // 704
@@ -46,8 +49,8 @@ constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);   // an 8-lane group owns p
 constexpr int CLUSTER = 2;                    // CTAs sharing one weight stream through TMA multicast
 
 // shared-memory map (bytes)
-constexpr int OFF_SEG = 0;                                         // 2 x 32 KB
-constexpr int OFF_ONES = OFF_SEG + 2 * SEG_BYTES;                  //  65536: constant (1,1,0..) K-step, 2 chunks
+constexpr int OFF_SEG = 0;                                         // NUM_SEG_BUFS x 32 KB
+constexpr int OFF_ONES = OFF_SEG + NUM_SEG_BUFS * SEG_BYTES;       // constant (1,1,0..) K-step, 2 chunks
 constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;                 //  69632
 constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;         //  94208
 constexpr int OFF_GEOM = OFF_RING + NUM_SLOTS * SLOT_BYTES;        // 192512  float4[128] (wx,wy,wz,z)   producer-owned
@@ -56,8 +59,8 @@ constexpr int OFF_RAW = OFF_GRID + TP * 16;                        // float4[128
 constexpr int OFF_Z = OFF_RAW + TP * 16;                           // float[128] z                       epilogue-owned
 constexpr int OFF_XF = OFF_Z + TP * 4;                             // FrameXf (producer-owned)
 constexpr int OFF_BAR = OFF_XF + 128;
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + 2,
-       BAR_ACC_FULL = 2 * NUM_SLOTS + 4, BAR_H_READY, BAR_GEOM_FULL, BAR_GEOM_FREE, NUM_BARS };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + NUM_SEG_BUFS,
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * NUM_SEG_BUFS, BAR_H_READY, BAR_GEOM_FULL, BAR_GEOM_FREE, NUM_BARS };
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == LOAD_WARP * 32) {
         for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], CLUSTER); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
+        for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
         tc::mbar_init(&bars[BAR_H_READY], EPI_WARPS * 32);
         tc::mbar_init(&bars[BAR_GEOM_FULL], PROD_WARPS);
@@ -227,8 +230,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
             int cur_lvl = -1;
             for (int seg = 0; seg < NUM_SEGS; ++seg) {
                 const uint32_t gseg = (uint32_t)it * NUM_SEGS + seg;
-                const uint32_t buf = gseg & 1;
-                tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg >> 1) & 1) ^ 1);
+                const uint32_t buf = gseg % NUM_SEG_BUFS;
+                tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1);
                 tr.ev(10 + seg);                                 // segment buffer free
                 unsigned char* hi_plane = smem + OFF_SEG + buf * SEG_BYTES;
                 unsigned char* lo_plane = hi_plane + SEG_CHUNKS * CHUNK_BYTES;
@@ -299,33 +302,41 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         if (lane == 0) {
             uint32_t cnt = 0;
             const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
-            auto push = [&](const unsigned char* src, uint32_t bytes) {
+            // one ring slot = one group: up to two source pieces (the per-frame step of layer 3 lives elsewhere)
+            auto push = [&](const unsigned char* src, uint32_t bytes, const unsigned char* src2 = nullptr, uint32_t bytes2 = 0) {
                 const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
+                unsigned char* dst = smem + OFF_RING + slot * SLOT_BYTES;
                 tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);     // every CTA of the cluster has consumed it
-                tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes);    // arm OUR barrier (a peer may issue the copy)
-                if (CLUSTER == 1) tc::bulk_g2s(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_W_FULL + slot]);
-                else if (cnt % CLUSTER == crank)
-                    tc::bulk_g2s_multicast(smem + OFF_RING + slot * SLOT_BYTES, src, bytes, &bars[BAR_W_FULL + slot], CMASK);
+                tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes + bytes2);   // arm OUR barrier (a peer may issue the copy)
+                if (CLUSTER == 1) {
+                    tc::bulk_g2s(dst, src, bytes, &bars[BAR_W_FULL + slot]);
+                    if (bytes2) tc::bulk_g2s(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot]);
+                } else if (cnt % CLUSTER == crank) {
+                    tc::bulk_g2s_multicast(dst, src, bytes, &bars[BAR_W_FULL + slot], CMASK);
+                    if (bytes2) tc::bulk_g2s_multicast(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot], CMASK);
+                }
                 ++cnt;
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int b = tile < P.n_groups ? tile / P.groups_per_frame : 0;
-                // layers 0-2: (hi, lo) pairs + bias step; the 1-pass mode skips the lo steps
+                // layers 0-2: per group [hi steps][lo steps] (the 1-pass mode skips the lo halves), then the bias step
                 for (int layer = 0; layer < 3; ++layer) {
-                    const int ksteps = layer == 0 ? 22 : 16;
+                    const int nks = layer == 0 ? kKsL0 : kKsL12;
                     const unsigned char* base = seq + 2 * (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        push(base + (size_t)(2 * ks) * SLOT_BYTES, SLOT_BYTES);
-                        if (NP == 3) push(base + (size_t)(2 * ks + 1) * SLOT_BYTES, SLOT_BYTES);
+                    for (int g0 = 0; g0 < nks; g0 += 4) {
+                        const int gs = (nks - g0) < 4 ? (nks - g0) : 4;
+                        push(base + 2 * step256_offset(g0, 0, nks), gs * STEP_BYTES);
+                        if (NP == 3) push(base + 2 * step256_offset(g0, 1, nks), gs * STEP_BYTES);
                     }
-                    push(base + (size_t)(2 * ksteps) * SLOT_BYTES, SLOT_BYTES);
+                    push(base + 2 * bias256_offset(nks), STEP_BYTES);
                 }
-                for (int s3 = 0; s3 < kStepsL3; ++s3) {
-                    const uint32_t bytes = kStepHalves3 * 2;
-                    push((s3 == kStepsL3 - 1) ? reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)b * bytes
-                                              : seq + sL3 * 2 + (size_t)s3 * bytes, bytes);
+                {   // layer 3: 16 h2 steps in 4 groups, then the 6 per-point-tile steps as 4 + (1 common + 1 per-frame)
+                    const uint32_t sb = kStepHalves3 * 2;
+                    const unsigned char* l3 = seq + sL3 * 2;
+                    for (int g0 = 0; g0 < 20; g0 += 4) push(l3 + (size_t)g0 * sb, 4 * sb);
+                    push(l3 + (size_t)20 * sb, sb, reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)b * sb, sb);
                 }
-                for (int s4 = 0; s4 < kStepsL4; ++s4) push(seq + sL4 * 2 + (size_t)s4 * kStepHalves4 * 2, kStepHalves4 * 2);
+                push(seq + sL4 * 2, kStepsL4 * kStepHalves4 * 2);   // layer 4: all 9 steps in one group
             }
         }
     }
@@ -351,59 +362,64 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 ++cnt;
             };
             auto a_desc = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * CHUNK_BYTES, CHUNK_BYTES, 128); };
-            auto b_desc = [&](uint32_t slot, int N) { return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES, N * 16, 128); };
+            // B operand = step i of the group held by `slot` (steps are N*32 bytes apart)
+            auto b_desc = [&](uint32_t slot, int i, int N) {
+                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32, N * 16, 128);
+            };
             auto wait_h = [&]() { tc::mbar_wait(&bars[BAR_H_READY], hcnt & 1); ++hcnt; tc::tc_fence_after(); };
 
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 uint32_t slot;
                 if (it > 0) wait_h();                 // previous tile's last epilogue has drained the accumulator
                 tr.ev(1);                             // tile begin
-                // ---- layer 0: A = gathered features, K-pipelined over 6 segments of the smem ring
-                bool first = true;
+                // ---- layer 0: A = gathered features, K-pipelined: segment = weight group = 4 K-steps
                 for (int seg = 0; seg < NUM_SEGS; ++seg) {
                     const uint32_t gseg = (uint32_t)it * NUM_SEGS + seg;
-                    const uint32_t buf = gseg & 1;
-                    tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg >> 1) & 1);
+                    const uint32_t buf = gseg % NUM_SEG_BUFS;
+                    tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
                     tc::tc_fence_after();
                     tr.ev(10 + seg);                  // segment available
                     const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * CHUNK_BYTES;
                     const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
+                    wait_slot(slot);
                     for (int ks = 0; ks < nks; ++ks) {
+                        tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, ks, 256), ID256, (seg | ks) != 0);
+                        if (NP == 3) tc::mma_ss(tmem + TM_ACC, a_desc(lo_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                    }
+                    release_slot(slot);
+                    if (NP == 3) {
                         wait_slot(slot);
-                        tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, 256), ID256, !first);
-                        first = false;
-                        if (NP == 3) tc::mma_ss(tmem + TM_ACC, a_desc(lo_addr, ks), b_desc(slot, 256), ID256, true);
+                        for (int ks = 0; ks < nks; ++ks)
+                            tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, ks, 256), ID256, true);
                         release_slot(slot);
-                        if (NP == 3) {
-                            wait_slot(slot);
-                            tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, 256), ID256, true);
-                            release_slot(slot);
-                        }
                     }
                     tc::mma_commit(&bars[BAR_SEG_EMPTY + buf]);
                 }
                 wait_slot(slot);
-                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 256), ID256, true);
+                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
                 tr.ev(20);                            // layer 0 issued
-                // ---- layers 1, 2: A = h (TMEM, in place), 16 steps (x passes) + ones step
+                // ---- layers 1, 2: A = h (TMEM, in place), 4 groups of 4 K-steps (x passes) + ones step
                 for (int layer = 1; layer <= 2; ++layer) {
                     wait_h();
                     tr.ev(30 + layer);                // h ready for this layer
-                    for (int ks = 0; ks < 16; ++ks) {
+                    for (int g0 = 0; g0 < 16; g0 += 4) {
                         wait_slot(slot);
-                        tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, 256), ID256, ks > 0);
-                        if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + ks * 8, b_desc(slot, 256), ID256, true);
+                        for (int i = 0; i < 4; ++i) {
+                            tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, 256), ID256, (g0 | i) != 0);
+                            if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + (g0 + i) * 8, b_desc(slot, i, 256), ID256, true);
+                        }
                         release_slot(slot);
                         if (NP == 3) {
                             wait_slot(slot);
-                            tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, 256), ID256, true);
+                            for (int i = 0; i < 4; ++i)
+                                tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, 256), ID256, true);
                             release_slot(slot);
                         }
                     }
                     wait_slot(slot);
-                    tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 256), ID256, true);
+                    tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
                     release_slot(slot);
                     tc::mma_commit(&bars[BAR_ACC_FULL]);
                     tr.ev(20 + layer);                // layer issued
@@ -411,29 +427,29 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                 // ---- layer 3: N = 144: A = h2 (hi [+ lo]), then the per-point tile (PE | ones) from smem
                 wait_h();
                 tr.ev(33);
-                for (int ks = 0; ks < 16; ++ks) {
+                for (int g0 = 0; g0 < 16; g0 += 4) {
                     wait_slot(slot);
-                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, kN3), ID3, ks > 0);
-                    if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + ks * 8, b_desc(slot, kN3), ID3, true);
-                    release_slot(slot);
-                }
-                for (int ks = 0; ks < kPeK / 16; ++ks) {
-                    wait_slot(slot);
-                    tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, ks), b_desc(slot, kN3), ID3, true);
-                    release_slot(slot);
-                }
-                tc::mma_commit(&bars[BAR_ACC_FULL]);
-                tr.ev(23);
-                // ---- layer 4: N = 16: A = relu(w) (fp16 in h_hi[0:64), K = 128) + ones step
-                wait_h();
-                tr.ev(34);
-                for (int ks = 0; ks < 8; ++ks) {
-                    wait_slot(slot);
-                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, kN4), ID4, ks > 0);
+                    for (int i = 0; i < 4; ++i) {
+                        tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, (g0 | i) != 0);
+                        if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, true);
+                    }
                     release_slot(slot);
                 }
                 wait_slot(slot);
-                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, kN4), ID4, true);
+                for (int i = 0; i < 4; ++i) tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, i), b_desc(slot, i, kN3), ID3, true);
+                release_slot(slot);
+                wait_slot(slot);
+                for (int i = 0; i < 2; ++i) tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, 4 + i), b_desc(slot, i, kN3), ID3, true);
+                release_slot(slot);
+                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(23);
+                // ---- layer 4: N = 16: A = relu(w) (fp16 in h_hi[0:64), K = 128) + ones step, one group
+                wait_h();
+                tr.ev(34);
+                wait_slot(slot);
+                for (int ks = 0; ks < 8; ++ks)
+                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, ks, kN4), ID4, ks > 0);
+                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 8, kN4), ID4, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
             }
