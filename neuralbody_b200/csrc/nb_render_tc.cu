@@ -39,8 +39,9 @@ constexpr int SLOT_BYTES = 4 * STEP_BYTES;    // one group of up to 4 K-steps pe
 constexpr int CHUNK_BYTES = 2048;             // one 8-wide K chunk of a 128-row A tile
 constexpr int SEG_CHUNKS = 8;                 // 64 channels per segment
 constexpr int NUM_SEGS = 6;                   // 44 feature chunks = 5 x 8 + 4
-constexpr int SEG_BYTES = 2 * SEG_CHUNKS * CHUNK_BYTES;   // hi plane + lo plane = 32 KB
-constexpr int NUM_SEG_BUFS = 3;               // segment ring depth (producers may run this far ahead of layer 0)
+constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * CHUNK_BYTES;   // 96 KB: 3 x (hi + lo plane) in the 3-pass mode, 6 x hi plane (a whole
+                                                              // tile of gather look-ahead) in the 1-pass mode
+constexpr int MAX_SEG_BUFS = 6;
 constexpr int PE_CHUNKS = 12;                 // 96-wide per-point tile of layer 3
 constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
 constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;   // 704
@@ -49,8 +50,8 @@ constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);   // an 8-lane group owns p
 constexpr int CLUSTER = 2;                    // CTAs sharing one weight stream through TMA multicast
 
 // shared-memory map (bytes)
-constexpr int OFF_SEG = 0;                                         // NUM_SEG_BUFS x 32 KB
-constexpr int OFF_ONES = OFF_SEG + NUM_SEG_BUFS * SEG_BYTES;       // constant (1,1,0..) K-step, 2 chunks
+constexpr int OFF_SEG = 0;                                         // segment ring
+constexpr int OFF_ONES = OFF_SEG + SEG_RING_BYTES;                 // constant (1,1,0..) K-step, 2 chunks
 constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;                 //  69632
 constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;         //  94208
 constexpr int OFF_GEOM = OFF_RING + NUM_SLOTS * SLOT_BYTES;        // 192512  float4[128] (wx,wy,wz,z)   producer-owned
@@ -59,8 +60,8 @@ constexpr int OFF_RAW = OFF_GRID + TP * 16;                        // float4[128
 constexpr int OFF_Z = OFF_RAW + TP * 16;                           // float[128] z                       epilogue-owned
 constexpr int OFF_XF = OFF_Z + TP * 4;                             // FrameXf (producer-owned)
 constexpr int OFF_BAR = OFF_XF + 128;
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + NUM_SEG_BUFS,
-       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * NUM_SEG_BUFS, BAR_H_READY, BAR_GEOM_FULL, BAR_GEOM_FREE, NUM_BARS };
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + MAX_SEG_BUFS,
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_H_READY, BAR_GEOM_FULL, BAR_GEOM_FREE, NUM_BARS };
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 
@@ -139,6 +140,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = P.n_samples;
+    constexpr int NUM_SEG_BUFS = (NP == 3) ? 3 : 6;          // segment ring depth (how far the gather may run ahead)
+    constexpr int SEG_BYTES = SEG_RING_BYTES / NUM_SEG_BUFS;  // hi (+ lo) plane of one 64-channel segment
 
     // ------------------------------------------------------------------ one-time set-up
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
@@ -469,23 +472,33 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
         tr.init(tid == 0 ? P.trace : nullptr, 2);
         auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
         // accumulator columns [0, ncols) -> relu -> fp16 hi (+ lo) pairs -> TMEM h (in place: the layer's MMAs are done)
+        // (software-pipelined: the tcgen05.ld of granule c+1 is in flight while granule c is converted and stored)
         auto relu_to_h = [&](int ncols, bool with_lo) {
-            for (int c = 0; c < ncols / 16; ++c) {
-                uint32_t v[16];
-                tc::tmem_ld16(lane_base + TM_ACC + c * 16, v);
-                tc::tmem_ld_wait();
-                uint32_t h[8];
+            const int ng = ncols / 8;
+            uint32_t va[8], vb[8];
+            auto convert_store = [&](const uint32_t (&v)[8], int c) {
+                uint32_t h[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                tc::tmem_st8(lane_base + TM_HI + c * 8, h);
+                for (int i = 0; i < 4; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                tc::tmem_st4(lane_base + TM_HI + c * 4, h);
                 if (NP == 3 && with_lo) {
-                    uint32_t l[8];
+                    uint32_t l[4];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 4; ++i)
                         l[i] = tc::cvt_f16x2(f16lo_of(fmaxf(__uint_as_float(v[2 * i]), 0.f), h[i], 0),
                                              f16lo_of(fmaxf(__uint_as_float(v[2 * i + 1]), 0.f), h[i], 1));
-                    tc::tmem_st8(lane_base + TM_LO + c * 8, l);
+                    tc::tmem_st4(lane_base + TM_LO + c * 4, l);
                 }
+            };
+            tc::tmem_ld8(lane_base + TM_ACC, va);
+            tc::tmem_ld_wait();
+            for (int c = 0; c < ng; c += 2) {
+                tc::tmem_ld8(lane_base + TM_ACC + (c + 1) * 8, vb);          // ng is even
+                convert_store(va, c);
+                tc::tmem_ld_wait();
+                if (c + 2 < ng) tc::tmem_ld8(lane_base + TM_ACC + (c + 2) * 8, va);
+                convert_store(vb, c + 1);
+                tc::tmem_ld_wait();
             }
             tc::tmem_st_wait();
         };
