@@ -125,6 +125,8 @@ typedef struct nb_render_args {
     float* weights;        /* device (B,n,S) or NULL to skip */
     float* depth_map;      /* device (B,n)   */
     float* raw;            /* device (B,n,S,4) decoder output (rgb logits, sigma) or NULL; debugging / parity */
+    float* save;           /* device (B,n,S,1312) activation record for nb_render_bwd, or NULL (NB_PRECISION_FP32 only);
+                              size from nb_render_save_bytes() */
     unsigned long long* trace; /* device, 4 x 4096 u64, or NULL: per-role (code<<48 | SM clock) timeline of CTA 0
                                   (tensor-core kernel only; diagnostics, see tools/trace_timeline.py) */
 } nb_render_args;
@@ -133,6 +135,32 @@ int nb_render_fwd(const nb_render_args* args, void* stream);
 
 /* number of kernels nb_render_fwd enqueues per call for the given precision (for launch accounting) */
 int nb_render_fwd_launches(int precision);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of the fused render (training, BASELINE config 3).  Replaces PyTorch autograd through
+ * raw2outputs (nerf_net_utils.py:6-51), Network.calculate_density_color (latent_xyzc.py:91-126) and
+ * F.grid_sample (latent_xyzc.py:62-72) as driven by Trainer.train (lib/train/trainers/trainer.py:46-53).
+ * Usage: run nb_render_fwd with NB_PRECISION_FP32, an fp32 volume blob, `raw` and `save` set; then call
+ * nb_render_bwd with the same nb_render_args and the output gradients.  Gradients are ACCUMULATED into the
+ * caller's (zeroed) buffers: `grads` mirrors nb_decoder_weights (same shapes; latent_index unused),
+ * d_volumes[l] is the NCDHW fp32 gradient of level l (what autograd hands back to the SparseConvNet). */
+typedef struct nb_render_bwd_args {
+    const nb_render_args* fwd;          /* the forward call's arguments (unchanged) */
+    const float* save;                  /* device, written by the forward call */
+    const float* raw;                   /* device (B,n,S,4), written by the forward call */
+    const float* d_rgb_map;             /* device (B,n,3) or NULL */
+    const float* d_depth_map;           /* device (B,n)   or NULL */
+    const float* d_acc_map;             /* device (B,n)   or NULL */
+    const nb_decoder_weights* weights;  /* the raw decoder tensors the forward blob was packed from */
+    const nb_decoder_weights* grads;    /* device gradient tensors, accumulated into */
+    float* d_volumes[NB_NUM_LEVELS];    /* device (B,C,D,H,W) fp32 each, accumulated into; all NULL to skip */
+    void* workspace;                    /* device scratch, nb_render_bwd_workspace_bytes() */
+    size_t workspace_bytes;
+} nb_render_bwd_args;
+
+size_t nb_render_save_bytes(int batch, int n_rays, int n_samples);
+size_t nb_render_bwd_workspace_bytes(int batch, int n_rays, int n_samples);
+int    nb_render_bwd(const nb_render_bwd_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics.  A two-layer tcgen05 micro-pipeline on one 128-row tile (see csrc/nb_tc_probe.cu):

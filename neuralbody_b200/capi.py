@@ -13,7 +13,8 @@ NB_NUM_LEVELS = 4
 
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
-           "nb_render_fwd_launches", "nb_debug_tc_probe"]
+           "nb_render_fwd_launches", "nb_debug_tc_probe", "nb_render_bwd", "nb_render_save_bytes",
+           "nb_render_bwd_workspace_bytes"]
 
 
 class nb_volume_level(C.Structure):
@@ -41,7 +42,16 @@ class nb_render_args(C.Structure):
         ("weights_blob", C.c_void_p),
         ("white_bkgd", C.c_int), ("precision", C.c_int),
         ("rgb_map", C.c_void_p), ("disp_map", C.c_void_p), ("acc_map", C.c_void_p), ("weights", C.c_void_p),
-        ("depth_map", C.c_void_p), ("raw", C.c_void_p), ("trace", C.c_void_p),
+        ("depth_map", C.c_void_p), ("raw", C.c_void_p), ("save", C.c_void_p), ("trace", C.c_void_p),
+    ]
+
+
+class nb_render_bwd_args(C.Structure):
+    _fields_ = [
+        ("fwd", C.POINTER(nb_render_args)), ("save", C.c_void_p), ("raw", C.c_void_p),
+        ("d_rgb_map", C.c_void_p), ("d_depth_map", C.c_void_p), ("d_acc_map", C.c_void_p),
+        ("weights", C.POINTER(nb_decoder_weights)), ("grads", C.POINTER(nb_decoder_weights)),
+        ("d_volumes", C.c_void_p * NB_NUM_LEVELS), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
 
@@ -77,6 +87,12 @@ def load(path=None):
     lib.nb_render_fwd.argtypes = [C.POINTER(nb_render_args), C.c_void_p]
     lib.nb_render_fwd_launches.restype = C.c_int
     lib.nb_render_fwd_launches.argtypes = [C.c_int]
+    lib.nb_render_bwd.restype = C.c_int
+    lib.nb_render_bwd.argtypes = [C.POINTER(nb_render_bwd_args), C.c_void_p]
+    lib.nb_render_save_bytes.restype = C.c_size_t
+    lib.nb_render_save_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.nb_render_bwd_workspace_bytes.restype = C.c_size_t
+    lib.nb_render_bwd_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.nb_debug_tc_probe.restype = C.c_int
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     if lib.nb_abi_version() != 1:

@@ -131,6 +131,7 @@ __global__ void fold_Wc_kernel(nb_decoder_weights w, const double* __restrict__ 
         for (int j = 0; j < kHidden; ++j) acc += T[n * kHidden + j] * (double)w.feature_w[j * kHidden + k];
         const float v = (float)acc;
         f32[oWct + (size_t)k * kColor + n] = v;
+        f32[oWc + (size_t)n * kHidden + k] = v;
     } else if (idx < kColor * kHidden + w.batch * kColor) {
         const int r = idx - kColor * kHidden;
         const int b = r / kColor, n = r % kColor;
@@ -355,10 +356,10 @@ int nb_pack_weights(const nb_decoder_weights* w, void* out_blob, size_t out_byte
 
 int nb_render_fwd_launches(int precision) { (void)precision; return 1; }
 
-int nb_render_fwd(const nb_render_args* a, void* stream) {
+// validate a forward call's arguments and translate them into the kernels' parameter block (shared with nb_render_bwd)
+int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
     if (!a) { set_error("nb_render_fwd: null args"); return NB_ERR_BAD_ARG; }
     if (a->batch <= 0 || a->n_rays < 0 || a->n_samples <= 0) { set_error("nb_render_fwd: bad batch/n_rays/n_samples"); return NB_ERR_BAD_ARG; }
-    if (a->n_rays == 0) return NB_OK;
     if (!a->ray_o || !a->ray_d || !a->near || !a->far || !a->R || !a->Th || !a->bounds || !a->volume_blob || !a->weights_blob ||
         !a->rgb_map || !a->disp_map || !a->acc_map || !a->depth_map) {
         set_error("nb_render_fwd: a required device pointer is null");
@@ -376,7 +377,7 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     for (int i = 0; i < 3; ++i)
         if (!(a->voxel_size[i] > 0.f) || a->out_sh[i] <= 0) { set_error("nb_render_fwd: voxel_size/out_sh must be > 0"); return NB_ERR_BAD_ARG; }
 
-    RenderParams p;
+    RenderParams& p = *out;
     p.batch = a->batch; p.n_rays = a->n_rays; p.n_samples = a->n_samples;
     p.ray_o = a->ray_o; p.ray_d = a->ray_d; p.near = a->near; p.far = a->far; p.t_vals = a->t_vals; p.t_rand = a->t_rand;
     p.R = a->R; p.Th = a->Th; p.bounds = a->bounds;
@@ -395,9 +396,21 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     p.bc = (const float*)(wb + kBcByteOffset);
     p.wframe = (const __half*)(wb + frame_step_byte_offset(a->batch));
     p.white_bkgd = a->white_bkgd;
-    p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace;
+    p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace; p.save = a->save;
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
 
+    return NB_OK;
+}
+
+int nb_render_fwd(const nb_render_args* a, void* stream) {
+    if (a && a->n_rays == 0 && a->batch > 0 && a->n_samples > 0) return NB_OK;
+    RenderParams p;
+    const int stp = nbi_fill_render_params(a, &p);
+    if (stp != NB_OK) return stp;
+    if (a->save && a->precision != NB_PRECISION_FP32) {
+        set_error("nb_render_fwd: the activation record for nb_render_bwd is written by the exact kernel only (NB_PRECISION_FP32)");
+        return NB_ERR_UNSUPPORTED;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (a->precision == NB_PRECISION_FP32) return launch_render_f32(p, a->volume_dtype, st);
     if (a->precision == NB_PRECISION_TC_FP16) return launch_render_tc(p, a->volume_dtype, 1, st);

@@ -31,6 +31,7 @@ struct RenderParams {
     int white_bkgd;
     float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *raw;
     unsigned long long* trace;
+    float* save;               // (B,n,S,kSaveDim) activation record for nb_render_bwd (exact kernel only) or null
     int rays_per_group;        // rays handled together by one CTA work item
     int tiles_per_group;       // point tiles per group
     int n_groups;              // total work items = batch * ceil(n_rays / rays_per_group)

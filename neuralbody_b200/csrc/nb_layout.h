@@ -19,6 +19,17 @@ constexpr int kXyzPE = 63;
 constexpr int kViewPE = 27;
 constexpr int kColorK = 320;    // 256 (h2) + 63 (PE xyz) + 1 zero pad
 
+// ---- per-point activation record the exact kernel saves for the backward pass (floats)
+constexpr int kSaveF = 0;                       // gathered features          [352]
+constexpr int kSaveH0 = kSaveF + kFeat;         // relu(fc_0)                  [256]
+constexpr int kSaveH1 = kSaveH0 + kHidden;      // relu(fc_1)                  [256]
+constexpr int kSaveH2 = kSaveH1 + kHidden;      // relu(fc_2) | PE(xyz) 63 | 0 [320]  (input of the folded colour layer)
+constexpr int kSaveW = kSaveH2 + kColorK;       // relu(colour hidden)         [128]
+constexpr int kSaveDim = kSaveW + kColor;       // 1312
+// backward scratch per point (floats): [d_raw 4 | d_wpre 128 | d_h2pre 256 | d_h1pre 256 | d_h0pre 256]
+constexpr int kGradRaw = 0, kGradW = 4, kGradH2 = kGradW + kColor, kGradH1 = kGradH2 + kHidden,
+              kGradH0 = kGradH1 + kHidden, kGradDim = kGradH0 + kHidden;   // 900
+
 // ---- fp32 section (float offsets). "t" = transposed / K-major: Wt[k][n] = W[n][k]
 constexpr size_t oW0t = 0;                                  // [352][256]
 constexpr size_t oB0 = oW0t + (size_t)kFeat * kHidden;      // [256]
@@ -32,7 +43,8 @@ constexpr size_t oWct = oAlphaB + 4;                        // [320][128]: rows 
 constexpr size_t oWvt = oWct + (size_t)kColorK * kColor;    // [27][128]  Wv^T (+ pad to 28 rows)
 constexpr size_t oRgbW = oWvt + (size_t)28 * kColor;        // [3][128]
 constexpr size_t oRgbB = oRgbW + 3 * kColor;                // [3] (+1 pad)
-constexpr size_t kF32Floats = oRgbB + 4;
+constexpr size_t oWc = oRgbB + 4;                           // [128][256] folded Wc, row-major (backward dgrad)
+constexpr size_t kF32Floats = oWc + (size_t)kColor * kHidden;
 
 // ---- fp16 section: the tensor-core kernel's weight STREAM, in consumption order.
 // One "step" = the B operand of one K=16 tcgen05.mma: an N x 16 tile in the canonical K-major

@@ -1,0 +1,485 @@
+// Backward of the fused render (nb_render_bwd): gradients of rgb_map / depth_map / acc_map with respect to
+// the four dense feature volumes, every decoder parameter and the latent table.
+//
+// Upstream this is PyTorch autograd through raw2outputs (nerf_net_utils.py:6-51), the eight Conv1d layers
+// and F.grid_sample (latent_xyzc.py:62-126), driven by Trainer.train (lib/train/trainers/trainer.py:46-53).
+// Here the exact-fp32 forward kernel saves the per-point activations (kSaveDim floats/point), and the
+// backward runs as a short sequence of fp32 kernels on the caller's stream:
+//   1. composite_bwd_kernel   d(outputs) -> d(rgb logits, sigma) per sample              (thread per ray)
+//   2. decoder_dgrad_kernel   back through the folded colour layer, fc_2, fc_1, fc_0 to the gathered
+//                             features, then the trilinear scatter-add into the NCDHW volume grads
+//   3. wgrad_kernel (x6), colsum_kernel, view_wgrad_kernel     weight / bias gradients (split over points)
+//   4. unfold_* kernels       gradients of the folded Wc / bc back to feature_fc, latent_fc, view_fc, latent
+// Training chunks are small (N_rand = 1024 rays), so this path is sized for correctness and simplicity:
+// fp32 FFMA, no tensor cores; the forward hot path is untouched.
+#include "nb_device.cuh"
+
+namespace nb {
+namespace bwd {
+
+struct BwdParams {
+    RenderParams f;                 // the forward call's parameters (rays, transforms, packed weights)
+    const float* save;              // (B,n,S,kSaveDim)
+    const float* raw;               // (B,n,S,4)
+    const float *d_rgb, *d_depth, *d_acc;   // any may be null
+    float* ws;                      // (B*n*S, kGradDim) scratch
+    nb_decoder_weights w;           // raw decoder tensors
+    float* d_vol[4];                // NCDHW fp32, caller-zeroed, accumulated into
+};
+
+// ------------------------------------------------------------------------------------------ 1. composite
+__global__ void composite_bwd_kernel(const BwdParams Q) {
+    const RenderParams& P = Q.f;
+    const int S = P.n_samples;
+    const size_t ri = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= (size_t)P.batch * P.n_rays) return;
+    const float near = P.near[ri], far = P.far[ri];
+    const float dx = P.ray_d[ri * 3], dy = P.ray_d[ri * 3 + 1], dz = P.ray_d[ri * 3 + 2];
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    const float* tr = P.t_rand ? P.t_rand + ri * S : nullptr;
+    const float4* raw = reinterpret_cast<const float4*>(Q.raw) + ri * S;
+    float dC[3] = {0.f, 0.f, 0.f};
+    if (Q.d_rgb) { dC[0] = Q.d_rgb[ri * 3]; dC[1] = Q.d_rgb[ri * 3 + 1]; dC[2] = Q.d_rgb[ri * 3 + 2]; }
+    const float dD = Q.d_depth ? Q.d_depth[ri] : 0.f;
+    float dA = Q.d_acc ? Q.d_acc[ri] : 0.f;
+    if (P.white_bkgd) dA -= dC[0] + dC[1] + dC[2];            // rgb_map += 1 - acc_map
+    float Tbuf[128];                                           // exclusive transmittance (S <= 128 checked by the host)
+    float T = 1.f;
+    for (int s = 0; s < S; ++s) {
+        Tbuf[s] = T;
+        const float z = z_sample(near, far, P.t_vals, s, S, tr);
+        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr), z) : 1e10f) * nrm;
+        const float alpha = 1.f - expf(-fmaxf(raw[s].w, 0.f) * dist);
+        T *= (1.f - alpha + 1e-10f);
+    }
+    // U_i = sum_{j>i} g_j alpha_j prod_{i<k<j} f_k  (no division => safe when 1 - alpha underflows)
+    float U = 0.f;
+    for (int s = S - 1; s >= 0; --s) {
+        const float4 rw = raw[s];
+        const float z = z_sample(near, far, P.t_vals, s, S, tr);
+        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr), z) : 1e10f) * nrm;
+        const float sg = fmaxf(rw.w, 0.f);
+        const float e = expf(-sg * dist);
+        const float alpha = 1.f - e;
+        const float f = 1.f - alpha + 1e-10f;
+        const float c0 = 1.f / (1.f + expf(-rw.x)), c1 = 1.f / (1.f + expf(-rw.y)), c2 = 1.f / (1.f + expf(-rw.z));
+        const float g = dC[0] * c0 + dC[1] * c1 + dC[2] * c2 + dD * z + dA;
+        const float Ti = Tbuf[s];
+        const float w = alpha * Ti;
+        const float dalpha = g * Ti - Ti * U;
+        U = g * alpha + f * U;
+        float4 o;
+        o.x = w * dC[0] * c0 * (1.f - c0);
+        o.y = w * dC[1] * c1 * (1.f - c1);
+        o.z = w * dC[2] * c2 * (1.f - c2);
+        o.w = (rw.w > 0.f) ? dalpha * dist * e : 0.f;
+        *reinterpret_cast<float4*>(Q.ws + (ri * S + s) * kGradDim + kGradRaw) = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 2. decoder dgrad
+constexpr int TP = 64, NT = 256, LDX = 356, LDY = 324, KC = 8;
+
+// out[p][n] = epi(p, n, sum_k in[p][k] * W[k][n]),  W row-major [K][N] in global memory
+template <int K, int N, int LDI, int LDO, typename Epi>
+__device__ __forceinline__ void gemm_tile(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ W,
+                                          float* __restrict__ Ws, Epi&& epi) {
+    static_assert(K % KC == 0 && N % 32 == 0, "shape");
+    constexpr int TN = N / 32;
+    const int tid = threadIdx.x, pg = tid & 7, ng = tid >> 3;
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int t = 0; t < TN; ++t) acc[i][t] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        for (int i = tid; i < KC * N; i += NT) Ws[i] = __ldg(W + (size_t)k0 * N + i);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < KC; ++kk) {
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = in[(pg + 8 * i) * LDI + k0 + kk];
+#pragma unroll
+            for (int t = 0; t < TN; ++t) {
+                const float wv = Ws[kk * N + ng + 32 * t];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i][t] = fmaf(a[i], wv, acc[i][t]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int t = 0; t < TN; ++t) out[(pg + 8 * i) * LDO + ng + 32 * t] = epi(pg + 8 * i, ng + 32 * t, acc[i][t]);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1) decoder_dgrad_kernel(const BwdParams Q) {
+    extern __shared__ __align__(16) float smem[];
+    float* X = smem;                    // [64][356]
+    float* Y = X + TP * LDX;            // [64][324]
+    float* Ws = Y + TP * LDY;           // [KC][352]
+    const RenderParams& P = Q.f;
+    const int S = P.n_samples;
+    const size_t npts = (size_t)P.batch * P.n_rays * S;
+    const int tid = threadIdx.x;
+    const float* wf = P.wf32;
+    for (size_t tile = blockIdx.x; tile * TP < npts; tile += gridDim.x) {
+        const size_t p0 = tile * TP;
+        auto gp = [&](int p) { return p0 + p; };
+        auto in_range = [&](int p) { return p0 + p < npts; };
+        // a. d_wpre[p][n] = (rgb_fc^T d_logits) * [w > 0]
+        for (int i = tid; i < TP * kColor; i += NT) {
+            const int p = i / kColor, n = i % kColor;
+            float v = 0.f;
+            if (in_range(p)) {
+                const float* dr = Q.ws + gp(p) * kGradDim + kGradRaw;
+                v = dr[0] * wf[oRgbW + n] + dr[1] * wf[oRgbW + kColor + n] + dr[2] * wf[oRgbW + 2 * kColor + n];
+                if (!(Q.save[gp(p) * kSaveDim + kSaveW + n] > 0.f)) v = 0.f;
+                Q.ws[gp(p) * kGradDim + kGradW + n] = v;
+            }
+            X[p * LDX + n] = v;
+        }
+        __syncthreads();
+        // b. d_h2pre = (d_wpre Wc + alpha_fc^T d_sigma) * [h2 > 0]          Wc row-major [128][256] in the blob
+        gemm_tile<kColor, kHidden, LDX, LDY>(X, Y, wf + oWc, Ws, [&](int p, int k, float v) {
+            if (!in_range(p)) return 0.f;
+            v += wf[oAlphaW + k] * Q.ws[gp(p) * kGradDim + kGradRaw + 3];
+            if (!(Q.save[gp(p) * kSaveDim + kSaveH2 + k] > 0.f)) v = 0.f;
+            Q.ws[gp(p) * kGradDim + kGradH2 + k] = v;
+            return v;
+        });
+        // c. d_h1pre = (d_h2pre fc_2) * [h1 > 0]        fc_2.weight is [out=256][in=256] = the [K][N] this GEMM needs
+        gemm_tile<kHidden, kHidden, LDY, LDX>(Y, X, Q.w.fc2_w, Ws, [&](int p, int k, float v) {
+            if (!in_range(p) || !(Q.save[gp(p) * kSaveDim + kSaveH1 + k] > 0.f)) v = 0.f;
+            if (in_range(p)) Q.ws[gp(p) * kGradDim + kGradH1 + k] = v;
+            return v;
+        });
+        // d. d_h0pre = (d_h1pre fc_1) * [h0 > 0]
+        gemm_tile<kHidden, kHidden, LDX, LDY>(X, Y, Q.w.fc1_w, Ws, [&](int p, int k, float v) {
+            if (!in_range(p) || !(Q.save[gp(p) * kSaveDim + kSaveH0 + k] > 0.f)) v = 0.f;
+            if (in_range(p)) Q.ws[gp(p) * kGradDim + kGradH0 + k] = v;
+            return v;
+        });
+        // e. d_f = d_h0pre fc_0        ([256][352])
+        gemm_tile<kHidden, kFeat, LDY, LDX>(Y, X, Q.w.fc0_w, Ws, [&](int, int, float v) { return v; });
+        // f. trilinear scatter-add (backward of F.grid_sample, zeros padding) into the NCDHW volume gradients
+        if (Q.d_vol[0]) {
+            for (int item = tid; item < TP * 4; item += NT) {   // (point, level): recompute the corner set-up
+                const int p = item >> 2, lvl = item & 3;
+                if (!in_range(p)) continue;
+                const size_t g = gp(p);
+                const size_t ri = g / S;
+                const int s = (int)(g % S), b = (int)(ri / P.n_rays);
+                // frame transform (threads of the same frame recompute it; cheap)
+                FrameXf fx;
+                for (int j = 0; j < 9; ++j) fx.R[j] = P.R[b * 9 + j];
+                for (int j = 0; j < 3; ++j) {
+                    fx.Th[j] = P.Th[b * 3 + j]; fx.min_dhw[j] = P.bounds[b * 6 + (2 - j)];
+                    fx.voxel[j] = P.voxel_size[j]; fx.out_sh[j] = P.out_sh[j];
+                }
+                const float z = z_sample(P.near[ri], P.far[ri], P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+                const float wx = __fadd_rn(P.ray_o[ri * 3], __fmul_rn(P.ray_d[ri * 3], z));
+                const float wy = __fadd_rn(P.ray_o[ri * 3 + 1], __fmul_rn(P.ray_d[ri * 3 + 1], z));
+                const float wz = __fadd_rn(P.ray_o[ri * 3 + 2], __fmul_rn(P.ray_d[ri * 3 + 2], z));
+                float gx, gy, gz;
+                world_to_grid(fx, wx, wy, wz, gx, gy, gz);
+                const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+                const int cbase = lvl == 0 ? 0 : lvl == 1 ? 32 : lvl == 2 ? 96 : 224;
+                Corners cn;
+                corner_setup(unnormalize(gx, W), unnormalize(gy, H), unnormalize(gz, D), W, H, D, cn);
+                float* dv = Q.d_vol[lvl] + (size_t)b * C * D * H * W;
+                const size_t cs = (size_t)D * H * W;
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    const int ddx = c8 & 1, ddy = (c8 >> 1) & 1, ddz = c8 >> 2;
+                    if (!corner_valid(cn, ddx, ddy, ddz, W, H, D)) continue;
+                    const float wgt = corner_weight(cn, ddx, ddy, ddz);
+                    const size_t vox = ((size_t)(cn.z0 + ddz) * H + (cn.y0 + ddy)) * W + (cn.x0 + ddx);
+                    for (int c = 0; c < C; ++c) {
+                        const float dfv = X[p * LDX + cbase + c];
+                        if (dfv != 0.f) atomicAdd(dv + (size_t)c * cs + vox, wgt * dfv);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ 3. weight gradients
+// dW[n * ldw + k] += sum_p A[p * lda + n] * Bm[p * ldb + k];  grid = (ceil(N/64), ceil(K/64), split over P)
+__global__ void __launch_bounds__(256) wgrad_kernel(const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
+                                                    size_t npts, int N, int K, float* __restrict__ dW, int ldw) {
+    __shared__ float As[16][65], Bs[16][65];
+    const int n0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const size_t per = (npts + gridDim.z - 1) / gridDim.z;
+    const size_t pbeg = (size_t)blockIdx.z * per, pend = pbeg + per < npts ? pbeg + per : npts;
+    const int tn = threadIdx.x >> 4, tk = threadIdx.x & 15;       // 16 x 16 threads, 4 x 4 outputs each
+    float acc[4][4] = {};
+    for (size_t p = pbeg; p < pend; p += 16) {
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            const int pp = i >> 6, c = i & 63;
+            const bool ok = p + pp < pend;
+            As[pp][c] = (ok && n0 + c < N) ? A[(p + pp) * lda + n0 + c] : 0.f;
+            Bs[pp][c] = (ok && k0 + c < K) ? Bm[(p + pp) * ldb + k0 + c] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int pp = 0; pp < 16; ++pp) {
+            float a[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[pp][tn + 16 * i]; bv[i] = Bs[pp][tk + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tn + 16 * i, k = k0 + tk + 16 * j;
+            if (n < N && k < K && acc[i][j] != 0.f) atomicAdd(dW + (size_t)n * ldw + k, acc[i][j]);
+        }
+}
+
+// out[seg * N + n] += sum_{p in segment seg} A[p * lda + n];  segments of seg_len consecutive points
+__global__ void colsum_kernel(const float* __restrict__ A, int lda, size_t npts, size_t seg_len, int N, float* __restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const size_t per = (npts + gridDim.y - 1) / gridDim.y;
+    const size_t pbeg = (size_t)blockIdx.y * per, pend = pbeg + per < npts ? pbeg + per : npts;
+    size_t p = pbeg;
+    while (p < pend) {
+        const size_t seg = p / seg_len;
+        const size_t send = (seg + 1) * seg_len < pend ? (seg + 1) * seg_len : pend;
+        float acc = 0.f;
+        for (; p < send; ++p) acc += A[p * lda + n];
+        atomicAdd(out + seg * N + n, acc);
+    }
+}
+
+// d view_fc[:, 256:283][n][j] += sum_rays (sum_s d_wpre[ray,s][n]) * PE4(viewdir(ray))[j];  block per ray, 128 threads
+__global__ void view_wgrad_kernel(const BwdParams Q, float* __restrict__ d_view_w /* (128,346) */) {
+    const RenderParams& P = Q.f;
+    const size_t ri = blockIdx.x;
+    const int n = threadIdx.x, S = P.n_samples;
+    __shared__ float pe[kViewPE];
+    if (n == 0) {
+        const float dx = P.ray_d[ri * 3], dy = P.ray_d[ri * 3 + 1], dz = P.ray_d[ri * 3 + 2];
+        const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+        positional_embed<4>(__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm), [&](int j, float v) { pe[j] = v; });
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int s = 0; s < S; ++s) acc += Q.ws[(ri * S + s) * kGradDim + kGradW + n];
+    if (acc != 0.f)
+        for (int j = 0; j < kViewPE; ++j) atomicAdd(d_view_w + n * 346 + 256 + j, acc * pe[j]);
+}
+
+// ------------------------------------------------------------------------------------------ 4. unfold Wc / bc
+// Forward fold (nb_capi.cu): T = V L (V = view_fc[:, :256], L = latent_fc[:, :256]);  Wc = T F (F = feature_fc);
+// u_b = Ll latent[idx_b] + b_l (Ll = latent_fc[:, 256:]);  bc_b = T b_f + V u_b + b_v.
+// Inputs: dWcx (128,320) [cols 0..255 = dWc, 256..318 = d view_fc[:, 283:346]], dbc (B,128).
+struct Unfold {
+    nb_decoder_weights w;
+    nb_decoder_weights g;            // gradient tensors (same shapes), accumulated into
+    const float* dWcx;               // (128,320)
+    const float* dbc;                // (B,128)
+    float* T;                        // (128,256) scratch
+    float* dT;                       // (128,256) scratch
+    float* u;                        // (B,256) scratch
+    float* du;                       // (B,256) scratch
+};
+#define NB_G(ptr) const_cast<float*>(ptr)
+
+__global__ void unfold_stage1(const Unfold U) {     // T, u, d b_v, d view_fc[:, 283:346]
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = U.w.batch;
+    if (idx < kColor * kHidden) {
+        const int n = idx / kHidden, k = idx % kHidden;
+        float acc = 0.f;
+        for (int j = 0; j < kHidden; ++j) acc = fmaf(U.w.view_w[n * 346 + j], U.w.latent_w[j * 384 + k], acc);
+        U.T[idx] = acc;
+    } else if (idx < kColor * kHidden + B * kHidden) {
+        const int r = idx - kColor * kHidden, b = r / kHidden, j = r % kHidden;
+        long long li = U.w.latent_index[b];
+        li = li < 0 ? 0 : (li >= U.w.num_train_frame ? U.w.num_train_frame - 1 : li);
+        float acc = U.w.latent_b[j];
+        for (int i = 0; i < 128; ++i) acc = fmaf(U.w.latent_w[j * 384 + 256 + i], U.w.latent[li * 128 + i], acc);
+        U.u[r] = acc;
+    } else if (idx < kColor * kHidden + B * kHidden + kColor) {
+        const int n = idx - kColor * kHidden - B * kHidden;
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += U.dbc[b * kColor + n];
+        NB_G(U.g.view_b)[n] += acc;
+        for (int j = 0; j < kXyzPE; ++j) NB_G(U.g.view_w)[n * 346 + 283 + j] += U.dWcx[n * kColorK + kHidden + j];
+    }
+}
+__global__ void unfold_stage2(const Unfold U) {     // dT, d feature_fc.W, d feature_fc.b, du
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = U.w.batch;
+    if (idx < kColor * kHidden) {                    // dT[n][j] = sum_k dWc[n][k] F[j][k] + sum_b dbc[b][n] b_f[j]
+        const int n = idx / kHidden, j = idx % kHidden;
+        float acc = 0.f;
+        for (int k = 0; k < kHidden; ++k) acc = fmaf(U.dWcx[n * kColorK + k], U.w.feature_w[j * kHidden + k], acc);
+        for (int b = 0; b < B; ++b) acc = fmaf(U.dbc[b * kColor + n], U.w.feature_b[j], acc);
+        U.dT[idx] = acc;
+    } else if (idx < kColor * kHidden + kHidden * kHidden) {   // dF[j][k] = sum_n T[n][j] dWc[n][k]
+        const int r = idx - kColor * kHidden, j = r / kHidden, k = r % kHidden;
+        float acc = 0.f;
+        for (int n = 0; n < kColor; ++n) acc = fmaf(U.T[n * kHidden + j], U.dWcx[n * kColorK + k], acc);
+        NB_G(U.g.feature_w)[r] += acc;
+    } else if (idx < kColor * kHidden + kHidden * kHidden + kHidden) {   // d b_f[j] = sum_b sum_n T[n][j] dbc[b][n]
+        const int j = idx - kColor * kHidden - kHidden * kHidden;
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b)
+            for (int n = 0; n < kColor; ++n) acc = fmaf(U.T[n * kHidden + j], U.dbc[b * kColor + n], acc);
+        NB_G(U.g.feature_b)[j] += acc;
+    } else if (idx < kColor * kHidden + kHidden * kHidden + kHidden + B * kHidden) {   // du[b][j] = sum_n V[n][j] dbc[b][n]
+        const int r = idx - kColor * kHidden - kHidden * kHidden - kHidden, b = r / kHidden, j = r % kHidden;
+        float acc = 0.f;
+        for (int n = 0; n < kColor; ++n) acc = fmaf(U.w.view_w[n * 346 + j], U.dbc[b * kColor + n], acc);
+        U.du[r] = acc;
+    }
+}
+__global__ void unfold_stage3(const Unfold U) {     // d view_fc[:, :256], d latent_fc, d latent, d b_l
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = U.w.batch;
+    if (idx < kColor * kHidden) {                    // dV[n][j] = sum_k dT[n][k] L[j][k] + sum_b dbc[b][n] u[b][j]
+        const int n = idx / kHidden, j = idx % kHidden;
+        float acc = 0.f;
+        for (int k = 0; k < kHidden; ++k) acc = fmaf(U.dT[n * kHidden + k], U.w.latent_w[j * 384 + k], acc);
+        for (int b = 0; b < B; ++b) acc = fmaf(U.dbc[b * kColor + n], U.u[b * kHidden + j], acc);
+        NB_G(U.g.view_w)[n * 346 + j] += acc;
+    } else if (idx < kColor * kHidden + kHidden * 384) {
+        const int r = idx - kColor * kHidden, j = r / 384, k = r % 384;
+        float acc = 0.f;
+        if (k < kHidden) {                           // dL[j][k] = sum_n V[n][j] dT[n][k]
+            for (int n = 0; n < kColor; ++n) acc = fmaf(U.w.view_w[n * 346 + j], U.dT[n * kHidden + k], acc);
+        } else {                                     // dLl[j][i] = sum_b du[b][j] latent[idx_b][i]
+            for (int b = 0; b < B; ++b) {
+                long long li = U.w.latent_index[b];
+                li = li < 0 ? 0 : (li >= U.w.num_train_frame ? U.w.num_train_frame - 1 : li);
+                acc = fmaf(U.du[b * kHidden + j], U.w.latent[li * 128 + (k - kHidden)], acc);
+            }
+        }
+        NB_G(U.g.latent_w)[r] += acc;
+    } else if (idx < kColor * kHidden + kHidden * 384 + kHidden) {    // d b_l
+        const int j = idx - kColor * kHidden - kHidden * 384;
+        float acc = 0.f;
+        for (int b = 0; b < B; ++b) acc += U.du[b * kHidden + j];
+        NB_G(U.g.latent_b)[j] += acc;
+    } else if (idx < kColor * kHidden + kHidden * 384 + kHidden + B * 128) {   // d latent[idx_b][i] += sum_j Ll[j][i] du[b][j]
+        const int r = idx - kColor * kHidden - kHidden * 384 - kHidden, b = r / 128, i = r % 128;
+        long long li = U.w.latent_index[b];
+        li = li < 0 ? 0 : (li >= U.w.num_train_frame ? U.w.num_train_frame - 1 : li);
+        float acc = 0.f;
+        for (int j = 0; j < kHidden; ++j) acc = fmaf(U.w.latent_w[j * 384 + 256 + i], U.du[b * kHidden + j], acc);
+        atomicAdd(NB_G(U.g.latent) + li * 128 + i, acc);
+    }
+}
+
+}  // namespace bwd
+}  // namespace nb
+
+using namespace nb;
+
+extern "C" size_t nb_render_bwd_workspace_bytes(int batch, int n_rays, int n_samples) {
+    const size_t npts = (size_t)batch * n_rays * n_samples;
+    // per-point scratch + unfold scratch (dWcx, dbc, T, dT, u, du)
+    return npts * kGradDim * 4 + ((size_t)kColor * kColorK + (size_t)batch * kColor + 2 * (size_t)kColor * kHidden +
+                                  2 * (size_t)batch * kHidden) * 4 + 1024;
+}
+extern "C" size_t nb_render_save_bytes(int batch, int n_rays, int n_samples) {
+    return (size_t)batch * n_rays * n_samples * kSaveDim * 4;
+}
+
+extern "C" int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out);   // nb_capi.cu (internal)
+
+extern "C" int nb_render_bwd(const nb_render_bwd_args* a, void* stream) {
+    if (!a || !a->fwd || !a->save || !a->raw || !a->workspace || !a->weights || !a->grads) {
+        set_error("nb_render_bwd: null argument");
+        return NB_ERR_BAD_ARG;
+    }
+    const nb_render_args* f = a->fwd;
+    if (f->precision != NB_PRECISION_FP32 || f->volume_dtype != NB_DTYPE_F32) {
+        set_error("nb_render_bwd: the training path runs the exact kernel (NB_PRECISION_FP32 + fp32 volume)");
+        return NB_ERR_UNSUPPORTED;
+    }
+    if (f->n_samples > 128) { set_error("nb_render_bwd: n_samples <= 128 supported (got %d)", f->n_samples); return NB_ERR_UNSUPPORTED; }
+    if (a->workspace_bytes < nb_render_bwd_workspace_bytes(f->batch, f->n_rays, f->n_samples)) {
+        set_error("nb_render_bwd: workspace too small");
+        return NB_ERR_BAD_ARG;
+    }
+    bwd::BwdParams Q;
+    int st = nbi_fill_render_params(f, &Q.f);
+    if (st != NB_OK) return st;
+    Q.save = a->save; Q.raw = a->raw;
+    Q.d_rgb = a->d_rgb_map; Q.d_depth = a->d_depth_map; Q.d_acc = a->d_acc_map;
+    Q.ws = (float*)a->workspace;
+    Q.w = *a->weights;
+    for (int l = 0; l < 4; ++l) Q.d_vol[l] = a->d_volumes[l];
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nrays = (size_t)f->batch * f->n_rays, npts = nrays * f->n_samples;
+    if (npts == 0) return NB_OK;
+    const nb_decoder_weights& g = *a->grads;
+
+    bwd::composite_bwd_kernel<<<(unsigned)((nrays + 127) / 128), 128, 0, s>>>(Q);
+
+    const size_t smem = ((size_t)bwd::TP * bwd::LDX + (size_t)bwd::TP * bwd::LDY + (size_t)bwd::KC * kFeat) * 4;
+    cudaFuncSetAttribute(bwd::decoder_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t ntiles = (npts + bwd::TP - 1) / bwd::TP;
+    bwd::decoder_dgrad_kernel<<<(unsigned)(ntiles < 148 ? ntiles : 148), bwd::NT, smem, s>>>(Q);
+
+    // scratch after the per-point region
+    float* extra = Q.ws + npts * kGradDim;
+    float* dWcx = extra;                               extra += (size_t)kColor * kColorK;
+    float* dbc = extra;                                extra += (size_t)f->batch * kColor;
+    float* T = extra;                                  extra += (size_t)kColor * kHidden;
+    float* dT = extra;                                 extra += (size_t)kColor * kHidden;
+    float* u = extra;                                  extra += (size_t)f->batch * kHidden;
+    float* du = extra;
+    cudaMemsetAsync(dWcx, 0, ((size_t)kColor * kColorK + (size_t)f->batch * kColor) * 4, s);
+
+    const int split = 64;
+    auto wgrad = [&](int goff, int N, int soff, int K, float* dW, int ldw) {
+        dim3 grid((N + 63) / 64, (K + 63) / 64, split);
+        bwd::wgrad_kernel<<<grid, 256, 0, s>>>(Q.ws + goff, kGradDim, Q.save + soff, kSaveDim, npts, N, K, dW, ldw);
+    };
+    wgrad(kGradH0, kHidden, kSaveF, kFeat, NB_G(g.fc0_w), kFeat);
+    wgrad(kGradH1, kHidden, kSaveH0, kHidden, NB_G(g.fc1_w), kHidden);
+    wgrad(kGradH2, kHidden, kSaveH1, kHidden, NB_G(g.fc2_w), kHidden);
+    wgrad(kGradW, kColor, kSaveH2, kColorK, dWcx, kColorK);
+    wgrad(kGradRaw, 3, kSaveW, kColor, NB_G(g.rgb_w), kColor);
+    wgrad(kGradRaw + 3, 1, kSaveH2, kHidden, NB_G(g.alpha_w), kHidden);
+    auto colsum = [&](int goff, int N, float* out, size_t seg) {
+        dim3 grid((N + 127) / 128, 32);
+        bwd::colsum_kernel<<<grid, 128, 0, s>>>(Q.ws + goff, kGradDim, npts, seg, N, out);
+    };
+    colsum(kGradH0, kHidden, NB_G(g.fc0_b), npts);
+    colsum(kGradH1, kHidden, NB_G(g.fc1_b), npts);
+    colsum(kGradH2, kHidden, NB_G(g.fc2_b), npts);
+    colsum(kGradRaw, 3, NB_G(g.rgb_b), npts);
+    colsum(kGradRaw + 3, 1, NB_G(g.alpha_b), npts);
+    colsum(kGradW, kColor, dbc, (size_t)f->n_rays * f->n_samples);           // per frame
+    bwd::view_wgrad_kernel<<<(unsigned)nrays, kColor, 0, s>>>(Q, NB_G(g.view_w));
+
+    bwd::Unfold U;
+    U.w = *a->weights; U.g = g; U.dWcx = dWcx; U.dbc = dbc; U.T = T; U.dT = dT; U.u = u; U.du = du;
+    const int B = f->batch;
+    const int n1 = kColor * kHidden + B * kHidden + kColor;
+    bwd::unfold_stage1<<<(n1 + 127) / 128, 128, 0, s>>>(U);
+    const int n2 = kColor * kHidden + kHidden * kHidden + kHidden + B * kHidden;
+    bwd::unfold_stage2<<<(n2 + 127) / 128, 128, 0, s>>>(U);
+    const int n3 = kColor * kHidden + kHidden * 384 + kHidden + B * 128;
+    bwd::unfold_stage3<<<(n3 + 127) / 128, 128, 0, s>>>(U);
+
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("nb_render_bwd: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
+    return NB_OK;
+}

@@ -260,10 +260,27 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
             }
             __syncthreads();
 
+            // training forward: keep the per-point activations the backward pass needs (nb_render_bwd)
+            // row p of the save buffer: [f 352 | h0 256 | h1 256 | h2 256 + PE 64 | w 128]
+            auto save_rows = [&](const float* src, int ld, int width, int col0) {
+                if (!P.save) return;
+                for (int i = tid; i < TP * width; i += NT) {
+                    const int p = i / width, c = i % width;
+                    if (pray[p] >= 0) {
+                        const size_t gp = ((size_t)b * P.n_rays + r0) * S + (size_t)tile * TP + p;
+                        P.save[gp * kSaveDim + col0 + c] = src[p * ld + c];
+                    }
+                }
+            };
+            save_rows(X, LDX, kFeat, kSaveF);
+
             // ---- decoder (a8)
             mlp_layer<kFeat, kHidden, LDX, LDY, true, false>(X, Y, wf + oW0t, wf + oB0, Ws, nullptr, nullptr);
+            save_rows(Y, LDY, kHidden, kSaveH0);
             mlp_layer<kHidden, kHidden, LDY, LDX, true, false>(Y, X, wf + oW1t, wf + oB1, Ws, nullptr, nullptr);
+            save_rows(X, LDX, kHidden, kSaveH1);
             mlp_layer<kHidden, kHidden, LDX, LDY, true, false>(X, Y, wf + oW2t, wf + oB2, Ws, nullptr, nullptr);
+            save_rows(Y, LDY, kColorK, kSaveH2);
             {   // sigma = alpha_fc h2: 4 threads per point
                 const int p = tid >> 2, q = tid & 3;
                 float acc = 0.f;
@@ -279,6 +296,7 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
             // w = relu(Wc h2 + Wx PE(xyz) + bc + vt[ray]); padding rows borrow ray 0's view term (discarded)
             __syncthreads();
             mlp_layer<kColorK, kColor, LDY, LDX, true, true>(Y, X, wf + oWct, P.bc + b * kColor, Ws, vt, prayc);
+            save_rows(X, LDX, kColor, kSaveW);
             {   // rgb = rgb_fc w: 4 threads per point, 3 outputs
                 const int p = tid >> 2, q = tid & 3;
                 float a0 = 0.f, a1 = 0.f, a2 = 0.f;

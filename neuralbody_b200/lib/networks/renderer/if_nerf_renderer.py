@@ -29,6 +29,28 @@ def _f32c(t, device):
     return t.to(device=device, dtype=torch.float32).contiguous()
 
 
+class _FusedRender(torch.autograd.Function):
+    """Autograd boundary of the training path (BASELINE config 3): forward = nb_render_fwd with the exact
+    kernel + activation record, backward = nb_render_bwd.  Differentiable outputs: rgb_map, depth_map,
+    acc_map (what lib/train/trainers/if_nerf_clight.py:25-32 and depth/mask losses consume); disp_map and
+    weights are returned detached.  Differentiable inputs: the four dense volumes (so gradients keep flowing
+    into the reference's SparseConvNet / code embedding) and the 17 decoder tensors."""
+
+    @staticmethod
+    def forward(ctx, renderer, call, *tensors):
+        out = renderer._launch(call, save=True)
+        ctx.renderer, ctx.call = renderer, call
+        ctx.n_vol = len(call["feature_volume"])
+        ctx.save_for_backward(*tensors)
+        ctx.mark_non_differentiable(out["disp_map"], out["weights"])
+        return out["rgb_map"], out["disp_map"], out["acc_map"], out["depth_map"], out["weights"]
+
+    @staticmethod
+    def backward(ctx, d_rgb, d_disp, d_acc, d_depth, d_weights):
+        grads = ctx.renderer._launch_bwd(ctx.call, d_rgb, d_depth, d_acc, ctx.needs_input_grad[2:])
+        return (None, None) + tuple(grads)
+
+
 class Renderer:
     def __init__(self, net):
         self.net = net
@@ -144,19 +166,7 @@ class Renderer:
         if key == self._w_key:
             return self._w_blob
         B = int(latent_index.shape[0])
-        w = capi.nb_decoder_weights()
-        names = [f[0] for f in capi.nb_decoder_weights._fields_][:17]
-        keep = []
-        for name, t in zip(names, tensors):
-            t = t.detach()
-            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
-                t = t.to(device=device, dtype=torch.float32).contiguous()
-            keep.append(t)
-            setattr(w, name, t.data_ptr())
-        li = latent_index.to(device=device, dtype=torch.int64).contiguous()
-        w.latent_index = li.data_ptr()
-        w.num_train_frame = int(self.net.latent.weight.shape[0])
-        w.batch = B
+        w, keep = self._weights_struct(tensors, latent_index, device)
         nbytes = self.lib.nb_packed_weights_bytes(B)
         blob = torch.empty(nbytes, dtype=torch.uint8, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
@@ -180,7 +190,9 @@ class Renderer:
     # ------------------------------------------------------------------ fused launch
     def render_rays(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, want_raw=False,
                     out=None, trace=None):
-        """One nb_render_fwd launch for (B,n) rays.  Returns the dict of get_pixel_value."""
+        """One nb_render_fwd launch for (B,n) rays.  Returns the dict of get_pixel_value.
+        When autograd is recording and any volume / decoder tensor requires grad, the call goes through
+        the exact kernel and `_FusedRender` so that `loss.backward()` works as it does upstream."""
         cfg = get_active_cfg()
         if float(cfg.raw_noise_std) > 0.:
             # upstream's branch draws CPU randn and would crash on GPU tensors (nerf_net_utils.py:33)
@@ -190,22 +202,38 @@ class Renderer:
             raise RuntimeError("Renderer.render needs CUDA tensors: the render path has no CPU implementation")
         B, n = int(ray_o.shape[0]), int(ray_o.shape[1])
         S = int(cfg.N_samples)
-        precision = self._precision()
-        vdtype = self._volume_dtype(precision)
-        with torch.cuda.device(dev):
-            vol_blob, dims = self.pack_volume(feature_volume, vdtype)
-            w_blob = self.pack_weights(sp_input['latent_index'], dev)
-            if t_rand is None and float(cfg.perturb) > 0. and self.net.training:
-                t_rand = self._draw_t_rand(B, n, S, dev)
-            ray_o, ray_d = _f32c(ray_o, dev), _f32c(ray_d, dev)
-            near, far = _f32c(near, dev), _f32c(far, dev)
-            R = _f32c(sp_input['R'], dev)
-            Th = _f32c(sp_input['Th'], dev).reshape(B, 3)           # (B,1,3) multi-view / (B,3) monocular
-            bounds = _f32c(sp_input['bounds'], dev)
+        params = self.net.decoder_tensors()
+        needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in params) or
+                                                  any(v.requires_grad for v in feature_volume))
+        precision = capi.NB_PRECISION_FP32 if needs_grad else self._precision()
+        if t_rand is None and float(cfg.perturb) > 0. and self.net.training:
+            t_rand = self._draw_t_rand(B, n, S, dev)
+        call = {
+            "B": B, "n": n, "S": S, "dev": dev, "precision": precision, "vdtype": self._volume_dtype(precision),
+            "ray_o": _f32c(ray_o, dev), "ray_d": _f32c(ray_d, dev), "near": _f32c(near, dev), "far": _f32c(far, dev),
+            "R": _f32c(sp_input['R'], dev), "Th": _f32c(sp_input['Th'], dev).reshape(B, 3),   # (B,1,3) or (B,3) upstream
+            "bounds": _f32c(sp_input['bounds'], dev), "latent_index": sp_input['latent_index'],
+            "out_sh": [int(v) for v in sp_input['out_sh']], "voxel_size": [float(v) for v in cfg.voxel_size],
+            "t_rand": None if t_rand is None else _f32c(t_rand, dev), "white_bkgd": bool(cfg.white_bkgd),
+            "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "out": out, "trace": trace,
+            "want_weights": bool(self._opt("render_return_weights", True)) or needs_grad,
+        }
+        if call["t_rand"] is not None:
+            assert tuple(call["t_rand"].shape) == (B, n, S)
+        if needs_grad:
+            rgb, disp, acc, depth, weights = _FusedRender.apply(self, call, *feature_volume, *params)
+            return {'rgb_map': rgb, 'disp_map': disp, 'acc_map': acc, 'weights': weights, 'depth_map': depth}
+        return self._launch(call, save=False)
+
+    def _launch(self, call, save):
+        """Pack (cached) + one nb_render_fwd on the current stream."""
+        dev, B, n, S = call["dev"], call["B"], call["n"], call["S"]
+        precision, vdtype = call["precision"], call["vdtype"]
+        with torch.cuda.device(dev), torch.no_grad():
+            vol_blob, dims = self.pack_volume(call["feature_volume"], vdtype)
+            w_blob = self.pack_weights(call["latent_index"], dev)
             t_vals = self._t_vals(S, dev)
-            if t_rand is not None:
-                t_rand = _f32c(t_rand, dev)
-                assert tuple(t_rand.shape) == (B, n, S)
+            out = call["out"]
             if out is None:
                 out = {
                     'rgb_map': torch.empty((B, n, 3), dtype=torch.float32, device=dev),
@@ -213,39 +241,99 @@ class Renderer:
                     'acc_map': torch.empty((B, n), dtype=torch.float32, device=dev),
                     'depth_map': torch.empty((B, n), dtype=torch.float32, device=dev),
                 }
-                if bool(self._opt("render_return_weights", True)):
+                if call["want_weights"]:
                     out['weights'] = torch.empty((B, n, S), dtype=torch.float32, device=dev)
-            raw = torch.empty((B, n, S, 4), dtype=torch.float32, device=dev) if want_raw else None
+            raw = torch.empty((B, n, S, 4), dtype=torch.float32, device=dev) if call["want_raw"] else None
+            sv = None
+            if save:
+                sv = torch.empty(self.lib.nb_render_save_bytes(B, n, S) // 4, dtype=torch.float32, device=dev)
 
             a = capi.nb_render_args()
             a.batch, a.n_rays, a.n_samples = B, n, S
-            a.ray_o, a.ray_d, a.near, a.far = ray_o.data_ptr(), ray_d.data_ptr(), near.data_ptr(), far.data_ptr()
+            a.ray_o, a.ray_d = call["ray_o"].data_ptr(), call["ray_d"].data_ptr()
+            a.near, a.far = call["near"].data_ptr(), call["far"].data_ptr()
             a.t_vals = t_vals.data_ptr()
-            a.t_rand = t_rand.data_ptr() if t_rand is not None else None
-            a.R, a.Th, a.bounds = R.data_ptr(), Th.data_ptr(), bounds.data_ptr()
-            vs = list(cfg.voxel_size)
+            a.t_rand = call["t_rand"].data_ptr() if call["t_rand"] is not None else None
+            a.R, a.Th, a.bounds = call["R"].data_ptr(), call["Th"].data_ptr(), call["bounds"].data_ptr()
             for i in range(3):
-                a.voxel_size[i] = float(vs[i])
-                a.out_sh[i] = int(sp_input['out_sh'][i])
+                a.voxel_size[i] = call["voxel_size"][i]
+                a.out_sh[i] = call["out_sh"][i]
             for l in range(capi.NB_NUM_LEVELS):
                 for j in range(4):
                     a.level_dims[l][j] = dims[l][j]
             a.volume_blob, a.volume_dtype = vol_blob.data_ptr(), vdtype
             a.weights_blob = w_blob.data_ptr()
-            a.white_bkgd = 1 if bool(cfg.white_bkgd) else 0
+            a.white_bkgd = 1 if call["white_bkgd"] else 0
             a.precision = precision
             a.rgb_map, a.disp_map = out['rgb_map'].data_ptr(), out['disp_map'].data_ptr()
             a.acc_map, a.depth_map = out['acc_map'].data_ptr(), out['depth_map'].data_ptr()
             a.weights = out['weights'].data_ptr() if 'weights' in out else None
             a.raw = raw.data_ptr() if raw is not None else None
-            a.trace = trace.data_ptr() if trace is not None else None   # diagnostics (tools/trace_timeline.py)
+            a.save = sv.data_ptr() if sv is not None else None
+            a.trace = call["trace"].data_ptr() if call["trace"] is not None else None   # diagnostics (tools/trace_timeline.py)
             stream = torch.cuda.current_stream(dev).cuda_stream
             capi.check(self.lib.nb_render_fwd(C.byref(a), C.c_void_p(stream)), "nb_render_fwd")
             self.launches += self.lib.nb_render_fwd_launches(precision)
-        if raw is not None:
+            if save:   # everything nb_render_bwd needs stays alive with the autograd node
+                call["args"], call["save"], call["raw"] = a, sv, raw
+                call["keep"] = (vol_blob, w_blob, t_vals, out)
+        if raw is not None and call["want_raw"] and not save:
             out = dict(out)
             out['raw'] = raw
         return out
+
+    def _launch_bwd(self, call, d_rgb, d_depth, d_acc, needs):
+        """nb_render_bwd: gradients for (volumes..., decoder tensors...) in the order of _FusedRender.apply."""
+        dev, B, n, S = call["dev"], call["B"], call["n"], call["S"]
+        params = self.net.decoder_tensors()
+        vols = call["feature_volume"]
+        with torch.cuda.device(dev), torch.no_grad():
+            def cf(t):
+                return None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
+            d_rgb, d_depth, d_acc = cf(d_rgb), cf(d_depth), cf(d_acc)
+            w = self._weights_struct(params, call["latent_index"], dev)
+            gparams = [torch.zeros_like(t, dtype=torch.float32, device=dev) for t in params]
+            g = capi.nb_decoder_weights()
+            names = [f[0] for f in capi.nb_decoder_weights._fields_][:17]
+            for name, t in zip(names, gparams):
+                setattr(g, name, t.data_ptr())
+            g.latent_index, g.num_train_frame, g.batch = w[0].latent_index, w[0].num_train_frame, B
+            want_vol = any(needs[:len(vols)])
+            gvols = [torch.zeros_like(v, dtype=torch.float32, device=dev) for v in vols] if want_vol else [None] * len(vols)
+            nbytes = self.lib.nb_render_bwd_workspace_bytes(B, n, S)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ba = capi.nb_render_bwd_args()
+            ba.fwd = C.pointer(call["args"])
+            ba.save, ba.raw = call["save"].data_ptr(), call["raw"].data_ptr()
+            ba.d_rgb_map = d_rgb.data_ptr() if d_rgb is not None else None
+            ba.d_depth_map = d_depth.data_ptr() if d_depth is not None else None
+            ba.d_acc_map = d_acc.data_ptr() if d_acc is not None else None
+            ba.weights, ba.grads = C.pointer(w[0]), C.pointer(g)
+            for l in range(capi.NB_NUM_LEVELS):
+                ba.d_volumes[l] = gvols[l].data_ptr() if want_vol else None
+            ba.workspace, ba.workspace_bytes = ws.data_ptr(), nbytes
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            capi.check(self.lib.nb_render_bwd(C.byref(ba), C.c_void_p(stream)), "nb_render_bwd")
+        grads = list(gvols) + [gp.view_as(t) for gp, t in zip(gparams, params)]
+        return [gr if need else None for gr, need in zip(grads, needs)]
+
+    def _weights_struct(self, tensors, latent_index, device):
+        """nb_decoder_weights over the raw parameter tensors (+ the tensors kept alive)."""
+        w = capi.nb_decoder_weights()
+        names = [f[0] for f in capi.nb_decoder_weights._fields_][:17]
+        keep = []
+        for name, t in zip(names, tensors):
+            t = t.detach()
+            if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(device=device, dtype=torch.float32).contiguous()
+            keep.append(t)
+            setattr(w, name, t.data_ptr())
+        li = latent_index.to(device=device, dtype=torch.int64).contiguous()
+        keep.append(li)
+        w.latent_index = li.data_ptr()
+        w.num_train_frame = int(self.net.latent.weight.shape[0])
+        w.batch = int(latent_index.shape[0])
+        return w, keep
 
     def get_pixel_value(self, ray_o, ray_d, near, far, feature_volume, sp_input, batch):
         """if_clight_renderer.py:62-92: same signature, same returned dict."""

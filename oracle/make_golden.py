@@ -35,5 +35,30 @@ def main():
             os.path.getsize(path) // 1024))
 
 
+def grad_golden():
+    """Per-tensor gradient fingerprints from the reference's own autograd (oracle/grad_case.py)."""
+    import torch
+    from neuralbody_b200 import synth
+    from oracle import ref_harness, grad_case
+    scene, t_rand, G = grad_case.build()
+    ret, net, vols = ref_harness.reference_render(scene, n_samples=grad_case.N_SAMPLES, perturb=1.0, training=True,
+                                                  white_bkgd=True, t_rand=t_rand, grad=True)
+    grad_case.loss_of(ret, G).backward()
+    sd = dict(net.named_parameters())
+    arrays = {"input_sha256": np.frombuffer(synth.scene_checksum(scene).encode(), dtype=np.uint8)}
+    for k in grad_case.GRAD_KEYS:
+        g = sd[k].grad
+        arrays["sum:" + k] = np.float64(g.double().sum())
+        arrays["abs:" + k] = np.float64(g.double().abs().sum())
+        arrays["head:" + k] = g.reshape(-1)[:64].numpy().astype(np.float32)
+    for l, v in enumerate(vols):
+        arrays["sum:vol%d" % l] = np.float64(v.grad.double().sum())
+        arrays["abs:vol%d" % l] = np.float64(v.grad.double().abs().sum())
+    path = os.path.join(ROOT, "tests", "golden", "grad_train_s32.npz")
+    np.savez_compressed(path, **arrays)
+    print("gradient fingerprints ->", path, "|dfc_0.weight|_1 = %.4e" % float(arrays["abs:fc_0.weight"]))
+
+
 if __name__ == "__main__":
+    grad_golden()
     main()

@@ -19,7 +19,8 @@ def load_golden(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     out = {k: z[k] for k in z.files}
     out["input_sha256"] = bytes(out["input_sha256"]).decode()
-    out["torch_version"] = bytes(out["torch_version"]).decode()
+    if "torch_version" in out:
+        out["torch_version"] = bytes(out["torch_version"]).decode()
     return out
 
 
@@ -36,7 +37,7 @@ def golden_case(name):
         gold = load_golden(name)
         assert synth.scene_checksum(scene) == gold["input_sha256"], (
             "rebuilt inputs differ from the ones the golden vectors were generated on "
-            "(torch %s here vs %s there?)" % (__import__("torch").__version__, gold["torch_version"]))
+            "(torch %s here vs %s there?)" % (__import__("torch").__version__, gold.get("torch_version")))
         _case_cache[name] = (scene, rkw, gold)
     return _case_cache[name]
 
