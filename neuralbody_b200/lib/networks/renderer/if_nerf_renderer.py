@@ -222,7 +222,10 @@ class Renderer:
             assert tuple(call["t_rand"].shape) == (B, n, S)
         if needs_grad:
             rgb, disp, acc, depth, weights = _FusedRender.apply(self, call, *feature_volume, *params)
-            return {'rgb_map': rgb, 'disp_map': disp, 'acc_map': acc, 'weights': weights, 'depth_map': depth}
+            ret = {'rgb_map': rgb, 'disp_map': disp, 'acc_map': acc, 'weights': weights, 'depth_map': depth}
+            if want_raw:
+                ret['raw'] = call["raw"]
+            return ret
         return self._launch(call, save=False)
 
     def _launch(self, call, save):

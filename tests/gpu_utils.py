@@ -37,8 +37,9 @@ def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=
     if t_rand is not None or want_raw:
         sp_input = renderer.prepare_sp_input(batch)
         vol = net.encode_sparse_voxels(sp_input)
-        out = renderer.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp_input,
-                                   t_rand=None if t_rand is None else t_rand.to(device), want_raw=want_raw)
+        with torch.no_grad():
+            out = renderer.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp_input,
+                                       t_rand=None if t_rand is None else t_rand.to(device), want_raw=want_raw)
     else:
         with torch.no_grad():
             out = renderer.render(batch)
