@@ -163,6 +163,7 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ product arm
+@torch.no_grad()      # inference, exactly as upstream's run.py:66 (`with torch.no_grad(): renderer.render(batch)`)
 def run_product(args, rank, world, local_rank):
     import torch.distributed as dist
     from neuralbody_b200 import capi, dist as nbdist

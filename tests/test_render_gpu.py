@@ -76,7 +76,8 @@ def test_fp16_volume_with_exact_mlp_is_close():
         cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.render_precision, cfg.chunk = 64, 0.0, False, "fp32", 0
         net.eval()
         batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}
-        out = {k: v.cpu() for k, v in ren.render(batch).items()}
+        with torch.no_grad():
+            out = {k: v.cpu() for k, v in ren.render(batch).items()}
     finally:
         cfg.render_volume_dtype = "auto"
     G.compare(out, gold, 1e-3, nan_mismatch_frac=0.01, label="fp16vol")
@@ -121,4 +122,5 @@ def test_product_path_fails_loudly_on_cpu_tensors():
     batch = {k: scene[k] for k in G.BATCH_KEYS}   # CPU tensors
     net.set_feature_volume(scene["volumes"])
     with pytest.raises(RuntimeError):
-        ren.render(batch)
+        with torch.no_grad():
+            ren.render(batch)
