@@ -180,6 +180,7 @@ def run_product(args, rank, world, local_rank):
         precision = "tc_fp16x3" if lib.nb_has_precision(capi.NB_PRECISION_TC_FP16X3) else "fp32"
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.raw_noise_std = S, 0.0, False, 0
     cfg.render_precision, cfg.render_volume_dtype, cfg.chunk = precision, "auto", 0
+    cfg.render_skip_empty = not args.dense
     cfg.render_return_weights = False     # `weights` (B,n,S) is unused downstream; rgb/depth/acc/disp are written
     cfg.num_train_frame = int(scene["weights"]["latent.weight"].shape[0])
     net = make_network(cfg)
@@ -187,6 +188,7 @@ def run_product(args, rank, world, local_rank):
     net = net.to(dev).eval()
     net.set_feature_volume([v.to(dev) for v in scene["volumes"]])
     ren = make_renderer(cfg, net)
+    ren.stats = torch.zeros(2, dtype=torch.int64, device=dev)   # tiles executed / occupied samples (sparse kernel)
 
     keys = ("coord", "out_sh", "bounds", "R", "Th", "latent_index", "ray_o", "ray_d", "near", "far")
     host = {k: scene[k].pin_memory() for k in keys}
@@ -219,6 +221,7 @@ def run_product(args, rank, world, local_rank):
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = ren.launches
+    ren.stats.zero_()
     for s0, s1 in ev:
         flush.fill_(1)                    # untimed L2 flush between timed steps
         barrier()
@@ -229,6 +232,7 @@ def run_product(args, rank, world, local_rank):
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
     launches = ren.launches - launches0
+    stats = [int(v) for v in ren.stats.tolist()]
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e through the public API with host buffers
@@ -276,6 +280,10 @@ def run_product(args, rank, world, local_rank):
     # (at N=1 the step IS n_views launches of it and nothing else)
     kernel_ms = total_ms / max(1, launches) if world == 1 else None
     samples_per_launch = n_local * S
+    skipping = precision != "fp32" and not args.dense
+    if skipping and launches:
+        # only EXECUTED work is credited: 128-row tiles the kernel actually ran (padding rows included), per launch
+        samples_per_launch = stats[0] * 128 / launches
     if kernel_ms:
         tflops_exec = samples_per_launch * FLOP_PER_SAMPLE_FOLDED / (kernel_ms * 1e-3) / 1e12
         tflops_written = samples_per_launch * FLOP_PER_SAMPLE_AS_WRITTEN / (kernel_ms * 1e-3) / 1e12
@@ -302,6 +310,9 @@ def run_product(args, rank, world, local_rank):
         "kernel": "render_tc_kernel<%d>" % (3 if precision == "tc_fp16x3" else 1) if precision != "fp32"
                   else "render_f32_kernel (fp32 FFMA pipe, no tensor cores)",
         "kernel_ms": kernel_ms,
+        "samples_evaluated_per_launch": samples_per_launch, "samples_total_per_launch": n_local * S,
+        "empty_sample_skipping": ("exact (sigma_empty < 0): %.1f%% of the samples occupied" % (
+            100.0 * stats[1] / max(1, launches * n_local * S))) if skipping else "off (dense evaluation)",
         "hbm_compulsory_gbs": (n_local * 56 / (kernel_ms * 1e-3) / 1e9) if kernel_ms else None,
     }
 
@@ -341,7 +352,7 @@ def run_product(args, rank, world, local_rank):
         "frames_per_s_512x512": value / (H * W),
         "config": {"workload": "synth-313 512x512 all-hit view x %d per step, 64 samples/ray, eval, perturb=0 "
                                "(BASELINE configs[1])" % n_views,
-                   "precision": precision, "rays_per_step": rays_per_step, "samples_per_ray": S,
+                   "precision": precision, "skip_empty": (precision != "fp32" and not args.dense), "rays_per_step": rays_per_step, "samples_per_ray": S,
                    "parallelism": "ray-sharded x%d, one all-gather per view" % world if world > 1 else "single GPU",
                    "l2": "256 MiB written between timed steps (untimed) to flush the 126 MB L2",
                    "volume": "fp16 channels-last 69 MB, packed once (cached across views of the frame)"
@@ -366,6 +377,7 @@ def main():
     ap.add_argument("--precision", default="auto", choices=["auto", "tc_fp16x3", "tc_fp16", "fp32"])
     ap.add_argument("--ref-rays", type=int, default=4096, help="rays per step of the CPU arm / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dense", action="store_true", help="disable the exact empty-sample skipping of the tensor-core kernels")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(1, args.warmup)
 

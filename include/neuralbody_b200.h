@@ -125,6 +125,9 @@ typedef struct nb_render_args {
     float* weights;        /* device (B,n,S) or NULL to skip */
     float* depth_map;      /* device (B,n)   */
     float* raw;            /* device (B,n,S,4) decoder output (rgb logits, sigma) or NULL; debugging / parity */
+    int   skip_empty;      /* tensor-core precisions: 1 = exact empty-sample skipping (samples whose trilinear cells are all
+                              unoccupied have weight exactly 0 when sigma(empty) < 0; their MLP evaluation is skipped) */
+    unsigned long long* stats; /* device u64[2] or NULL: [0] += 128-sample tiles executed, [1] += occupied samples */
     float* save;           /* device (B,n,S,1312) activation record for nb_render_bwd, or NULL (NB_PRECISION_FP32 only);
                               size from nb_render_save_bytes() */
     unsigned long long* trace; /* device, 4 x 4096 u64, or NULL: per-role (code<<48 | SM clock) timeline of CTA 0

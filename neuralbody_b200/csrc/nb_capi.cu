@@ -175,6 +175,28 @@ __global__ void relayout_kernel(nb_decoder_weights w, float* __restrict__ f32, _
     if (t0 < 4) f32[oRgbB + t0] = (t0 < 3) ? w.rgb_b[t0] : 0.f;
 }
 
+// sigma of a sample whose gathered features are all zero: alpha_fc(relu(fc_2(relu(fc_1(relu(b_0)))))) (latent_xyzc.py:99-104)
+__global__ void sigma_empty_kernel(nb_decoder_weights w, float* __restrict__ f32) {
+    __shared__ float h0[kHidden], h1[kHidden], h2[kHidden];
+    const int n = threadIdx.x;
+    h0[n] = fmaxf(w.fc0_b[n], 0.f);
+    __syncthreads();
+    float a = w.fc1_b[n];
+    for (int k = 0; k < kHidden; ++k) a = fmaf(w.fc1_w[n * kHidden + k], h0[k], a);
+    h1[n] = fmaxf(a, 0.f);
+    __syncthreads();
+    a = w.fc2_b[n];
+    for (int k = 0; k < kHidden; ++k) a = fmaf(w.fc2_w[n * kHidden + k], h1[k], a);
+    h2[n] = fmaxf(a, 0.f);
+    __syncthreads();
+    if (n == 0) {
+        float sgm = w.alpha_b[0];
+        for (int k = 0; k < kHidden; ++k) sgm = fmaf(w.alpha_w[k], h2[k], sgm);
+        f32[oSigmaEmpty] = sgm;
+        f32[oSigmaEmpty + 1] = f32[oSigmaEmpty + 2] = f32[oSigmaEmpty + 3] = 0.f;
+    }
+}
+
 // fp16 split of an fp32 value: hi = fp16(x), lo = fp16(x - hi): hi + lo carries ~21 mantissa bits.
 __device__ __forceinline__ __half f16_hi(float x) { return __float2half_rn(x); }
 __device__ __forceinline__ __half f16_lo(float x) { return __float2half_rn(x - __half2float(__float2half_rn(x))); }
@@ -348,6 +370,7 @@ int nb_pack_weights(const nb_decoder_weights* w, void* out_blob, size_t out_byte
     const int n2 = kColor * kHidden + w->batch * kColor;
     fold_Wc_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(*w, T, u, f32, f16, bc);
     relayout_kernel<<<148, 256, 0, st>>>(*w, f32, f16);
+    sigma_empty_kernel<<<1, kHidden, 0, st>>>(*w, f32);
     stream_kernel<<<148, 256, 0, st>>>(*w, f32, bc, f16, (__half*)(base + frame_step_byte_offset(w->batch)));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("nb_pack_weights: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
@@ -396,7 +419,7 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
     p.bc = (const float*)(wb + kBcByteOffset);
     p.wframe = (const __half*)(wb + frame_step_byte_offset(a->batch));
     p.white_bkgd = a->white_bkgd;
-    p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace; p.save = a->save;
+    p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace; p.save = a->save; p.stats = a->stats;
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
 
     return NB_OK;
@@ -413,8 +436,10 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (a->precision == NB_PRECISION_FP32) return launch_render_f32(p, a->volume_dtype, st);
-    if (a->precision == NB_PRECISION_TC_FP16) return launch_render_tc(p, a->volume_dtype, 1, st);
-    if (a->precision == NB_PRECISION_TC_FP16X3) return launch_render_tc(p, a->volume_dtype, 3, st);
+    if (a->precision == NB_PRECISION_TC_FP16 || a->precision == NB_PRECISION_TC_FP16X3) {
+        const int passes = a->precision == NB_PRECISION_TC_FP16X3 ? 3 : 1;
+        return a->skip_empty ? launch_render_tc_sparse(p, a->volume_dtype, passes, st) : launch_render_tc(p, a->volume_dtype, passes, st);
+    }
     set_error("nb_render_fwd: unknown precision %d", a->precision);
     return NB_ERR_BAD_ARG;
 }

@@ -31,6 +31,7 @@ struct RenderParams {
     int white_bkgd;
     float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *raw;
     unsigned long long* trace;
+    unsigned long long* stats; // [0] += tiles executed, [1] += occupied samples (sparse kernel) or null
     float* save;               // (B,n,S,kSaveDim) activation record for nb_render_bwd (exact kernel only) or null
     int rays_per_group;        // rays handled together by one CTA work item
     int tiles_per_group;       // point tiles per group
@@ -40,6 +41,7 @@ struct RenderParams {
 
 int launch_render_f32(const RenderParams& p, int volume_dtype, cudaStream_t stream);
 int launch_render_tc(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
+int launch_render_tc_sparse(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
 bool tc_available();
 
 }  // namespace nb

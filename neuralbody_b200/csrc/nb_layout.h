@@ -44,7 +44,8 @@ constexpr size_t oWvt = oWct + (size_t)kColorK * kColor;    // [27][128]  Wv^T (
 constexpr size_t oRgbW = oWvt + (size_t)28 * kColor;        // [3][128]
 constexpr size_t oRgbB = oRgbW + 3 * kColor;                // [3] (+1 pad)
 constexpr size_t oWc = oRgbB + 4;                           // [128][256] folded Wc, row-major (backward dgrad)
-constexpr size_t kF32Floats = oWc + (size_t)kColor * kHidden;
+constexpr size_t oSigmaEmpty = oWc + (size_t)kColor * kHidden;   // [1] (+3 pad): sigma of an all-zero feature vector
+constexpr size_t kF32Floats = oSigmaEmpty + 4;
 
 // ---- fp16 section: the tensor-core kernel's weight STREAM, in consumption order.
 // One "step" = the B operand of one K=16 tcgen05.mma: an N x 16 tile in the canonical K-major

@@ -106,6 +106,7 @@ def _defaults():
     c.render_precision = "tc_fp16x3"    # "fp32" exact FFMA kernel | "tc_fp16x3" tcgen05, 3-pass hi/lo density path
                                         # (meets the 1e-3 parity gate) | "tc_fp16" tcgen05 1-pass (fastest, ~4e-3 on depth)
     c.render_volume_dtype = "auto"      # "auto": fp16 volume for tc_fp16, fp32 otherwise
+    c.render_skip_empty = True          # tensor-core modes: exact empty-sample skipping (bit-identical outputs)
     c.render_return_weights = True      # 'weights' (B,n,S) is unused downstream; may be skipped
     c.chunk = 0                         # 0 = all rays of the call in one launch
     return c

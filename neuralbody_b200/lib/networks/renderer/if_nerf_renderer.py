@@ -217,6 +217,7 @@ class Renderer:
             "t_rand": None if t_rand is None else _f32c(t_rand, dev), "white_bkgd": bool(cfg.white_bkgd),
             "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "out": out, "trace": trace,
             "want_weights": bool(self._opt("render_return_weights", True)) or needs_grad,
+            "skip_empty": bool(self._opt("render_skip_empty", True)), "stats": getattr(self, "stats", None),
         }
         if call["t_rand"] is not None:
             assert tuple(call["t_rand"].shape) == (B, n, S)
@@ -273,6 +274,8 @@ class Renderer:
             a.weights = out['weights'].data_ptr() if 'weights' in out else None
             a.raw = raw.data_ptr() if raw is not None else None
             a.save = sv.data_ptr() if sv is not None else None
+            a.skip_empty = 1 if call["skip_empty"] else 0
+            a.stats = call["stats"].data_ptr() if call["stats"] is not None else None
             a.trace = call["trace"].data_ptr() if call["trace"] is not None else None   # diagnostics (tools/trace_timeline.py)
             stream = torch.cuda.current_stream(dev).cuda_stream
             capi.check(self.lib.nb_render_fwd(C.byref(a), C.c_void_p(stream)), "nb_render_fwd")

@@ -21,7 +21,7 @@ def make_net_and_renderer(scene, device="cuda:0"):
 
 
 def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False, t_rand=None,
-                   precision="fp32", device="cuda:0", want_raw=False, chunk=0, renderer=None, net=None):
+                   precision="fp32", device="cuda:0", want_raw=False, chunk=0, renderer=None, net=None, skip_empty=True):
     """Render `scene` through the public API on the GPU; returns dict of CPU tensors."""
     cfg.N_samples = int(n_samples)
     cfg.perturb = float(perturb)
@@ -30,6 +30,7 @@ def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=
     cfg.render_precision = precision
     cfg.render_volume_dtype = "auto"
     cfg.chunk = int(chunk)
+    cfg.render_skip_empty = bool(skip_empty)
     if renderer is None:
         net, renderer = make_net_and_renderer(scene, device)
     net.train(training)

@@ -26,12 +26,15 @@ def _precisions():
 
 
 @pytest.mark.parametrize("name", list(golden_cases.CASES))
-@pytest.mark.parametrize("precision", ALL_PREC)
+@pytest.mark.parametrize("precision", ALL_PREC + ["tc_fp16x3_dense", "tc_fp16_dense"])
 def test_golden_parity(name, precision):
+    """tensor-core modes run twice: with exact empty-sample skipping (default) and dense."""
+    skip_empty = not precision.endswith("_dense")
+    precision = precision.replace("_dense", "")
     if precision not in _precisions():
         pytest.skip("precision %s not built" % precision)
     scene, rkw, gold = golden_case(name)
-    out = G.render_product(scene, precision=precision, **rkw)
+    out = G.render_product(scene, precision=precision, skip_empty=skip_empty, **rkw)
     rep = G.compare(out, gold, TOL[precision], nan_mismatch_frac=0.0 if precision != "tc_fp16" else 0.01,
                     label="%s/%s" % (name, precision))
     print(name, precision, rep)
@@ -56,6 +59,25 @@ def test_raw_decoder_output_vs_oracle(precision):
     if precision == "tc_fp16x3":   # the density path is ~fp32-accurate in the 3-pass mode
         assert float(d[..., 3].max()) < 5e-4, float(d[..., 3].max())
     assert float(d.max()) < tol, float(d.max())
+
+
+@pytest.mark.parametrize("precision", ["tc_fp16x3", "tc_fp16"])
+@pytest.mark.parametrize("name", ["eval_s64", "train_jitter_white", "batch2_s32", "eval_s48_seed7", "full_313"])
+def test_empty_sample_skipping_is_bit_exact(name, precision):
+    """Skipping samples whose trilinear cells are all unoccupied changes no output bit (sigma_empty < 0)."""
+    scene, rkw, _ = golden_case(name)
+    net, ren = G.make_net_and_renderer(scene)
+    ren.stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    dense = G.render_product(scene, precision=precision, skip_empty=False, renderer=ren, net=net, **rkw)
+    assert int(ren.stats[0]) == 0                      # the dense kernel does not count
+    sparse = G.render_product(scene, precision=precision, skip_empty=True, renderer=ren, net=net, **rkw)
+    B, n = scene["ray_o"].shape[:2]
+    S = rkw["n_samples"]
+    tiles, occ = int(ren.stats[0]), int(ren.stats[1])
+    assert 0 < occ < B * n * S and tiles * 128 >= occ  # some, but not all, samples were evaluated
+    print(name, precision, "evaluated %.1f%% of the samples in %d tiles" % (100.0 * occ / (B * n * S), tiles))
+    for k in ("rgb_map", "depth_map", "acc_map", "weights", "disp_map"):
+        assert torch.equal(torch.nan_to_num(dense[k], nan=-1.0), torch.nan_to_num(sparse[k], nan=-1.0)), k
 
 
 def test_chunked_equals_single_launch():
