@@ -46,7 +46,8 @@ def test_raw_decoder_output_vs_oracle(precision):
     if precision not in _precisions():
         pytest.skip("precision %s not built" % precision)
     scene, rkw, _ = golden_case("eval_s64")
-    out = G.render_product(scene, precision=precision, want_raw=True, **rkw)
+    # dense evaluation: with empty-sample skipping the raw rgb logits of skipped samples are (by design) not computed
+    out = G.render_product(scene, precision=precision, want_raw=True, skip_empty=False, **rkw)
     sp = O.prepare_sp_input(scene)
     wpts, z = O.get_sampling_points(scene["ray_o"], scene["ray_d"], scene["near"], scene["far"], 64)
     vd = scene["ray_d"] / scene["ray_d"].norm(dim=2, keepdim=True)
