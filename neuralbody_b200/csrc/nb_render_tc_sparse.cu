@@ -131,6 +131,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
         const int grp = pw * 4 + (lane >> 3);
         const int t = lane & 7;
         uint32_t msg = 0, it = 0;                      // messages sent, real tiles sent
+        Tracer tr;
+        tr.init((pw == 0 && lane == 0) ? P.trace : nullptr, 0);
         unsigned long long n_tiles_done = 0, n_occ = 0;
         auto publish = [&](int nrows, int off, int blk, int flags) {
             tc::mbar_wait(&bars[BAR_MSG_FREE], (msg & 1) ^ 1);        // everybody has read the previous message
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
         };
         for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
             const BlockCoord bc = block_coord(P, blk);
+            tr.ev(2);                                   // block begin
             // the previous block's list may be overwritten once the epilogue has copied its last tile's rows
             tc::mbar_wait(&bars[BAR_MSG_FREE], (msg & 1) ^ 1);
             if (pt < 9) xf->R[pt] = __ldg(P.R + bc.b * 9 + pt);
@@ -197,11 +200,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
             named_bar_sync(1, PROD_THREADS);
             n_occ += (pt == 0) ? total : 0;
             const int ntile = (total + TP - 1) / TP;
+            tr.ev(3);                                   // block classified
             if (ntile == 0) publish(0, 0, blk, 3);
             for (int tl = 0; tl < ntile; ++tl) {
                 const int off = tl * TP;
                 const int nrows = min(TP, total - off);
                 publish(nrows, off, blk, (tl == 0 ? 1 : 0) | (tl == ntile - 1 ? 2 : 0));
+                tr.ev(1);                               // tile published
                 // ---- gather this tile (same unit mapping as the dense kernel; rows >= nrows are zero)
                 float4 g[PTS_PER_GROUP];
 #pragma unroll
@@ -218,6 +223,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                     const uint32_t gseg = it * NUM_SEGS + seg;
                     const uint32_t buf = gseg % NUM_SEG_BUFS;
                     tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1);
+                    tr.ev(10 + seg);
                     unsigned char* hi_plane = smem + OFF_SEG + buf * SEG_BYTES;
                     unsigned char* lo_plane = hi_plane + SEG_CHUNKS * CHUNK_BYTES;
                     const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                     tc::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&bars[BAR_SEG_FULL + buf]);
+                    tr.ev(20 + seg);
                 }
                 ++it;
                 ++n_tiles_done;
@@ -350,6 +357,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32, N * 16, 128);
             };
             auto wait_h = [&]() { tc::mbar_wait(&bars[BAR_H_READY], hcnt & 1); ++hcnt; tc::tc_fence_after(); };
+            Tracer tr;
+            tr.init(P.trace, 1);
             for (;;) {
                 tc::mbar_wait(&bars[BAR_MSG_FULL], msg & 1);
                 const int nrows = info[msg & 1].nrows, flags = info[msg & 1].flags;
@@ -359,11 +368,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 if (nrows == 0) continue;
                 uint32_t slot;
                 if (it > 0) wait_h();
+                tr.ev(1);
                 for (int seg = 0; seg < NUM_SEGS; ++seg) {
                     const uint32_t gseg = it * NUM_SEGS + seg;
                     const uint32_t buf = gseg % NUM_SEG_BUFS;
                     tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
                     tc::tc_fence_after();
+                    tr.ev(10 + seg);
                     const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * CHUNK_BYTES;
                     const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
                     wait_slot(slot);
@@ -384,8 +395,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(20);
                 for (int layer = 1; layer <= 2; ++layer) {
                     wait_h();
+                    tr.ev(30 + layer);
                     for (int g0 = 0; g0 < 16; g0 += 4) {
                         wait_slot(slot);
                         for (int i = 0; i < 4; ++i) {
@@ -404,8 +417,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                     tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
                     release_slot(slot);
                     tc::mma_commit(&bars[BAR_ACC_FULL]);
+                    tr.ev(20 + layer);
                 }
                 wait_h();
+                tr.ev(33);
                 for (int g0 = 0; g0 < 16; g0 += 4) {
                     wait_slot(slot);
                     for (int i = 0; i < 4; ++i) {
@@ -421,7 +436,9 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 for (int i = 0; i < 2; ++i) tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, 4 + i), b_desc(slot, i, kN3), ID3, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(23);
                 wait_h();
+                tr.ev(34);
                 wait_slot(slot);
                 for (int ks = 0; ks < 8; ++ks)
                     tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, ks, kN4), ID4, ks > 0);

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
-PROD = {1: "geom done"}
+PROD = {1: "geom done / tile published", 2: "block begin", 3: "block classified"}
 PROD.update({10 + s: "seg%d buf free" % s for s in range(6)})
 PROD.update({20 + s: "seg%d gathered" % s for s in range(6)})
 MMA = {1: "tile begin", 20: "L0 issued", 21: "L1 issued", 22: "L2 issued", 23: "L3 issued", 31: "h ready L1", 32: "h ready L2",
@@ -28,6 +28,7 @@ def main():
     scene = synth.make_scene(H=512, W=512, scale=1.0, all_hit=True)
     net, ren = G.make_net_and_renderer(scene)
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.render_precision, cfg.render_volume_dtype = 64, 0.0, False, prec, "auto"
+    cfg.render_skip_empty = len(sys.argv) > 4 and sys.argv[4] == "sparse"
     net.eval()
     batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}
     sp = ren.prepare_sp_input(batch)
@@ -35,7 +36,8 @@ def main():
     trace = torch.zeros(4 * 4096, dtype=torch.int64, device="cuda")
     for _ in range(2):
         trace.zero_()
-        ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp, trace=trace)
+        with torch.no_grad():
+            ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp, trace=trace)
     torch.cuda.synchronize()
     t = trace.cpu().view(4, 4096)
     roles = [("PROD", PROD, 13, 1), ("MMA", MMA, None, 1), ("EPI", EPI, None, 1)]
