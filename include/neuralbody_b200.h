@@ -125,6 +125,12 @@ typedef struct nb_render_args {
     float* weights;        /* device (B,n,S) or NULL to skip */
     float* depth_map;      /* device (B,n)   */
     float* raw;            /* device (B,n,S,4) decoder output (rgb logits, sigma) or NULL; debugging / parity */
+    /* f-1, masked renderers (if_clight_renderer_mmsk.py:12-45; B = 1 only, as upstream): a sample is evaluated only if it
+       projects into the foreground of every mask view; elsewhere raw = 0.  mask_msks NULL => no masking */
+    const unsigned char* mask_msks;  /* device (nv, mask_H, mask_W) uint8 */
+    const float* mask_RT;            /* device (nv,3,4) world->camera */
+    const float* mask_Ks;            /* device (nv,3,3) */
+    int   mask_nv, mask_H, mask_W;
     int   skip_empty;      /* tensor-core precisions: 1 = exact empty-sample skipping (samples whose trilinear cells are all
                               unoccupied have weight exactly 0 when sigma(empty) < 0; their MLP evaluation is skipped) */
     unsigned long long* stats; /* device u64[2] or NULL: [0] += 128-sample tiles executed, [1] += occupied samples */

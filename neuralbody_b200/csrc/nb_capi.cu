@@ -420,6 +420,12 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
     p.wframe = (const __half*)(wb + frame_step_byte_offset(a->batch));
     p.white_bkgd = a->white_bkgd;
     p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace; p.save = a->save; p.stats = a->stats;
+    p.mask_msks = a->mask_msks; p.mask_RT = a->mask_RT; p.mask_Ks = a->mask_Ks;
+    p.mask_nv = a->mask_msks ? a->mask_nv : 0; p.mask_H = a->mask_H; p.mask_W = a->mask_W;
+    if (a->mask_msks && (a->batch != 1 || !a->mask_RT || !a->mask_Ks || a->mask_nv <= 0 || a->mask_H <= 0 || a->mask_W <= 0)) {
+        set_error("nb_render_fwd: mask views need batch == 1 (as upstream), RT, Ks and positive nv/H/W");
+        return NB_ERR_BAD_ARG;
+    }
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
 
     return NB_OK;
@@ -430,6 +436,7 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     RenderParams p;
     const int stp = nbi_fill_render_params(a, &p);
     if (stp != NB_OK) return stp;
+    if (a->save && a->mask_msks) { set_error("nb_render_fwd: mask views are an inference feature (no activation record)"); return NB_ERR_UNSUPPORTED; }
     if (a->save && a->precision != NB_PRECISION_FP32) {
         set_error("nb_render_fwd: the activation record for nb_render_bwd is written by the exact kernel only (NB_PRECISION_FP32)");
         return NB_ERR_UNSUPPORTED;
@@ -438,7 +445,9 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     if (a->precision == NB_PRECISION_FP32) return launch_render_f32(p, a->volume_dtype, st);
     if (a->precision == NB_PRECISION_TC_FP16 || a->precision == NB_PRECISION_TC_FP16X3) {
         const int passes = a->precision == NB_PRECISION_TC_FP16X3 ? 3 : 1;
-        return a->skip_empty ? launch_render_tc_sparse(p, a->volume_dtype, passes, st) : launch_render_tc(p, a->volume_dtype, passes, st);
+        // mask views are a per-sample predicate: they live in the sample classifier of the sparse kernel
+        return (a->skip_empty || a->mask_msks) ? launch_render_tc_sparse(p, a->volume_dtype, passes, st)
+                                               : launch_render_tc(p, a->volume_dtype, passes, st);
     }
     set_error("nb_render_fwd: unknown precision %d", a->precision);
     return NB_ERR_BAD_ARG;

@@ -98,6 +98,32 @@ __device__ __forceinline__ float corner_weight(const Corners& c, int dx, int dy,
     return __fmul_rn(__fmul_rn(c.wx[dx], c.wy[dy]), c.wz[dz]);
 }
 
+// ---------------------------------------------------------------- f-1: if_clight_renderer_mmsk.py:12-45
+// inside = AND over the mask views of msk[round(v)][round(u)], (u, v) = perspective projection of the world
+// point, rounded half-to-even (torch.round) and clamped to the image like upstream.
+__device__ __forceinline__ int mask_pixel(float r, int size) {
+    // torch: .round().long() then clamp(0, size-1); non-finite / out-of-range casts give LONG_MIN on x86 => 0
+    if (!(fabsf(r) < 9.0e18f)) return 0;
+    const long long q = (long long)rintf(r);
+    return (int)(q < 0 ? 0 : (q > size - 1 ? size - 1 : q));
+}
+__device__ __forceinline__ bool inside_masks(const RenderParams& P, float wx, float wy, float wz) {
+    for (int v = 0; v < P.mask_nv; ++v) {
+        const float* RT = P.mask_RT + v * 12;
+        const float* K = P.mask_Ks + v * 9;
+        // pts @ R^T + T, then @ K^T
+        const float cx = __fadd_rn(fmaf(wz, RT[2], fmaf(wy, RT[1], __fmul_rn(wx, RT[0]))), RT[3]);
+        const float cy = __fadd_rn(fmaf(wz, RT[6], fmaf(wy, RT[5], __fmul_rn(wx, RT[4]))), RT[7]);
+        const float cz = __fadd_rn(fmaf(wz, RT[10], fmaf(wy, RT[9], __fmul_rn(wx, RT[8]))), RT[11]);
+        const float ix = fmaf(cz, K[2], fmaf(cy, K[1], __fmul_rn(cx, K[0])));
+        const float iy = fmaf(cz, K[5], fmaf(cy, K[4], __fmul_rn(cx, K[3])));
+        const float iz = fmaf(cz, K[8], fmaf(cy, K[7], __fmul_rn(cx, K[6])));
+        const int u = mask_pixel(__fdiv_rn(ix, iz), P.mask_W), w = mask_pixel(__fdiv_rn(iy, iz), P.mask_H);
+        if (!__ldg(P.mask_msks + ((size_t)v * P.mask_H + w) * P.mask_W + u)) return false;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------- a9: embedder.py:5-50
 // out[0..2] = x; out[3+6f+j] = sin(2^f x_j); out[6+6f+j] = cos(2^f x_j)   (x * freq is exact: freq = 2^f)
 template <int L, typename Store>

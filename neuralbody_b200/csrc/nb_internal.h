@@ -31,6 +31,8 @@ struct RenderParams {
     int white_bkgd;
     float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *raw;
     unsigned long long* trace;
+    const unsigned char* mask_msks; const float* mask_RT; const float* mask_Ks;   // f-1 mask views (null = none)
+    int mask_nv, mask_H, mask_W;
     unsigned long long* stats; // [0] += tiles executed, [1] += occupied samples (sparse kernel) or null
     float* save;               // (B,n,S,kSaveDim) activation record for nb_render_bwd (exact kernel only) or null
     int rays_per_group;        // rays handled together by one CTA work item

@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
     float* gcoord = Ws + 2 * KC * 256;         // [64][3] grid coords (x,y,z)
     int* pray = reinterpret_cast<int*>(gcoord + TP * 3);   // [64] local ray of each tile point (-1 = padding)
     int* prayc = pray + TP;                                // [64] same, padding clamped to ray 0
-    float* vt = reinterpret_cast<float*>(prayc + TP);      // [G][128] per-ray view term
+    int* pins = prayc + TP;                                // [64] f-1: sample projects into every mask view
+    float* vt = reinterpret_cast<float*>(pins + TP);       // [G][128] per-ray view term
     const int G = P.rays_per_group, S = P.n_samples;
     float* zbuf = vt + G * kColor;             // [G][S]
     float4* rawbuf = reinterpret_cast<float4*>(zbuf + ((G * S + 3) & ~3));  // [G][S]
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
                 const bool valid = ry < nr;
                 pray[tid] = valid ? ry : -1;
                 prayc[tid] = valid ? ry : 0;
+                pins[tid] = 1;
                 float* yrow = Y + tid * LDY + kHidden;
                 if (valid) {
                     const RayInfo& r = rays[ry];
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
                     const float wz = __fadd_rn(r.o[2], __fmul_rn(r.d[2], z));
                     float gx, gy, gz;
                     world_to_grid(xf, wx, wy, wz, gx, gy, gz);
+                    if (P.mask_nv > 0) pins[tid] = inside_masks(P, wx, wy, wz) ? 1 : 0;
                     gcoord[tid * 3 + 0] = gx; gcoord[tid * 3 + 1] = gy; gcoord[tid * 3 + 2] = gz;
                     positional_embed<10>(wx, wy, wz, [&](int j, float v) { yrow[j] = v; });   // PE of WORLD xyz (latent_xyzc.py:115)
                     yrow[kXyzPE] = 0.f;
@@ -318,6 +321,9 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
                 }
             }
             __syncthreads();
+            if (P.mask_nv > 0 && tid < TP && pray[tid] >= 0 && !pins[tid])      // if_clight_renderer_mmsk.py:54-59: raw = 0 outside
+                rawbuf[tile * TP + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
         }
 
         // ---- composite (a10): one warp per ray
@@ -344,7 +350,7 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
 }
 
 size_t smem_bytes(int G, int S) {
-    size_t fl = (size_t)TP * LDX + (size_t)TP * LDY + 2 * KC * 256 + TP * 3 + 2 * TP /*pray, prayc*/ + (size_t)G * kColor +
+    size_t fl = (size_t)TP * LDX + (size_t)TP * LDY + 2 * KC * 256 + TP * 3 + 3 * TP /*pray, prayc, pins*/ + (size_t)G * kColor +
                 (size_t)((G * S + 3) & ~3);
     return fl * 4 + (size_t)G * S * 16 + (size_t)G * sizeof(RayInfo) + 16;
 }

@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 world_to_grid(*xf, gm.x, gm.y, gm.z, gr.x, gr.y, gr.z);
                 gr.w = __int_as_float(pt);
                 occ = !can_skip;
+                const bool inside = P.mask_nv == 0 || inside_masks(P, gm.x, gm.y, gm.z);   // f-1 mask views
 #pragma unroll
-                for (int lvl = 0; lvl < 4 && !occ; ++lvl) {
+                for (int lvl = 0; lvl < 4 && !occ && inside; ++lvl) {
                     const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
                     Corners cn;
                     corner_setup(unnormalize(gr.x, W), unnormalize(gr.y, H), unnormalize(gr.z, D), W, H, D, cn);
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                         occ = (__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u;
                     }
                 }
+                occ = occ && inside;
             }
             // ---- order-preserving compaction of the occupied samples
             const uint32_t bal = __ballot_sync(0xffffffffu, occ);
@@ -505,7 +507,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
             const int nsmp = bc.nr * S;
             if (flags & 1) {            // first message of the block: every sample starts as "empty"
                 for (int j = row; j < nsmp; j += EPI_WARPS * 32) {
-                    rawb[j] = make_float4(0.f, 0.f, 0.f, sigma_empty);
+                    rawb[j] = make_float4(0.f, 0.f, 0.f, fminf(sigma_empty, 0.f));   // skipped samples: weight exactly 0
                     const size_t ri = (size_t)bc.b * P.n_rays + bc.r0 + j / S;
                     zb[j] = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, j % S, S, P.t_rand ? P.t_rand + ri * S : nullptr);
                 }

@@ -189,7 +189,7 @@ class Renderer:
 
     # ------------------------------------------------------------------ fused launch
     def render_rays(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, want_raw=False,
-                    out=None, trace=None):
+                    out=None, trace=None, masks=None):
         """One nb_render_fwd launch for (B,n) rays.  Returns the dict of get_pixel_value.
         When autograd is recording and any volume / decoder tensor requires grad, the call goes through
         the exact kernel and `_FusedRender` so that `loss.backward()` works as it does upstream."""
@@ -218,7 +218,13 @@ class Renderer:
             "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "out": out, "trace": trace,
             "want_weights": bool(self._opt("render_return_weights", True)) or needs_grad,
             "skip_empty": bool(self._opt("render_skip_empty", True)), "stats": getattr(self, "stats", None),
+            "masks": None,
         }
+        if masks is not None:   # f-1: mask views of if_clight_renderer_mmsk.py (B = 1 only, as upstream)
+            if needs_grad:
+                raise NotImplementedError("mask views are an inference feature upstream (vis_novel_view / vis_novel_pose)")
+            msks = masks["msks"][0].to(device=dev, dtype=torch.uint8).contiguous()
+            call["masks"] = (msks, _f32c(masks["RT"][0][:, :3, :4], dev), _f32c(masks["Ks"][0], dev))
         if call["t_rand"] is not None:
             assert tuple(call["t_rand"].shape) == (B, n, S)
         if needs_grad:
@@ -275,6 +281,10 @@ class Renderer:
             a.raw = raw.data_ptr() if raw is not None else None
             a.save = sv.data_ptr() if sv is not None else None
             a.skip_empty = 1 if call["skip_empty"] else 0
+            if call["masks"] is not None:
+                msks, RT, Ks = call["masks"]
+                a.mask_msks, a.mask_RT, a.mask_Ks = msks.data_ptr(), RT.data_ptr(), Ks.data_ptr()
+                a.mask_nv, a.mask_H, a.mask_W = int(msks.shape[0]), int(msks.shape[1]), int(msks.shape[2])
             a.stats = call["stats"].data_ptr() if call["stats"] is not None else None
             a.trace = call["trace"].data_ptr() if call["trace"] is not None else None   # diagnostics (tools/trace_timeline.py)
             stream = torch.cuda.current_stream(dev).cuda_stream

@@ -341,9 +341,41 @@ def make_scene(seed=313, H=512, W=512, scale=1.0, voxel_size=(0.005, 0.005, 0.00
         "ray_o": stack(ro_l), "ray_d": stack(rd_l), "near": stack(near_l), "far": stack(far_l),
         "mask_at_box": torch.from_numpy(np.stack(masks, 0)),
         "volumes": volumes, "weights": weights, "voxel_size": [float(v) for v in voxel_size],
-        "active_fraction": fracs, "H": H, "W": W,
+        "active_fraction": fracs, "H": H, "W": W, "verts_world": torch.from_numpy(world),
     }
     return scene
+
+
+def make_mask_views(scene, nv=4, H=128, W=128, radius=3, distance=None):
+    """Inputs of the masked renderers (lib/networks/renderer/if_clight_renderer_mmsk.py:12-45): `nv` training
+    views around the body with their world->camera RT (nv,3,4), intrinsics Ks (nv,3,3) and foreground masks
+    msks (nv,H,W) uint8 -- here the silhouette of the vertex cloud splatted with discs of `radius` pixels.
+    Returned with the leading batch dimension of 1 the reference expects (B = 1 only upstream)."""
+    verts = scene["verts_world"].numpy().astype(np.float64)
+    cb = scene["can_bounds"][0].numpy().astype(np.float64)
+    center = 0.5 * (cb[0] + cb[1])
+    ext = float(np.max(cb[1] - cb[0]))
+    distance = distance if distance is not None else 2.2 * ext
+    f = 0.9 * min(H, W) * distance / ext
+    RT, Ks, msks = [], [], []
+    yy, xx = np.mgrid[-radius:radius + 1, -radius:radius + 1]
+    disc = (yy ** 2 + xx ** 2) <= radius ** 2
+    for v in range(nv):
+        R, T = look_at_camera(center, distance, azimuth_deg=15.0 + 360.0 * v / nv, elevation_deg=8.0)
+        K = np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1.0]])
+        cam = verts @ R.T + T.ravel()
+        uv = cam @ K.T
+        u = np.round(uv[:, 0] / uv[:, 2]).astype(int)
+        w_ = np.round(uv[:, 1] / uv[:, 2]).astype(int)
+        m = np.zeros((H, W), np.uint8)
+        for dy, dx in zip(yy[disc], xx[disc]):
+            uu, vv = u + dx, w_ + dy
+            ok = (uu >= 0) & (uu < W) & (vv >= 0) & (vv < H)
+            m[vv[ok], uu[ok]] = 1
+        RT.append(np.concatenate([R, T], 1)); Ks.append(K); msks.append(m)
+    return {"RT": torch.from_numpy(np.stack(RT).astype(np.float32))[None],
+            "Ks": torch.from_numpy(np.stack(Ks).astype(np.float32))[None],
+            "msks": torch.from_numpy(np.stack(msks))[None], "mask_H": H, "mask_W": W}
 
 
 def scene_checksum(scene):

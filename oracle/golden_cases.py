@@ -21,6 +21,8 @@ CASES = {
                        dict(n_samples=48), 5),
     # full-size synth-313 body (out_sh [96,352,192], 137 MB of volumes), 512x512 all-hit view, strided rays
     "full_313": (dict(H=512, W=512, scale=1.0, all_hit=True), dict(n_samples=64), 521),
+    # f-1 masked renderer (if_clight_renderer_mmsk): 4 mask views, samples outside any silhouette get raw = 0
+    "mmsk_s64": (dict(H=48, W=48, scale=0.3, all_hit=True), dict(n_samples=64), 9),
 }
 
 
@@ -37,4 +39,6 @@ def build_case(name):
     if rkw.get("perturb", 0) > 0 and rkw.get("training", False):
         g = torch.Generator().manual_seed(1234)
         rkw["t_rand"] = torch.rand((scene["ray_o"].shape[0], scene["ray_o"].shape[1], rkw["n_samples"]), generator=g)
+    if name.startswith("mmsk"):
+        rkw["masks"] = synth.make_mask_views(scene, nv=4, H=96, W=96, radius=2)
     return scene, rkw

@@ -25,6 +25,9 @@ def main():
         scene, rkw = golden_cases.build_case(name)
         ret = ref_harness.reference_render(scene, **rkw)
         arrays = {k: v.numpy().astype(np.float32) for k, v in ret.items()}
+        if "masks" in rkw:
+            arrays["mask_sha256"] = np.frombuffer(synth.scene_checksum({**scene, "weights": {}, "volumes": [
+                rkw["masks"]["RT"], rkw["masks"]["Ks"], rkw["masks"]["msks"].float()]}).encode(), dtype=np.uint8)
         arrays["input_sha256"] = np.frombuffer(synth.scene_checksum(scene).encode(), dtype=np.uint8)
         arrays["torch_version"] = np.frombuffer(torch.__version__.encode(), dtype=np.uint8)
         path = os.path.join(out_dir, name + ".npz")

@@ -153,6 +153,62 @@ def get_pixel_value(w, ray_o, ray_d, near, far, feature_volume, sp_input, voxel_
             'depth_map': depth_map.view(n_batch, n_pixel)}
 
 
+# ------------------------------------------------------------------ f-1: masked renderer (vis_novel_view / vis_novel_pose)
+def prepare_inside_pts(pts, batch, H, W):
+    """lib/networks/renderer/if_clight_renderer_mmsk.py:12-45.  pts (1,n,S,3) -> inside (1, n*S) bool:
+    a sample is kept only if it projects into the foreground mask of EVERY training view
+    (H, W = int(cfg.H * cfg.ratio), int(cfg.W * cfg.ratio) upstream; B = 1 only)."""
+    sh = pts.shape
+    pts = pts.view(sh[0], -1, sh[3])
+    inside = None
+    for nv in range(batch['Ks'].size(1)):
+        R = batch['RT'][:, nv, :3, :3]
+        T = batch['RT'][:, nv, :3, 3]
+        pts_ = torch.matmul(pts, R.transpose(2, 1)) + T[:, None]
+        pts_ = torch.matmul(pts_, batch['Ks'][:, nv].transpose(2, 1))
+        pts2d = pts_[..., :2] / pts_[..., 2:]
+        pts2d = pts2d.round().long()
+        pts2d[..., 0] = torch.clamp(pts2d[..., 0], 0, W - 1)
+        pts2d[..., 1] = torch.clamp(pts2d[..., 1], 0, H - 1)
+        pts2d = pts2d[0]
+        msk = batch['msks'][0, nv]
+        ins = msk[pts2d[:, 1], pts2d[:, 0]][None].bool()
+        inside = ins if inside is None else inside * ins
+    return inside
+
+
+def get_pixel_value_mmsk(w, ray_o, ray_d, near, far, feature_volume, sp_input, voxel_size, n_samples, masks,
+                         white_bkgd=False):
+    """if_clight_renderer_mmsk.py:47-94: decoder only on inside samples, raw = 0 elsewhere."""
+    wpts, z_vals = get_sampling_points(ray_o, ray_d, near, far, n_samples)
+    inside = prepare_inside_pts(wpts, masks, masks["mask_H"], masks["mask_W"])
+    viewdir = ray_d / torch.norm(ray_d, dim=2, keepdim=True)
+    n_batch, n_pixel, n_sample = wpts.shape[:3]
+    wp = wpts.view(n_batch, n_pixel * n_sample, -1)
+    vd = viewdir[:, :, None].repeat(1, 1, n_sample, 1).contiguous().view(n_batch, n_pixel * n_sample, -1)
+    full_raw = torch.zeros([n_batch, n_pixel * n_sample, 4]).to(wp)
+    if inside.sum() > 0:
+        raw = calculate_density_color(w, wp[inside][None], vd[inside][None], feature_volume, sp_input, voxel_size)
+        full_raw[inside] = raw[0]
+    raw = full_raw.reshape(-1, n_sample, 4)
+    rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals.view(-1, n_sample), ray_d.reshape(-1, 3), white_bkgd)
+    return {'rgb_map': rgb_map.view(n_batch, n_pixel, -1), 'disp_map': disp_map.view(n_batch, n_pixel),
+            'acc_map': acc_map.view(n_batch, n_pixel), 'weights': weights.view(n_batch, n_pixel, -1),
+            'depth_map': depth_map.view(n_batch, n_pixel)}
+
+
+def render_mmsk(scene, masks, n_samples=64, white_bkgd=False, chunk=2048):
+    """Renderer.render (if_clight_renderer.py:94-122) driving the masked get_pixel_value."""
+    sp_input = prepare_sp_input(scene)
+    n_pixel = scene['ray_o'].shape[1]
+    ret_list = []
+    for i in range(0, n_pixel, chunk):
+        ret_list.append(get_pixel_value_mmsk(
+            scene['weights'], scene['ray_o'][:, i:i + chunk], scene['ray_d'][:, i:i + chunk], scene['near'][:, i:i + chunk],
+            scene['far'][:, i:i + chunk], scene['volumes'], sp_input, scene['voxel_size'], n_samples, masks, white_bkgd))
+    return {k: torch.cat([r[k] for r in ret_list], dim=1) for k in ret_list[0]}
+
+
 def render(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False, t_rand=None, chunk=2048,
            max_rays=None):
     """lib/networks/renderer/if_clight_renderer.py:94-122 with the dense volumes supplied

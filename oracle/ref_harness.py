@@ -91,7 +91,7 @@ def load_reference(cfg_file="configs/snapshot_exp/snapshot_f3c.yaml"):
 
 
 def reference_render(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False,
-                     t_rand=None, chunk=2048, num_train_frame=None, grad=False):
+                     t_rand=None, chunk=2048, num_train_frame=None, grad=False, masks=None):
     """Run the reference renderer on a synthetic scene dict (neuralbody_b200.synth).
 
     Follows Renderer.render (if_clight_renderer.py:94-122) literally, except that
@@ -118,9 +118,15 @@ def reference_render(scene, n_samples=64, perturb=0.0, training=False, white_bkg
     net.train(training)
     volumes = [v.clone().requires_grad_(grad) for v in scene["volumes"]]
     net.encode_sparse_voxels = lambda sp_input: volumes
-    renderer = if_clight_renderer.Renderer(net)
     batch = {k: scene[k] for k in ("coord", "out_sh", "bounds", "R", "Th", "latent_index",
                                    "ray_o", "ray_d", "near", "far")}
+    if masks is None:
+        renderer = if_clight_renderer.Renderer(net)
+    else:   # f-1: lib/networks/renderer/if_clight_renderer_mmsk.py (H, W come from cfg.H * cfg.ratio)
+        from lib.networks.renderer import if_clight_renderer_mmsk
+        cfg.H, cfg.W, cfg.ratio = int(masks["mask_H"]), int(masks["mask_W"]), 1.0
+        renderer = if_clight_renderer_mmsk.Renderer(net)
+        batch.update({k: masks[k] for k in ("RT", "Ks", "msks")})
 
     state = {"ofs": 0}
     real_rand = torch.rand

@@ -21,7 +21,8 @@ def make_net_and_renderer(scene, device="cuda:0"):
 
 
 def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False, t_rand=None,
-                   precision="fp32", device="cuda:0", want_raw=False, chunk=0, renderer=None, net=None, skip_empty=True):
+                   precision="fp32", device="cuda:0", want_raw=False, chunk=0, renderer=None, net=None, skip_empty=True,
+                   masks=None):
     """Render `scene` through the public API on the GPU; returns dict of CPU tensors."""
     cfg.N_samples = int(n_samples)
     cfg.perturb = float(perturb)
@@ -35,6 +36,18 @@ def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=
         net, renderer = make_net_and_renderer(scene, device)
     net.train(training)
     batch = {k: scene[k].to(device) for k in BATCH_KEYS}
+    if masks is not None:   # f-1: the masked renderer plugin, selected by path like any other renderer
+        import os
+        from neuralbody_b200.lib.networks.make_network import load_source
+        here = os.path.dirname(os.path.abspath(__file__))
+        path = os.path.join(here, "..", "neuralbody_b200", "lib", "networks", "renderer", "if_nerf_renderer_mmsk.py")
+        mren = load_source("neuralbody_b200.lib.networks.renderer.if_nerf_renderer_mmsk", os.path.abspath(path)).Renderer(net)
+        cfg.H, cfg.W, cfg.ratio = int(masks["mask_H"]), int(masks["mask_W"]), 1.0
+        batch.update({k: masks[k].to(device) for k in ("RT", "Ks", "msks")})
+        with torch.no_grad():
+            out = mren.render(batch)
+        torch.cuda.synchronize()
+        return {k: v.detach().cpu() for k, v in out.items()}
     if t_rand is not None or want_raw:
         sp_input = renderer.prepare_sp_input(batch)
         vol = net.encode_sparse_voxels(sp_input)

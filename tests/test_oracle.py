@@ -15,7 +15,7 @@ KEYS = ("rgb_map", "disp_map", "acc_map", "weights", "depth_map")
 @pytest.mark.parametrize("name", list(golden_cases.CASES))
 def test_oracle_matches_reference_golden(name):
     scene, rkw, gold = golden_case(name)
-    out = O.render(scene, **rkw)
+    out = O.render_mmsk(scene, **rkw) if "masks" in rkw else O.render(scene, **rkw)
     for k in KEYS:
         a, b = out[k].numpy(), gold[k]
         assert a.shape == b.shape
