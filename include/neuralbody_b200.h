@@ -142,6 +142,12 @@ typedef struct nb_render_args {
 
 int nb_render_fwd(const nb_render_args* args, void* stream);
 
+/* f-3: density on arbitrary world points.  Replaces Network.calculate_density (lib/networks/latent_xyzc.py:74-89), the
+ * alpha decoder of the mesh renderer (lib/networks/renderer/if_mesh_renderer.py:36-41).  Only the frame fields of `frame`
+ * are read (batch, R, Th, bounds, voxel_size, out_sh, level_dims, volume_blob/dtype, weights_blob); exact fp32 arithmetic.
+ * points: device (B, n_points, 3) world coordinates; sigma: device (B, n_points). */
+int nb_decode_density(const nb_render_args* frame, const float* points, int n_points, float* sigma, void* stream);
+
 /* number of kernels nb_render_fwd enqueues per call for the given precision (for launch accounting) */
 int nb_render_fwd_launches(int precision);
 

@@ -14,7 +14,7 @@ NB_NUM_LEVELS = 4
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
            "nb_render_fwd_launches", "nb_debug_tc_probe", "nb_render_bwd", "nb_render_save_bytes",
-           "nb_render_bwd_workspace_bytes"]
+           "nb_render_bwd_workspace_bytes", "nb_decode_density"]
 
 
 class nb_volume_level(C.Structure):
@@ -96,6 +96,8 @@ def load(path=None):
     lib.nb_render_save_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.nb_render_bwd_workspace_bytes.restype = C.c_size_t
     lib.nb_render_bwd_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.nb_decode_density.restype = C.c_int
+    lib.nb_decode_density.argtypes = [C.POINTER(nb_render_args), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.nb_debug_tc_probe.restype = C.c_int
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     if lib.nb_abi_version() != 1:

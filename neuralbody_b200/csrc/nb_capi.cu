@@ -431,6 +431,22 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
     return NB_OK;
 }
 
+int nb_decode_density(const nb_render_args* a, const float* points, int n_points, float* sigma, void* stream) {
+    if (!a || !points || !sigma || n_points < 0) { set_error("nb_decode_density: null argument"); return NB_ERR_BAD_ARG; }
+    // reuse the forward call's validation: only the frame / volume / weight fields matter here
+    nb_render_args tmp = *a;
+    static float dummy;   // never dereferenced: the density kernel touches no ray or output-map pointer
+    float* d = &dummy;
+    tmp.n_rays = 1; tmp.n_samples = 1;
+    tmp.ray_o = tmp.ray_d = tmp.near = tmp.far = d;
+    tmp.rgb_map = tmp.disp_map = tmp.acc_map = tmp.depth_map = d;
+    tmp.mask_msks = nullptr; tmp.save = nullptr;
+    RenderParams p;
+    const int stp = nbi_fill_render_params(&tmp, &p);
+    if (stp != NB_OK) return stp;
+    return launch_density_f32(p, a->volume_dtype, points, n_points, sigma, (cudaStream_t)stream);
+}
+
 int nb_render_fwd(const nb_render_args* a, void* stream) {
     if (a && a->n_rays == 0 && a->batch > 0 && a->n_samples > 0) return NB_OK;
     RenderParams p;

@@ -44,6 +44,7 @@ struct RenderParams {
 int launch_render_f32(const RenderParams& p, int volume_dtype, cudaStream_t stream);
 int launch_render_tc(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
 int launch_render_tc_sparse(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
+int launch_density_f32(const RenderParams& p, int volume_dtype, const float* pts, int n_points, float* sigma, cudaStream_t stream);
 bool tc_available();
 
 }  // namespace nb

@@ -132,6 +132,45 @@ __device__ __forceinline__ float4 load4<__half>(const __half* p) {
     return make_float4(a.x, a.y, b.x, b.y);
 }
 
+// Trilinear gather of one 64-point tile (a7, latent_xyzc.py:62-72): work item = (point, level, channel quad);
+// lanes run over the quads of one corner => contiguous 16-byte loads.  gcoord = [64][3] grid coords, X = [64][LDX].
+template <typename VT>
+__device__ __forceinline__ void gather_tile(const RenderParams& P, int b, const float* __restrict__ gcoord, float* __restrict__ X) {
+    const int tid = threadIdx.x;
+    constexpr int QUADS = kFeat / 4;   // 88 per point
+    for (int item = tid; item < TP * QUADS; item += NT) {
+        const int p = item / QUADS, q = item % QUADS;
+        int lvl, c0;   // channel offset inside the level
+        if (q < 8) { lvl = 0; c0 = q * 4; }
+        else if (q < 24) { lvl = 1; c0 = (q - 8) * 4; }
+        else if (q < 56) { lvl = 2; c0 = (q - 24) * 4; }
+        else { lvl = 3; c0 = (q - 56) * 4; }
+        const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+        Corners cn;
+        corner_setup(unnormalize(gcoord[p * 3 + 0], W), unnormalize(gcoord[p * 3 + 1], H),
+                     unnormalize(gcoord[p * 3 + 2], D), W, H, D, cn);
+        const VT* vol = reinterpret_cast<const VT*>(reinterpret_cast<const char*>(P.volume) + P.lvl_off[lvl]) +
+                        (size_t)b * P.lvl_bstride[lvl];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ATen accumulation order: tnw, tne, tsw, tse, bnw, bne, bsw, bse  (x fastest)
+#pragma unroll
+        for (int dz = 0; dz < 2; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    if (corner_valid(cn, dx, dy, dz, W, H, D)) {
+                        const float wgt = corner_weight(cn, dx, dy, dz);
+                        const size_t vox = ((size_t)(cn.z0 + dz) * H + (cn.y0 + dy)) * W + (cn.x0 + dx);
+                        const float4 v = load4<VT>(vol + vox * C + c0);
+                        acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y);
+                        acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
+                    }
+                }
+        *reinterpret_cast<float4*>(X + p * LDX + q * 4) = acc;
+    }
+}
+
 struct RayInfo {
     float o[3], d[3], near, far, norm, vd[3];
 };
@@ -225,42 +264,8 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
             }
             __syncthreads();
 
-            // ---- phase 2: trilinear gather (a7).  Work item = (point, level, channel quad);
-            // lanes run over the quads of one corner => contiguous 16-byte loads.
-            {
-                constexpr int QUADS = kFeat / 4;   // 88 per point
-                for (int item = tid; item < TP * QUADS; item += NT) {
-                    const int p = item / QUADS, q = item % QUADS;
-                    int lvl, c0;   // channel offset inside the level
-                    if (q < 8) { lvl = 0; c0 = q * 4; }
-                    else if (q < 24) { lvl = 1; c0 = (q - 8) * 4; }
-                    else if (q < 56) { lvl = 2; c0 = (q - 24) * 4; }
-                    else { lvl = 3; c0 = (q - 56) * 4; }
-                    const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
-                    Corners cn;
-                    corner_setup(unnormalize(gcoord[p * 3 + 0], W), unnormalize(gcoord[p * 3 + 1], H),
-                                 unnormalize(gcoord[p * 3 + 2], D), W, H, D, cn);
-                    const VT* vol = reinterpret_cast<const VT*>(reinterpret_cast<const char*>(P.volume) + P.lvl_off[lvl]) +
-                                    (size_t)b * P.lvl_bstride[lvl];
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    // ATen accumulation order: tnw, tne, tsw, tse, bnw, bne, bsw, bse  (x fastest)
-#pragma unroll
-                    for (int dz = 0; dz < 2; ++dz)
-#pragma unroll
-                        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                            for (int dx = 0; dx < 2; ++dx) {
-                                if (corner_valid(cn, dx, dy, dz, W, H, D)) {
-                                    const float wgt = corner_weight(cn, dx, dy, dz);
-                                    const size_t vox = ((size_t)(cn.z0 + dz) * H + (cn.y0 + dy)) * W + (cn.x0 + dx);
-                                    const float4 v = load4<VT>(vol + vox * C + c0);
-                                    acc.x = fmaf(v.x, wgt, acc.x); acc.y = fmaf(v.y, wgt, acc.y);
-                                    acc.z = fmaf(v.z, wgt, acc.z); acc.w = fmaf(v.w, wgt, acc.w);
-                                }
-                            }
-                    *reinterpret_cast<float4*>(X + p * LDX + q * 4) = acc;
-                }
-            }
+            // ---- phase 2: trilinear gather (a7)
+            gather_tile<VT>(P, b, gcoord, X);
             __syncthreads();
 
             // training forward: keep the per-point activations the backward pass needs (nb_render_bwd)
@@ -349,6 +354,57 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
     }
 }
 
+// f-3: density only, on arbitrary world points (Network.calculate_density, latent_xyzc.py:74-89; the mesh renderer's
+// alpha decoder, if_mesh_renderer.py:36-39): gather -> fc_0 -> fc_1 -> fc_2 -> alpha_fc.  64 points per tile.
+template <typename VT>
+__global__ void __launch_bounds__(NT, 1) density_f32_kernel(const __grid_constant__ RenderParams P, const float* __restrict__ pts,
+                                                            int n_points, float* __restrict__ sigma) {
+    extern __shared__ __align__(16) float smem[];
+    float* X = smem;
+    float* Y = X + TP * LDX;
+    float* Ws = Y + TP * LDY;
+    float* gcoord = Ws + 2 * KC * 256;
+    __shared__ FrameXf xf;
+    const int tid = threadIdx.x;
+    const float* wf = P.wf32;
+    const int tiles_per_frame = (n_points + TP - 1) / TP;
+    for (int t = blockIdx.x; t < tiles_per_frame * P.batch; t += gridDim.x) {
+        const int b = t / tiles_per_frame, p0 = (t % tiles_per_frame) * TP;
+        if (tid < 9) xf.R[tid] = __ldg(P.R + b * 9 + tid);
+        if (tid < 3) {
+            xf.Th[tid] = __ldg(P.Th + b * 3 + tid);
+            xf.min_dhw[tid] = __ldg(P.bounds + b * 6 + (2 - tid));
+            xf.voxel[tid] = P.voxel_size[tid];
+            xf.out_sh[tid] = P.out_sh[tid];
+        }
+        __syncthreads();
+        if (tid < TP) {
+            float gx = -4.f, gy = -4.f, gz = -4.f;
+            if (p0 + tid < n_points) {
+                const float* w = pts + ((size_t)b * n_points + p0 + tid) * 3;
+                world_to_grid(xf, __ldg(w), __ldg(w + 1), __ldg(w + 2), gx, gy, gz);
+            }
+            gcoord[tid * 3 + 0] = gx; gcoord[tid * 3 + 1] = gy; gcoord[tid * 3 + 2] = gz;
+        }
+        __syncthreads();
+        gather_tile<VT>(P, b, gcoord, X);
+        __syncthreads();
+        mlp_layer<kFeat, kHidden, LDX, LDY, true, false>(X, Y, wf + oW0t, wf + oB0, Ws, nullptr, nullptr);
+        mlp_layer<kHidden, kHidden, LDY, LDX, true, false>(Y, X, wf + oW1t, wf + oB1, Ws, nullptr, nullptr);
+        mlp_layer<kHidden, kHidden, LDX, LDY, true, false>(X, Y, wf + oW2t, wf + oB2, Ws, nullptr, nullptr);
+        {
+            const int p = tid >> 2, q = tid & 3;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int k = q; k < kHidden; k += 4) acc = fmaf(Y[p * LDY + k], __ldg(wf + oAlphaW + k), acc);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            if (q == 0 && p0 + p < n_points) sigma[(size_t)b * n_points + p0 + p] = acc + __ldg(wf + oAlphaB);
+        }
+        __syncthreads();
+    }
+}
+
 size_t smem_bytes(int G, int S) {
     size_t fl = (size_t)TP * LDX + (size_t)TP * LDY + 2 * KC * 256 + TP * 3 + 3 * TP /*pray, prayc, pins*/ + (size_t)G * kColor +
                 (size_t)((G * S + 3) & ~3);
@@ -381,6 +437,27 @@ int launch_render_f32(const RenderParams& p_in, int volume_dtype, cudaStream_t s
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("render_f32 launch failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
+    return NB_OK;
+}
+
+int launch_density_f32(const RenderParams& p, int volume_dtype, const float* pts, int n_points, float* sigma, cudaStream_t stream) {
+    const size_t smem = ((size_t)f32::TP * f32::LDX + (size_t)f32::TP * f32::LDY + 2 * f32::KC * 256 + f32::TP * 3) * 4;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int tiles = ((n_points + f32::TP - 1) / f32::TP) * p.batch;
+    if (tiles == 0) return NB_OK;
+    const int grid = tiles < sms ? tiles : sms;
+    cudaError_t e;
+    if (volume_dtype == NB_DTYPE_F32) {
+        e = cudaFuncSetAttribute(f32::density_f32_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) f32::density_f32_kernel<float><<<grid, f32::NT, smem, stream>>>(p, pts, n_points, sigma);
+    } else {
+        e = cudaFuncSetAttribute(f32::density_f32_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) f32::density_f32_kernel<__half><<<grid, f32::NT, smem, stream>>>(p, pts, n_points, sigma);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("density_f32 launch failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
     return NB_OK;
 }
 

@@ -57,6 +57,14 @@ class Network(nn.Module):
         xyzc = spconv.SparseConvTensor(code, coord, sp_input['out_sh'], sp_input['batch_size'])
         return self.xyzc_net(xyzc)
 
+    def calculate_density(self, wpts, feature_volume, sp_input):
+        """latent_xyzc.py:74-89 (called by the reference's mesh renderer, if_mesh_renderer.py:36-39): (B,P,3) -> (B,P,1),
+        evaluated by the fused density kernel (nb_decode_density); no PyTorch decoder path exists."""
+        if getattr(self, "_density_renderer", None) is None:
+            from neuralbody_b200.lib.networks.renderer.if_nerf_renderer import Renderer
+            object.__setattr__(self, "_density_renderer", Renderer(self))
+        return self._density_renderer.calculate_density(wpts, feature_volume, sp_input)
+
     def decoder_tensors(self):
         """The 17 decoder tensors in the order nb_decoder_weights expects."""
         return [self.fc_0.weight, self.fc_0.bias, self.fc_1.weight, self.fc_1.bias, self.fc_2.weight, self.fc_2.bias,

@@ -351,6 +351,37 @@ class Renderer:
         w.batch = int(latent_index.shape[0])
         return w, keep
 
+    def calculate_density(self, wpts, feature_volume, sp_input):
+        """Network.calculate_density (latent_xyzc.py:74-89) on arbitrary world points: (B,P,3) -> (B,P,1).
+        f-3: the alpha decoder of the mesh renderer (if_mesh_renderer.py:36-41); exact fp32 kernel."""
+        cfg = get_active_cfg()
+        dev = wpts.device
+        if dev.type != "cuda":
+            raise RuntimeError("calculate_density needs CUDA tensors: there is no CPU implementation")
+        B, Pn = int(wpts.shape[0]), int(wpts.shape[1])
+        with torch.cuda.device(dev), torch.no_grad():
+            vol_blob, dims = self.pack_volume(feature_volume, capi.NB_DTYPE_F32)
+            w_blob = self.pack_weights(sp_input['latent_index'], dev)
+            pts = _f32c(wpts, dev)
+            R, Th = _f32c(sp_input['R'], dev), _f32c(sp_input['Th'], dev).reshape(B, 3)
+            bounds = _f32c(sp_input['bounds'], dev)
+            sigma = torch.empty((B, Pn, 1), dtype=torch.float32, device=dev)
+            a = capi.nb_render_args()
+            a.batch = B
+            a.R, a.Th, a.bounds = R.data_ptr(), Th.data_ptr(), bounds.data_ptr()
+            for i in range(3):
+                a.voxel_size[i] = float(cfg.voxel_size[i])
+                a.out_sh[i] = int(sp_input['out_sh'][i])
+            for l in range(capi.NB_NUM_LEVELS):
+                for j in range(4):
+                    a.level_dims[l][j] = dims[l][j]
+            a.volume_blob, a.volume_dtype, a.weights_blob = vol_blob.data_ptr(), capi.NB_DTYPE_F32, w_blob.data_ptr()
+            a.precision = capi.NB_PRECISION_FP32
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            capi.check(self.lib.nb_decode_density(C.byref(a), pts.data_ptr(), Pn, sigma.data_ptr(), C.c_void_p(stream)),
+                       "nb_decode_density")
+        return sigma
+
     def get_pixel_value(self, ray_o, ray_d, near, far, feature_volume, sp_input, batch):
         """if_clight_renderer.py:62-92: same signature, same returned dict."""
         return self.render_rays(ray_o, ray_d, near, far, feature_volume, sp_input)

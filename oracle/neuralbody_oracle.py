@@ -108,6 +108,17 @@ def calculate_density_color(w, wpts, viewdir, feature_volume, sp_input, voxel_si
     return raw.transpose(1, 2)
 
 
+def calculate_density(w, wpts, feature_volume, sp_input, voxel_size):
+    """lib/networks/latent_xyzc.py:74-89 (f-3, the mesh renderer's alpha decoder): (B,P,3) -> (B,P,1)."""
+    ppts = pts_to_can_pts(wpts, sp_input['R'], sp_input['Th'])
+    grid_coords = get_grid_coords(ppts, sp_input['bounds'], sp_input['out_sh'], voxel_size)
+    xyzc_features = interpolate_features(grid_coords, feature_volume)
+    net = F.relu(_conv(w, "fc_0", xyzc_features))
+    net = F.relu(_conv(w, "fc_1", net))
+    net = F.relu(_conv(w, "fc_2", net))
+    return _conv(w, "alpha_fc", net).transpose(1, 2)
+
+
 # ------------------------------------------------------------------ a10 composite
 def raw2outputs(raw, z_vals, rays_d, white_bkgd=False):
     """lib/networks/renderer/nerf_net_utils.py:6-51 (raw_noise_std = 0 as in every config)."""

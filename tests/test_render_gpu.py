@@ -81,6 +81,23 @@ def test_empty_sample_skipping_is_bit_exact(name, precision):
         assert torch.equal(torch.nan_to_num(dense[k], nan=-1.0), torch.nan_to_num(sparse[k], nan=-1.0)), k
 
 
+def test_density_only_decoder_matches_oracle():
+    """f-3: Network.calculate_density on a voxel grid of world points (mesh extraction, if_mesh_renderer.py)."""
+    scene, _, _ = golden_case("batch2_s32")
+    net, ren = G.make_net_and_renderer(scene)
+    g = torch.Generator().manual_seed(5)
+    lo, hi = scene["can_bounds"][0, 0], scene["can_bounds"][0, 1]
+    pts = (torch.rand((2, 5000, 3), generator=g) * 1.2 - 0.1) * (hi - lo) + lo          # some points outside the box
+    sp = O.prepare_sp_input(scene)
+    want = O.calculate_density(scene["weights"], pts, scene["volumes"], sp, scene["voxel_size"])
+    batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}
+    spg = ren.prepare_sp_input(batch)
+    got = net.calculate_density(pts.cuda(), net.encode_sparse_voxels(spg), spg).cpu()
+    assert got.shape == want.shape == (2, 5000, 1)
+    assert float((got - want).abs().max()) < 2e-4
+    assert float(want.max()) > 5.0 and float(want.min()) < -5.0          # not vacuous
+
+
 def test_chunked_equals_single_launch():
     scene, rkw, _ = golden_case("eval_s64")
     a = G.render_product(scene, precision="fp32", **rkw)
