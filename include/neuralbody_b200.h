@@ -148,6 +148,22 @@ int nb_render_fwd(const nb_render_args* args, void* stream);
  * points: device (B, n_points, 3) world coordinates; sigma: device (B, n_points). */
 int nb_decode_density(const nb_render_args* frame, const float* points, int n_points, float* sigma, void* stream);
 
+/* f-2: ray generation on the device.  Replaces the per-view numpy of get_rays (lib/utils/if_nerf/if_nerf_data_utils.py:8-21)
+ * and get_near_far (:54-69) as called from image_rays (lib/utils/render_utils.py:120-137): fp64 arithmetic like upstream, fp32
+ * results.  Writes ALL H*W pixels (row-major) plus mask_at_box; the caller compacts with the mask (upstream: ray_o[mask_at_box]).
+ * K_inv, R, T: the view's inverse intrinsics / world->camera rotation / translation (host memory, row-major doubles);
+ * bounds: host (2,3) doubles, the world box (can_bounds). */
+typedef struct nb_camera {
+    double K_inv[9];
+    double R[9];
+    double T[3];
+    double bounds[6];
+    int H, W;
+} nb_camera;
+int nb_gen_rays(const nb_camera* cam, float* ray_o /* device (H*W,3) */, float* ray_d /* device (H*W,3) */,
+                float* near /* device (H*W) */, float* far /* device (H*W) */, unsigned char* mask_at_box /* device (H*W) */,
+                void* stream);
+
 /* number of kernels nb_render_fwd enqueues per call for the given precision (for launch accounting) */
 int nb_render_fwd_launches(int precision);
 

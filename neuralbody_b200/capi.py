@@ -14,7 +14,7 @@ NB_NUM_LEVELS = 4
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
            "nb_render_fwd_launches", "nb_debug_tc_probe", "nb_render_bwd", "nb_render_save_bytes",
-           "nb_render_bwd_workspace_bytes", "nb_decode_density"]
+           "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays"]
 
 
 class nb_volume_level(C.Structure):
@@ -26,6 +26,11 @@ class nb_decoder_weights(C.Structure):
         "fc0_w", "fc0_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b", "alpha_w", "alpha_b", "feature_w", "feature_b",
         "latent_w", "latent_b", "view_w", "view_b", "rgb_w", "rgb_b", "latent", "latent_index")] + \
         [("num_train_frame", C.c_int), ("batch", C.c_int)]
+
+
+class nb_camera(C.Structure):
+    _fields_ = [("K_inv", C.c_double * 9), ("R", C.c_double * 9), ("T", C.c_double * 3), ("bounds", C.c_double * 6),
+                ("H", C.c_int), ("W", C.c_int)]
 
 
 LevelDims = (C.c_int * 4) * NB_NUM_LEVELS
@@ -98,6 +103,8 @@ def load(path=None):
     lib.nb_render_bwd_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.nb_decode_density.restype = C.c_int
     lib.nb_decode_density.argtypes = [C.POINTER(nb_render_args), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.nb_gen_rays.restype = C.c_int
+    lib.nb_gen_rays.argtypes = [C.POINTER(nb_camera)] + [C.c_void_p] * 6
     lib.nb_debug_tc_probe.restype = C.c_int
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     if lib.nb_abi_version() != 1:

@@ -73,3 +73,29 @@ def test_pack_weights_fold_matches_fp64_torch():
     # bc lives after the fp16 stream + fold scratch; find it through the sigma-free identity of the render itself:
     # (layout offsets are internal) -> check through a render of a point with zero features instead
     assert bc.shape == (2, 128)
+
+
+def test_gen_rays_matches_reference_numpy():
+    """f-2: nb_gen_rays vs get_rays / get_near_far (restated literally in neuralbody_b200/synth.py)."""
+    from neuralbody_b200 import synth, rays
+    scene, _, _ = golden_case("eval_s64")
+    cb = scene["can_bounds"][0].numpy()
+    center = 0.5 * (cb[0] + cb[1]).astype(np.float64)
+    for az, f in ((20.0, 150.0), (133.0, 90.0)):
+        R, T = synth.look_at_camera(center, 0.9, az)
+        H = W = 96
+        K = np.array([[f, 0, W / 2.0], [0, f * 1.1, H / 2.0], [0, 0, 1.0]])
+        ro, rd = synth.get_rays(H, W, K, R, T)
+        ro = ro.reshape(-1, 3).astype(np.float32); rd = rd.reshape(-1, 3).astype(np.float32)
+        near, far, mask = synth.get_near_far(cb, ro, rd)
+        RT = np.concatenate([R, T], 1)
+        g_ro, g_rd, g_near, g_far, g_mask = rays.image_rays(RT, K, cb, H, W)
+        gm = g_mask.cpu().numpy()
+        assert (gm != mask).mean() < 1e-3                    # grazing rays may flip
+        both = mask & gm
+        sel_ref = both[mask]; sel_gpu = both[gm]
+        np.testing.assert_allclose(g_ro.cpu().numpy()[sel_gpu], ro[mask][sel_ref], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(g_rd.cpu().numpy()[sel_gpu], rd[mask][sel_ref], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(g_near.cpu().numpy()[sel_gpu], near.astype(np.float32)[sel_ref], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(g_far.cpu().numpy()[sel_gpu], far.astype(np.float32)[sel_ref], rtol=1e-5, atol=1e-5)
+        assert 0 < mask.sum() < H * W
