@@ -248,7 +248,7 @@ def run_product(args, rank, world, local_rank):
             batch = {k: v.to(dev, non_blocking=True) for k, v in host_local.items()}
             ret = ren.render(batch)
             if world > 1:
-                g = nbdist.unpack_slab(nbdist.gather_slabs(nbdist.pack_slab(ret)), n_local * world)
+                g = nbdist.unpack_slab(nbdist.gather_slabs(nbdist.pack_slab(ret)), H * W)
             pin_rgb.copy_(ret["rgb_map"], non_blocking=True)
             pin_depth.copy_(ret["depth_map"], non_blocking=True)
         torch.cuda.synchronize(dev)
@@ -353,7 +353,7 @@ def run_product(args, rank, world, local_rank):
         "config": {"workload": "synth-313 512x512 all-hit view x %d per step, 64 samples/ray, eval, perturb=0 "
                                "(BASELINE configs[1])" % n_views,
                    "precision": precision, "skip_empty": (precision != "fp32" and not args.dense), "rays_per_step": rays_per_step, "samples_per_ray": S,
-                   "parallelism": "ray-sharded x%d, one all-gather per view" % world if world > 1 else "single GPU",
+                   "parallelism": "ray-sharded x%d (interleaved 256-ray chunks), one all-gather per view" % world if world > 1 else "single GPU",
                    "l2": "256 MiB written between timed steps (untimed) to flush the 126 MB L2",
                    "volume": "fp16 channels-last 69 MB, packed once (cached across views of the frame)"
                              if precision == "tc_fp16" else "fp32 channels-last 137 MB, packed once (cached across views)"},

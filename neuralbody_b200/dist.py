@@ -23,18 +23,30 @@ def shard_bounds(n_rays, rank, world):
     return start, stop, per
 
 
-def shard_batch(batch, rank, world):
-    """Slice the per-ray tensors of a reference-style batch dict to this rank's slab.  A rank whose
-    slab would be short is padded by repeating the last ray (padding is dropped after the gather)."""
+def shard_indices(n_rays, rank, world, chunk=256):
+    """Interleaved sharding: ray chunk c (of `chunk` consecutive rays) goes to rank c % world.  With exact empty-sample
+    skipping the cost of a ray depends on how much body it crosses, so contiguous image slabs are unbalanced
+    (SURVEY 8e); interleaved chunks give every rank the same mix.  Returns (idx, per): idx is a LongTensor of
+    `per` ray indices (equal on all ranks; short shards are padded by repeating the last real ray)."""
+    n_chunks = (n_rays + chunk - 1) // chunk
+    per_chunks = (n_chunks + world - 1) // world
+    per = per_chunks * chunk
+    mine = torch.arange(rank, n_chunks, world) if rank < n_chunks else torch.zeros(0, dtype=torch.long)
+    idx = (mine[:, None] * chunk + torch.arange(chunk)[None, :]).reshape(-1)
+    idx = idx[idx < n_rays]
+    if idx.numel() < per:
+        pad = idx[-1:] if idx.numel() else torch.full((1,), max(n_rays - 1, 0), dtype=torch.long)
+        idx = torch.cat([idx, pad.expand(per - idx.numel())])
+    return idx, per
+
+
+def shard_batch(batch, rank, world, chunk=256):
+    """Slice the per-ray tensors of a reference-style batch dict to this rank's interleaved shard."""
     n = batch["ray_o"].shape[1]
-    start, stop, per = shard_bounds(n, rank, world)
+    idx, per = shard_indices(n, rank, world, chunk)
     out = dict(batch)
     for k in ("ray_o", "ray_d", "near", "far"):
-        t = batch[k][:, start:stop]
-        if t.shape[1] < per:
-            last = batch[k][:, n - 1:n]
-            t = torch.cat([t] + [last] * (per - t.shape[1]), dim=1)
-        out[k] = t.contiguous()
+        out[k] = batch[k].index_select(1, idx.to(batch[k].device)).contiguous()
     return out, per
 
 
@@ -44,10 +56,12 @@ def pack_slab(ret):
     return torch.cat(parts, dim=-1).contiguous()
 
 
-def unpack_slab(slab, n_rays):
-    """(world, B, per, 6) gathered slabs -> dict of (B, n_rays, *) in the original ray order."""
+def unpack_slab(slab, n_rays, chunk=256):
+    """(world, B, per, 6) gathered slabs -> dict of (B, n_rays, *) in the original ray order (fixed permutation)."""
     world, B, per, _ = slab.shape
-    full = slab.permute(1, 0, 2, 3).reshape(B, world * per, SLAB_WIDTH)[:, :n_rays]
+    perm = torch.cat([shard_indices(n_rays, r, world, chunk)[0] for r in range(world)]).to(slab.device)
+    full = torch.empty((B, n_rays, SLAB_WIDTH), dtype=slab.dtype, device=slab.device)
+    full[:, perm] = slab.permute(1, 0, 2, 3).reshape(B, world * per, SLAB_WIDTH)   # padding duplicates rewrite equal values
     out, c = {}, 0
     for k, w in SLAB_KEYS:
         out[k] = full[..., c:c + w] if w > 1 else full[..., c]
@@ -68,11 +82,11 @@ def gather_slabs(local_slab, group=None):
     return out
 
 
-def render_sharded(render_fn, batch, group=None):
+def render_sharded(render_fn, batch, group=None, chunk=256):
     """render_fn(batch) -> dict (e.g. Renderer.render).  Every rank returns the full image dict."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     n = batch["ray_o"].shape[1]
-    local, _ = shard_batch(batch, rank, world)
+    local, _ = shard_batch(batch, rank, world, chunk)
     ret = render_fn(local)
     gathered = gather_slabs(pack_slab(ret), group)
-    return unpack_slab(gathered, n)
+    return unpack_slab(gathered, n, chunk)

@@ -34,7 +34,7 @@ def _worker(rank, world, port, n_rays, out_dir):
             return O.render(sc, n_samples=16)
 
         batch = {k: scene[k] for k in ("coord", "out_sh", "bounds", "R", "Th", "latent_index", "ray_o", "ray_d", "near", "far")}
-        full = nbdist.render_sharded(render_fn, batch)
+        full = nbdist.render_sharded(render_fn, batch, chunk=8)
         torch.save({k: v.clone() for k, v in full.items()}, os.path.join(out_dir, "rank%d.pt" % rank))
         if rank == 0:
             torch.save(render_fn(batch), os.path.join(out_dir, "single.pt"))
@@ -54,13 +54,16 @@ def test_ray_sharded_render_equals_single_process(tmp_path, n_rays):
             assert torch.equal(torch.nan_to_num(got[k]), torch.nan_to_num(single[k])), (r, k)
 
 
-def test_shard_bounds_cover_all_rays_once():
-    from neuralbody_b200.dist import shard_bounds
-    for n in (0, 1, 7, 262144, 262145):
+def test_interleaved_shards_cover_all_rays():
+    from neuralbody_b200.dist import shard_indices
+    for n in (1, 7, 300, 262144, 262145):
         for world in (1, 2, 3, 8):
-            seen = []
-            for r in range(world):
-                a, b, per = shard_bounds(n, r, world)
-                assert b - a <= per
-                seen += list(range(a, b))
-            assert seen == list(range(n))
+            for chunk in (4, 256):
+                seen, pers = [], set()
+                for r in range(world):
+                    idx, per = shard_indices(n, r, world, chunk)
+                    assert idx.numel() == per and int(idx.max()) < n
+                    pers.add(per)
+                    seen += idx.tolist()
+                assert len(pers) == 1                         # equal shard sizes => one plain all-gather
+                assert sorted(set(seen)) == list(range(n))   # every ray rendered (padding only duplicates)
