@@ -2,7 +2,7 @@
 //
 // Same tile pipeline as nb_render_tc.cu (producers -> K-segmented layer-0 operand, weight-stream ring,
 // tcgen05 MMAs with TMEM-resident activations, epilogue warps), but the 128 rows of a tile are no longer
-// "two whole rays": a CTA takes a BLOCK of rays (<= 512 samples), classifies every sample with the
+// "two whole rays": a CTA takes a BLOCK of rays (<= 1024 samples), classifies every sample with the
 // cell-occupancy bitmaps built by nb_pack_volume, and packs only the occupied samples into tiles.
 //
 // Why this is exact.  A sample whose four trilinear cells are all unoccupied interpolates features that are
@@ -39,17 +39,16 @@ constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_W
 constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;               // 704
 constexpr int PROD_THREADS = PROD_WARPS * 32;                     // 512
 constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);
-constexpr int MAXS = 512;                                          // samples per ray block (= producer threads)
+constexpr int MAXS = 1024;                                         // samples per ray block (2 classification passes of 512)
 
 // shared-memory map (bytes)
 constexpr int OFF_SEG = 0;
 constexpr int OFF_ONES = OFF_SEG + SEG_RING_BYTES;
 constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;
 constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;
-constexpr int OFF_LGEOM = OFF_RING + NUM_SLOTS * SLOT_BYTES;       // float4[512] compact list: (wx,wy,wz,z)      producer-owned
-constexpr int OFF_LGRID = OFF_LGEOM + MAXS * 16;                   // float4[512] compact list: (gx,gy,gz,sample) producer-owned
-constexpr int OFF_RAWB = OFF_LGRID + MAXS * 16;                    // float4[512] (r,g,b,sigma) per block sample  epilogue-owned
-constexpr int OFF_ZB = OFF_RAWB + MAXS * 16;                       // float[512] z per block sample               epilogue-owned
+constexpr int OFF_LIST = OFF_RING + NUM_SLOTS * SLOT_BYTES;        // float4[1024] compact list: (wx,wy,wz,sample) producer-owned
+constexpr int OFF_RAWB = OFF_LIST + MAXS * 16;                     // float4[1024] (r,g,b,sigma) per block sample epilogue-owned
+constexpr int OFF_ZB = OFF_RAWB + MAXS * 16;                       // float[1024] z per block sample              epilogue-owned
 constexpr int OFF_ROWS = OFF_ZB + MAXS * 4;                        // int[128] block sample of each tile row      epilogue-owned
 constexpr int OFF_XF = OFF_ROWS + TP * 4;                          // FrameXf
 constexpr int OFF_INFO = OFF_XF + 128;                             // TileInfo[2]
@@ -122,8 +121,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
     if (warp >= PROD_WARP0) {
         const int pt = tid - PROD_WARP0 * 32;          // 0..511 = sample of the block during classification
         const int pw = warp - PROD_WARP0;
-        float4* lgeom = reinterpret_cast<float4*>(smem + OFF_LGEOM);
-        float4* lgrid = reinterpret_cast<float4*>(smem + OFF_LGRID);
+        float4* lst = reinterpret_cast<float4*>(smem + OFF_LIST);
         int* wcnt = reinterpret_cast<int*>(smem + OFF_WCNT);
         FrameXf* xf = reinterpret_cast<FrameXf*>(smem + OFF_XF);
         const unsigned char* volbase = reinterpret_cast<const unsigned char*>(P.volume);
@@ -157,49 +155,48 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 xf->out_sh[pt] = P.out_sh[pt];
             }
             named_bar_sync(1, PROD_THREADS);
-            // ---- classify: one sample per thread
-            const int ry = pt / S, s = pt % S;
-            bool occ = false;
-            float4 gm = make_float4(0.f, 0.f, 0.f, 0.f), gr = make_float4(-4.f, -4.f, -4.f, 0.f);
-            if (ry < bc.nr) {
-                const size_t ri = (size_t)bc.b * P.n_rays + bc.r0 + ry;
-                const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
-                const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
-                const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
-                gm.x = __fadd_rn(ox, __fmul_rn(dx, z));
-                gm.y = __fadd_rn(oy, __fmul_rn(dy, z));
-                gm.z = __fadd_rn(oz, __fmul_rn(dz, z));
-                gm.w = z;
-                world_to_grid(*xf, gm.x, gm.y, gm.z, gr.x, gr.y, gr.z);
-                gr.w = __int_as_float(pt);
-                occ = !can_skip;
-                const bool inside = P.mask_nv == 0 || inside_masks(P, gm.x, gm.y, gm.z);   // f-1 mask views
+            // ---- classify (one sample per thread, MAXS / 512 passes) + order-preserving compaction of the occupied ones
+            int total = 0;
+            for (int pass = 0; pass < MAXS / PROD_THREADS; ++pass) {
+                const int j = pass * PROD_THREADS + pt;          // sample of the block
+                const int ry = j / S, s = j % S;
+                bool occ = false;
+                float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ry < bc.nr) {
+                    const size_t ri = (size_t)bc.b * P.n_rays + bc.r0 + ry;
+                    const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
+                    const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
+                    const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+                    gm.x = __fadd_rn(ox, __fmul_rn(dx, z));
+                    gm.y = __fadd_rn(oy, __fmul_rn(dy, z));
+                    gm.z = __fadd_rn(oz, __fmul_rn(dz, z));
+                    gm.w = __int_as_float(j);
+                    float gx, gy, gz;
+                    world_to_grid(*xf, gm.x, gm.y, gm.z, gx, gy, gz);
+                    occ = !can_skip;
+                    const bool inside = P.mask_nv == 0 || inside_masks(P, gm.x, gm.y, gm.z);   // f-1 mask views
 #pragma unroll
-                for (int lvl = 0; lvl < 4 && !occ && inside; ++lvl) {
-                    const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
-                    Corners cn;
-                    corner_setup(unnormalize(gr.x, W), unnormalize(gr.y, H), unnormalize(gr.z, D), W, H, D, cn);
-                    if (cn.x0 != -2) {
-                        const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)bc.b * P.occ_bstride[lvl];
-                        const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
-                        occ = (__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u;
+                    for (int lvl = 0; lvl < 4 && !occ && inside; ++lvl) {
+                        const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+                        Corners cn;
+                        corner_setup(unnormalize(gx, W), unnormalize(gy, H), unnormalize(gz, D), W, H, D, cn);
+                        if (cn.x0 != -2) {
+                            const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)bc.b * P.occ_bstride[lvl];
+                            const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
+                            occ = (__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u;
+                        }
                     }
+                    occ = occ && inside;
                 }
-                occ = occ && inside;
-            }
-            // ---- order-preserving compaction of the occupied samples
-            const uint32_t bal = __ballot_sync(0xffffffffu, occ);
-            if (lane == 0) wcnt[pw] = __popc(bal);
-            named_bar_sync(1, PROD_THREADS);
-            int base = 0, total = 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, occ);
+                if (lane == 0) wcnt[pw] = __popc(bal);
+                named_bar_sync(1, PROD_THREADS);
+                int base = total;
 #pragma unroll
-            for (int w = 0; w < PROD_WARPS; ++w) { const int c = wcnt[w]; base += (w < pw) ? c : 0; total += c; }
-            if (occ) {
-                const int pos = base + __popc(bal & ((1u << lane) - 1));
-                lgeom[pos] = gm;
-                lgrid[pos] = gr;
+                for (int w = 0; w < PROD_WARPS; ++w) { const int c = wcnt[w]; base += (w < pw) ? c : 0; total += c; }
+                if (occ) lst[base + __popc(bal & ((1u << lane) - 1))] = gm;
+                named_bar_sync(1, PROD_THREADS);
             }
-            named_bar_sync(1, PROD_THREADS);
             n_occ += (pt == 0) ? total : 0;
             const int ntile = (total + TP - 1) / TP;
             tr.ev(3);                                   // block classified
@@ -214,7 +211,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
 #pragma unroll
                 for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
                     const int row = grp + 64 * pp;
-                    g[pp] = row < nrows ? lgrid[off + row] : make_float4(-4.f, -4.f, -4.f, 0.f);
+                    g[pp] = make_float4(-4.f, -4.f, -4.f, 0.f);
+                    if (row < nrows) {
+                        const float4 e = lst[off + row];
+                        world_to_grid(*xf, e.x, e.y, e.z, g[pp].x, g[pp].y, g[pp].z);
+                    }
                 }
                 uint32_t coff[PTS_PER_GROUP][8];
                 float cw[PTS_PER_GROUP][8];
@@ -455,8 +456,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
     else {
         const int row = tid;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
-        const float4* lgeom = reinterpret_cast<const float4*>(smem + OFF_LGEOM);
-        const float4* lgrid = reinterpret_cast<const float4*>(smem + OFF_LGRID);
+        const float4* lst = reinterpret_cast<const float4*>(smem + OFF_LIST);
         float4* rawb = reinterpret_cast<float4*>(smem + OFF_RAWB);
         float* zb = reinterpret_cast<float*>(smem + OFF_ZB);
         unsigned char* PE = smem + OFF_PE;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
             // copy this row's entry of the producer-owned list, then release the message
             float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
             int smp = -1;
-            if (row < nrows) { gm = lgeom[off + row]; smp = __float_as_int(lgrid[off + row].w); }
+            if (row < nrows) { gm = lst[off + row]; smp = __float_as_int(gm.w); }
             tc::mbar_arrive(&bars[BAR_MSG_FREE]);
             ++msg;
             if (flags & 4) break;
