@@ -206,6 +206,10 @@ class Renderer:
         needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in params) or
                                                   any(v.requires_grad for v in feature_volume))
         precision = capi.NB_PRECISION_FP32 if needs_grad else self._precision()
+        if S > 128 and precision != capi.NB_PRECISION_FP32:
+            # the tensor-core kernels tile whole rays into 128-row MMA tiles (N_samples <= 128, every reference config);
+            # longer rays run on the exact CUDA kernel (still one fused launch, still no PyTorch op in the ray loop)
+            precision = capi.NB_PRECISION_FP32
         if t_rand is None and float(cfg.perturb) > 0. and self.net.training:
             t_rand = self._draw_t_rand(B, n, S, dev)
         call = {

@@ -98,6 +98,18 @@ def test_density_only_decoder_matches_oracle():
     assert float(want.max()) > 5.0 and float(want.min()) < -5.0          # not vacuous
 
 
+def test_long_rays_run_on_the_exact_kernel():
+    """N_samples > 128 (e.g. 64 coarse + 128 importance merged) is served by the exact fused kernel."""
+    scene, rkw, _ = golden_case("eval_s64")
+    sub = dict(scene)
+    for k in ("ray_o", "ray_d", "near", "far"):
+        sub[k] = scene[k][:, :64].contiguous()
+    out = G.render_product(sub, precision="tc_fp16x3", n_samples=192)
+    ref = O.render(sub, n_samples=192)
+    for k in ("rgb_map", "depth_map", "acc_map"):
+        assert float((out[k] - ref[k]).abs().max()) < 1e-4, k
+
+
 def test_chunked_equals_single_launch():
     scene, rkw, _ = golden_case("eval_s64")
     a = G.render_product(scene, precision="fp32", **rkw)
