@@ -71,7 +71,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIB_PATH
+    path = path or os.environ.get("NB_LIB_PATH") or _build.LIB_PATH
     if not os.path.exists(path):
         raise RuntimeError(
             "libneuralbody_b200.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
@@ -109,7 +109,7 @@ def load(path=None):
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     if lib.nb_abi_version() != 1:
         raise RuntimeError("libneuralbody_b200.so ABI version mismatch")
-    if path == _build.LIB_PATH:
+    if path in (_build.LIB_PATH, os.environ.get("NB_LIB_PATH")):
         _lib = lib
     return lib
 
