@@ -170,23 +170,26 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                     gm.x = __fadd_rn(ox, __fmul_rn(dx, z));
                     gm.y = __fadd_rn(oy, __fmul_rn(dy, z));
                     gm.z = __fadd_rn(oz, __fmul_rn(dz, z));
-                    gm.w = __int_as_float(j);
                     float gx, gy, gz;
                     world_to_grid(*xf, gm.x, gm.y, gm.z, gx, gy, gz);
-                    occ = !can_skip;
+                    // per-level cell occupancy (bit l = the sample's level-l cell holds a non-zero voxel); the gather reuses it
+                    uint32_t lm = 0;
                     const bool inside = P.mask_nv == 0 || inside_masks(P, gm.x, gm.y, gm.z);   // f-1 mask views
+                    if (inside) {
 #pragma unroll
-                    for (int lvl = 0; lvl < 4 && !occ && inside; ++lvl) {
-                        const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
-                        Corners cn;
-                        corner_setup(unnormalize(gx, W), unnormalize(gy, H), unnormalize(gz, D), W, H, D, cn);
-                        if (cn.x0 != -2) {
-                            const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)bc.b * P.occ_bstride[lvl];
-                            const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
-                            occ = (__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u;
+                        for (int lvl = 0; lvl < 4; ++lvl) {
+                            const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+                            Corners cn;
+                            corner_setup(unnormalize(gx, W), unnormalize(gy, H), unnormalize(gz, D), W, H, D, cn);
+                            if (cn.x0 != -2) {
+                                const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)bc.b * P.occ_bstride[lvl];
+                                const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
+                                lm |= ((__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u) << lvl;
+                            }
                         }
                     }
-                    occ = occ && inside;
+                    occ = inside && (lm != 0u || !can_skip);
+                    gm.w = __int_as_float(j | (int)(lm << 16));
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, occ);
                 if (lane == 0) wcnt[pw] = __popc(bal);
@@ -215,6 +218,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                     if (row < nrows) {
                         const float4 e = lst[off + row];
                         world_to_grid(*xf, e.x, e.y, e.z, g[pp].x, g[pp].y, g[pp].z);
+                        g[pp].w = __int_as_float(__float_as_int(e.w) >> 16);     // per-level occupancy bits
                     }
                 }
                 uint32_t coff[PTS_PER_GROUP][8];
@@ -241,22 +245,21 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                             cur_lvl = lvl;
                             const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
                             vol = reinterpret_cast<const VT*>(volbase + P.lvl_off[lvl]) + (size_t)bc.b * P.lvl_bstride[lvl];
-                            const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)bc.b * P.occ_bstride[lvl];
+                            // lane t of the row's 8-lane group sets up corner t; the group exchanges the 8 (weight, offset) pairs
+                            const int ddx = t & 1, ddy = (t >> 1) & 1, ddz = t >> 2;
 #pragma unroll
                             for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
                                 Corners cn;
                                 corner_setup(unnormalize(g[pp].x, W), unnormalize(g[pp].y, H), unnormalize(g[pp].z, D), W, H, D, cn);
-                                occupied[pp] = false;
-                                if (cn.x0 != -2) {
-                                    const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
-                                    occupied[pp] = (__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u;
-                                }
+                                occupied[pp] = (__float_as_int(g[pp].w) >> lvl) & 1;
+                                const bool ok = occupied[pp] && corner_valid(cn, ddx, ddy, ddz, W, H, D);
+                                const float w_own = ok ? __fmul_rn(__fmul_rn(ddx ? cn.wx[1] : cn.wx[0], ddy ? cn.wy[1] : cn.wy[0]),
+                                                                   ddz ? cn.wz[1] : cn.wz[0]) : 0.f;
+                                const uint32_t o_own = ok ? (uint32_t)((((cn.z0 + ddz) * H + (cn.y0 + ddy)) * W + (cn.x0 + ddx)) * C) : 0u;
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
-                                    const int ddx = c & 1, ddy = (c >> 1) & 1, ddz = c >> 2;
-                                    const bool ok = occupied[pp] && corner_valid(cn, ddx, ddy, ddz, W, H, D);
-                                    cw[pp][c] = ok ? corner_weight(cn, ddx, ddy, ddz) : 0.f;
-                                    coff[pp][c] = ok ? (uint32_t)((((cn.z0 + ddz) * H + (cn.y0 + ddy)) * W + (cn.x0 + ddx)) * C) : 0u;
+                                    cw[pp][c] = __shfl_sync(0xffffffffu, w_own, c, 8);
+                                    coff[pp][c] = __shfl_sync(0xffffffffu, o_own, c, 8);
                                 }
                             }
                         }
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
             // copy this row's entry of the producer-owned list, then release the message
             float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
             int smp = -1;
-            if (row < nrows) { gm = lst[off + row]; smp = __float_as_int(gm.w); }
+            if (row < nrows) { gm = lst[off + row]; smp = __float_as_int(gm.w) & 0xFFFF; }
             tc::mbar_arrive(&bars[BAR_MSG_FREE]);
             ++msg;
             if (flags & 4) break;
