@@ -158,11 +158,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
             // ---- classify (one sample per thread, MAXS / 512 passes) + order-preserving compaction of the occupied ones
             int total = 0;
             for (int pass = 0; pass < MAXS / PROD_THREADS; ++pass) {
-                const int j = pass * PROD_THREADS + pt;          // sample of the block
-                const int ry = j / S, s = j % S;
+                // SAMPLE-major enumeration: consecutive list entries are the same depth sample of neighbouring rays, which
+                // cross the same cells at every level, so a tile's rows share most of their corner lines in L1
+                const int j = pass * PROD_THREADS + pt;
+                const int ry = j % P.rays_per_group, s = j / P.rays_per_group;
                 bool occ = false;
                 float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ry < bc.nr) {
+                if (ry < bc.nr && s < S) {
                     const size_t ri = (size_t)bc.b * P.n_rays + bc.r0 + ry;
                     const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
                     const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
@@ -189,7 +191,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                         }
                     }
                     occ = inside && (lm != 0u || !can_skip);
-                    gm.w = __int_as_float(j | (int)(lm << 16));
+                    gm.w = __int_as_float((ry * S + s) | (int)(lm << 16));   // block sample id (ray-major, as rawb / zb) | level bits
                 }
                 const uint32_t bal = __ballot_sync(0xffffffffu, occ);
                 if (lane == 0) wcnt[pw] = __popc(bal);
