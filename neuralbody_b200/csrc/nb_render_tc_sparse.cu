@@ -228,13 +228,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 bool occupied[PTS_PER_GROUP];
                 const VT* vol = nullptr;
                 int cur_lvl = -1;
+                const uint32_t seg_base = tc::smem_u32(smem + OFF_SEG);
+                const uint32_t so0 = (uint32_t)((((t >> 1) * 16 + (grp >> 3)) * 128) + (grp & 7) * 16 + (t & 1) * 8);
                 for (int seg = 0; seg < NUM_SEGS; ++seg) {
                     const uint32_t gseg = it * NUM_SEGS + seg;
                     const uint32_t buf = gseg % NUM_SEG_BUFS;
                     tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1);
                     tr.ev(10 + seg);
-                    unsigned char* hi_plane = smem + OFF_SEG + buf * SEG_BYTES;
-                    unsigned char* lo_plane = hi_plane + SEG_CHUNKS * CHUNK_BYTES;
+                    // this thread's (row, channel quad) slot of the hi plane; the lo plane follows SEG_CHUNKS chunks later
+                    const uint32_t dst = seg_base + buf * SEG_BYTES + so0;
                     const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
                     for (int uu = 0; uu < nunits; ++uu) {
                         const int unit = 2 * seg + uu;
@@ -257,35 +259,37 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                                 const bool ok = occupied[pp] && corner_valid(cn, ddx, ddy, ddz, W, H, D);
                                 const float w_own = ok ? __fmul_rn(__fmul_rn(ddx ? cn.wx[1] : cn.wx[0], ddy ? cn.wy[1] : cn.wy[0]),
                                                                    ddz ? cn.wz[1] : cn.wz[0]) : 0.f;
-                                const uint32_t o_own = ok ? (uint32_t)((((cn.z0 + ddz) * H + (cn.y0 + ddy)) * W + (cn.x0 + ddx)) * C) : 0u;
+                                // byte offset of the corner vector inside this frame's level; corners that do not contribute
+                                // (out of range, zero weight, unoccupied cell) point at voxel 0 and are never accumulated
+                                const uint32_t o_own = ok ? (uint32_t)((((cn.z0 + ddz) * H + (cn.y0 + ddy)) * W + (cn.x0 + ddx)) * C) * (uint32_t)sizeof(VT) : 0u;
 #pragma unroll
                                 for (int c = 0; c < 8; ++c) {
                                     cw[pp][c] = __shfl_sync(0xffffffffu, w_own, c, 8);
-                                    coff[pp][c] = __shfl_sync(0xffffffffu, o_own, c, 8);
+                                    coff[pp][c] = __shfl_sync(0xffffffffu, o_own, c, 8) + (uint32_t)(4 * t * sizeof(VT));
                                 }
                             }
                         }
 #pragma unroll
                         for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
-                            const int p = grp + 64 * pp;
                             float a[4] = {0.f, 0.f, 0.f, 0.f};
                             if (occupied[pp]) {
+                                const unsigned char* ub = reinterpret_cast<const unsigned char*>(vol + c0);   // warp-uniform
                                 typename Quad<VT>::raw v[8];
 #pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    v[c] = (cw[pp][c] != 0.f) ? Quad<VT>::load(vol + coff[pp][c] + c0 + 4 * t) : Quad<VT>::zero();
+                                for (int c = 0; c < 8; ++c) v[c] = Quad<VT>::load_bytes(ub + coff[pp][c]);
 #pragma unroll
-                                for (int c = 0; c < 8; ++c) Quad<VT>::fma(a, v[c], cw[pp][c]);
+                                for (int c = 0; c < 8; ++c)
+                                    if (cw[pp][c] != 0.f) Quad<VT>::fma(a, v[c], cw[pp][c]);
                             }
                             uint2 hi;
                             hi.x = tc::cvt_f16x2(a[0], a[1]); hi.y = tc::cvt_f16x2(a[2], a[3]);
-                            const int so = ((uu * 4 + (t >> 1)) * 16 + (p >> 3)) * 128 + (p & 7) * 16 + (t & 1) * 8;
-                            *reinterpret_cast<uint2*>(hi_plane + so) = hi;
+                            const uint32_t so = dst + (uint32_t)(uu * 4 * 16 * 128 + pp * 8 * 128);   // K-major core-matrix layout
+                            tcr::sts_v2(so, hi);
                             if (NP == 3) {
                                 uint2 lo;
                                 lo.x = tc::cvt_f16x2(f16lo_of(a[0], hi.x, 0), f16lo_of(a[1], hi.x, 1));
                                 lo.y = tc::cvt_f16x2(f16lo_of(a[2], hi.y, 0), f16lo_of(a[3], hi.y, 1));
-                                *reinterpret_cast<uint2*>(lo_plane + so) = lo;
+                                tcr::sts_v2(so + SEG_CHUNKS * CHUNK_BYTES, lo);
                             }
                         }
                     }

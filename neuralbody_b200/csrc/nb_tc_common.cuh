@@ -14,6 +14,9 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ float f16lo_of(float x, uint32_t hi_pair, int which) {
     // x - float(hi) for one element of a packed fp16 pair
     const __half2 h = *reinterpret_cast<const __half2*>(&hi_pair);
@@ -41,6 +44,7 @@ template <> struct Quad<float> {
     using raw = uint4;
     static __device__ __forceinline__ raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
     static __device__ __forceinline__ raw load(const float* p) { return ldg_nc_v4(p); }
+    static __device__ __forceinline__ raw load_bytes(const unsigned char* p) { return ldg_nc_v4(p); }
     static __device__ __forceinline__ void fma(float (&a)[4], const raw& v, float w) {
         a[0] = fmaf(__uint_as_float(v.x), w, a[0]); a[1] = fmaf(__uint_as_float(v.y), w, a[1]);
         a[2] = fmaf(__uint_as_float(v.z), w, a[2]); a[3] = fmaf(__uint_as_float(v.w), w, a[3]);
@@ -54,6 +58,7 @@ template <> struct Quad<__half> {
         asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
         return r;
     }
+    static __device__ __forceinline__ raw load_bytes(const unsigned char* p) { return load(reinterpret_cast<const __half*>(p)); }
     static __device__ __forceinline__ void fma(float (&a)[4], const raw& v, float w) {
         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
         const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
