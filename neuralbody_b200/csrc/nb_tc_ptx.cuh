@@ -28,7 +28,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
+#ifdef NB_NO_WAIT_HINT
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+#else
+        // suspend-time hint: the waiting warp stays parked in hardware until the phase flips (or ~1 ms passes) instead of
+        // re-issuing the probe every few cycles and competing with the producer warps for issue slots
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+#endif
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
