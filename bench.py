@@ -181,6 +181,7 @@ def run_product(args, rank, world, local_rank):
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.raw_noise_std = S, 0.0, False, 0
     cfg.render_precision, cfg.render_volume_dtype, cfg.chunk = precision, "auto", 0
     cfg.render_skip_empty = not args.dense
+    cfg.render_compact_frame = not args.fused
     cfg.render_return_weights = False     # `weights` (B,n,S) is unused downstream; rgb/depth/acc/disp are written
     cfg.num_train_frame = int(scene["weights"]["latent.weight"].shape[0])
     net = make_network(cfg)
@@ -188,7 +189,7 @@ def run_product(args, rank, world, local_rank):
     net = net.to(dev).eval()
     net.set_feature_volume([v.to(dev) for v in scene["volumes"]])
     ren = make_renderer(cfg, net)
-    ren.stats = torch.zeros(2, dtype=torch.int64, device=dev)   # tiles executed / occupied samples (sparse kernel)
+    ren.stats = torch.zeros(4, dtype=torch.int64, device=dev)   # tiles executed / occupied samples / decoder ns / decoder launches
 
     keys = ("coord", "out_sh", "bounds", "R", "Th", "latent_index", "ray_o", "ray_d", "near", "far")
     host = {k: scene[k].pin_memory() for k in keys}
@@ -279,11 +280,19 @@ def run_product(args, rank, world, local_rank):
     # dominant kernel = the fused render kernel; its launch duration = device step time / launches per step
     # (at N=1 the step IS n_views launches of it and nothing else)
     kernel_ms = total_ms / max(1, launches) if world == 1 else None
+    kernel_ms_source = "CUDA events around the step / launches per step (the step is that one kernel)"
+    kernel_launches = launches
     samples_per_launch = n_local * S
     skipping = precision != "fp32" and not args.dense
-    if skipping and launches:
+    if skipping and stats[3] > 0:
+        # frame-compacting pipeline: 3 launches per view (classify, decoder, composite).  The decoder kernel is the dominant
+        # one; it times itself on the device (%globaltimer: first CTA start -> last CTA end, accumulated in stats[2])
+        kernel_launches = stats[3]
+        kernel_ms = stats[2] * 1e-6 / stats[3]
+        kernel_ms_source = "%globaltimer, first CTA start to last CTA end of render_tc_list_kernel, mean over the timed launches"
+    if skipping and kernel_launches:
         # only EXECUTED work is credited: 128-row tiles the kernel actually ran (padding rows included), per launch
-        samples_per_launch = stats[0] * 128 / launches
+        samples_per_launch = stats[0] * 128 / kernel_launches
     if kernel_ms:
         tflops_exec = samples_per_launch * FLOP_PER_SAMPLE_FOLDED / (kernel_ms * 1e-3) / 1e12
         tflops_written = samples_per_launch * FLOP_PER_SAMPLE_AS_WRITTEN / (kernel_ms * 1e-3) / 1e12
@@ -307,12 +316,14 @@ def run_product(args, rank, world, local_rank):
         "tensor_issued_frac_of_sustained": (tflops_exec * FLOP_PER_SAMPLE_ISSUED[precision] / FLOP_PER_SAMPLE_FOLDED)
                                            / peaks["tf_sustained"],
         "achieved_if_counted_as_written": tflops_written,
-        "kernel": "render_tc_kernel<%d>" % (3 if precision == "tc_fp16x3" else 1) if precision != "fp32"
+        "kernel": ("%s<%d>" % ("render_tc_list_kernel" if stats[3] > 0 else "render_tc_sparse_kernel" if skipping else "render_tc_kernel",
+                               3 if precision == "tc_fp16x3" else 1)) if precision != "fp32"
                   else "render_f32_kernel (fp32 FFMA pipe, no tensor cores)",
-        "kernel_ms": kernel_ms,
+        "kernel_ms": kernel_ms, "kernel_ms_source": kernel_ms_source,
+        "kernel_share_of_step": (kernel_ms * kernel_launches / total_ms) if kernel_ms else None,
         "samples_evaluated_per_launch": samples_per_launch, "samples_total_per_launch": n_local * S,
         "empty_sample_skipping": ("exact (sigma_empty < 0): %.1f%% of the samples occupied" % (
-            100.0 * stats[1] / max(1, launches * n_local * S))) if skipping else "off (dense evaluation)",
+            100.0 * stats[1] / max(1, kernel_launches * n_local * S))) if skipping else "off (dense evaluation)",
         "hbm_compulsory_gbs": (n_local * 56 / (kernel_ms * 1e-3) / 1e9) if kernel_ms else None,
     }
 
@@ -352,7 +363,7 @@ def run_product(args, rank, world, local_rank):
         "frames_per_s_512x512": value / (H * W),
         "config": {"workload": "synth-313 512x512 all-hit view x %d per step, 64 samples/ray, eval, perturb=0 "
                                "(BASELINE configs[1])" % n_views,
-                   "precision": precision, "skip_empty": (precision != "fp32" and not args.dense), "rays_per_step": rays_per_step, "samples_per_ray": S,
+                   "precision": precision, "skip_empty": (precision != "fp32" and not args.dense), "pipeline": ("fused single kernel" if (args.fused or args.dense or precision == "fp32") else "classify -> decoder over the frame's compact sample list -> composite (3 launches per view)"), "rays_per_step": rays_per_step, "samples_per_ray": S,
                    "parallelism": "ray-sharded x%d (interleaved 256-ray chunks), one all-gather per view" % world if world > 1 else "single GPU",
                    "l2": "256 MiB written between timed steps (untimed) to flush the 126 MB L2",
                    "volume": "fp16 channels-last 69 MB, packed once (cached across views of the frame)"
@@ -378,6 +389,8 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=4096, help="rays per step of the CPU arm / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense", action="store_true", help="disable the exact empty-sample skipping of the tensor-core kernels")
+    ap.add_argument("--fused", action="store_true", help="single fused kernel (compaction per 1024-sample block) instead of the "
+                                                         "frame-compacting classify/decoder/composite pipeline")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(1, args.warmup)
 

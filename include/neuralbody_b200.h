@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NB_ABI_VERSION 1
+#define NB_ABI_VERSION 2
 
 #define NB_OK               0
 #define NB_ERR_BAD_ARG     (-1)
@@ -133,14 +133,27 @@ typedef struct nb_render_args {
     int   mask_nv, mask_H, mask_W;
     int   skip_empty;      /* tensor-core precisions: 1 = exact empty-sample skipping (samples whose trilinear cells are all
                               unoccupied have weight exactly 0 when sigma(empty) < 0; their MLP evaluation is skipped) */
-    unsigned long long* stats; /* device u64[2] or NULL: [0] += 128-sample tiles executed, [1] += occupied samples */
+    unsigned long long* stats; /* device u64[4] or NULL: [0] += 128-sample tiles executed, [1] += occupied samples,
+                                  [2] += ns spent in the decoder kernel (%globaltimer, first CTA start to last CTA end) and
+                                  [3] += decoder launches -- [2], [3] only with a workspace */
     float* save;           /* device (B,n,S,1312) activation record for nb_render_bwd, or NULL (NB_PRECISION_FP32 only);
                               size from nb_render_save_bytes() */
     unsigned long long* trace; /* device, 4 x 4096 u64, or NULL: per-role (code<<48 | SM clock) timeline of CTA 0
                                   (tensor-core kernel only; diagnostics, see tools/trace_timeline.py) */
+    void*  workspace;      /* device scratch of nb_render_fwd_workspace_bytes() bytes, or NULL.  With it (tensor-core precisions,
+                              skip_empty or mask views) the occupied samples of a whole frame are compacted into one list and
+                              the decoder runs over full 128-sample tiles: 3 launches per frame (classify, decoder, composite)
+                              instead of the single fused kernel, same results bit for bit */
+    size_t workspace_bytes;
+    int    trace_fused;    /* diagnostics: 1 = keep the single fused kernel even when a workspace is given */
 } nb_render_args;
 
 int nb_render_fwd(const nb_render_args* args, void* stream);
+
+/* Scratch bytes nb_render_fwd wants in nb_render_args.workspace for (batch, n_rays, n_samples): a 32-byte control block per
+ * frame + one frame's sample list + one frame's raw records (16 B per sample each).  The buffer may be reused by
+ * later calls on the same stream. */
+size_t nb_render_fwd_workspace_bytes(int batch, int n_rays, int n_samples);
 
 /* f-3: density on arbitrary world points.  Replaces Network.calculate_density (lib/networks/latent_xyzc.py:74-89), the
  * alpha decoder of the mesh renderer (lib/networks/renderer/if_mesh_renderer.py:36-41).  Only the frame fields of `frame`

@@ -13,7 +13,7 @@ NB_NUM_LEVELS = 4
 
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
-           "nb_render_fwd_launches", "nb_debug_tc_probe", "nb_render_bwd", "nb_render_save_bytes",
+           "nb_render_fwd_launches", "nb_render_fwd_workspace_bytes", "nb_debug_tc_probe", "nb_render_bwd", "nb_render_save_bytes",
            "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays"]
 
 
@@ -50,7 +50,7 @@ class nb_render_args(C.Structure):
         ("depth_map", C.c_void_p), ("raw", C.c_void_p),
         ("mask_msks", C.c_void_p), ("mask_RT", C.c_void_p), ("mask_Ks", C.c_void_p),
         ("mask_nv", C.c_int), ("mask_H", C.c_int), ("mask_W", C.c_int), ("skip_empty", C.c_int), ("stats", C.c_void_p), ("save", C.c_void_p),
-        ("trace", C.c_void_p),
+        ("trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("trace_fused", C.c_int),
     ]
 
 
@@ -95,6 +95,8 @@ def load(path=None):
     lib.nb_render_fwd.argtypes = [C.POINTER(nb_render_args), C.c_void_p]
     lib.nb_render_fwd_launches.restype = C.c_int
     lib.nb_render_fwd_launches.argtypes = [C.c_int]
+    lib.nb_render_fwd_workspace_bytes.restype = C.c_size_t
+    lib.nb_render_fwd_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.nb_render_bwd.restype = C.c_int
     lib.nb_render_bwd.argtypes = [C.POINTER(nb_render_bwd_args), C.c_void_p]
     lib.nb_render_save_bytes.restype = C.c_size_t
@@ -107,7 +109,7 @@ def load(path=None):
     lib.nb_gen_rays.argtypes = [C.POINTER(nb_camera)] + [C.c_void_p] * 6
     lib.nb_debug_tc_probe.restype = C.c_int
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
-    if lib.nb_abi_version() != 1:
+    if lib.nb_abi_version() != 2:
         raise RuntimeError("libneuralbody_b200.so ABI version mismatch")
     if path in (_build.LIB_PATH, os.environ.get("NB_LIB_PATH")):
         _lib = lib

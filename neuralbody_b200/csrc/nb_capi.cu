@@ -412,6 +412,11 @@ int nb_pack_weights(const nb_decoder_weights* w, void* out_blob, size_t out_byte
 
 int nb_render_fwd_launches(int precision) { (void)precision; return 1; }
 
+size_t nb_render_fwd_workspace_bytes(int batch, int n_rays, int n_samples) {
+    if (batch <= 0 || n_rays <= 0 || n_samples <= 0) return 0;
+    return render_tc_list_workspace_bytes(batch, n_rays, n_samples);
+}
+
 // validate a forward call's arguments and translate them into the kernels' parameter block (shared with nb_render_bwd)
 int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
     if (!a) { set_error("nb_render_fwd: null args"); return NB_ERR_BAD_ARG; }
@@ -460,6 +465,7 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
         return NB_ERR_BAD_ARG;
     }
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
+    p.frame = 0; p.list = nullptr; p.list_count = nullptr; p.frame_clock = nullptr; p.raw_ws = nullptr;
 
     return NB_OK;
 }
@@ -507,8 +513,12 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     if (a->precision == NB_PRECISION_TC_FP16 || a->precision == NB_PRECISION_TC_FP16X3) {
         const int passes = a->precision == NB_PRECISION_TC_FP16X3 ? 3 : 1;
         // mask views are a per-sample predicate: they live in the sample classifier of the sparse kernel
-        return (a->skip_empty || a->mask_msks) ? launch_render_tc_sparse(p, a->volume_dtype, passes, st)
-                                               : launch_render_tc(p, a->volume_dtype, passes, st);
+        if (!(a->skip_empty || a->mask_msks)) return launch_render_tc(p, a->volume_dtype, passes, st);
+        // with a workspace the samples are compacted across the whole frame (classify -> decoder over full tiles -> composite);
+        // without one the single fused kernel compacts inside each 1024-sample block
+        if (a->workspace && !a->trace_fused && render_tc_list_supported(p))
+            return launch_render_tc_list(p, a->volume_dtype, passes, a->workspace, a->workspace_bytes, st);
+        return launch_render_tc_sparse(p, a->volume_dtype, passes, st);
     }
     set_error("nb_render_fwd: unknown precision %d", a->precision);
     return NB_ERR_BAD_ARG;

@@ -33,17 +33,27 @@ struct RenderParams {
     unsigned long long* trace;
     const unsigned char* mask_msks; const float* mask_RT; const float* mask_Ks;   // f-1 mask views (null = none)
     int mask_nv, mask_H, mask_W;
-    unsigned long long* stats; // [0] += tiles executed, [1] += occupied samples (sparse kernel) or null
+    unsigned long long* stats; // u64[4] or null: [0] += tiles executed, [1] += occupied samples (sparse / list kernels),
+                               // [2] += decoder-kernel ns, [3] += decoder launches (list pipeline)
     float* save;               // (B,n,S,kSaveDim) activation record for nb_render_bwd (exact kernel only) or null
     int rays_per_group;        // rays handled together by one CTA work item
     int tiles_per_group;       // point tiles per group
     int n_groups;              // total work items = batch * ceil(n_rays / rays_per_group)
     int groups_per_frame;
+    // list pipeline (nb_render_tc_list.cu): one frame per launch
+    int frame;                 // frame of this launch
+    float4* list;              // compact sample list: (world xyz, frame sample id | level bits << 28)
+    unsigned int* list_count;  // entries appended by classify_compact_kernel
+    unsigned long long* frame_clock;   // [0] max(~start), [1] max(end) of the decoder launch (%globaltimer ns)
+    float4* raw_ws;            // (n, S) raw records of this frame: (rgb logits, sigma)
 };
 
 int launch_render_f32(const RenderParams& p, int volume_dtype, cudaStream_t stream);
 int launch_render_tc(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
 int launch_render_tc_sparse(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
+int launch_render_tc_list(const RenderParams& p, int volume_dtype, int passes, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+size_t render_tc_list_workspace_bytes(int batch, int n_rays, int n_samples);
+bool render_tc_list_supported(const RenderParams& p);
 int launch_density_f32(const RenderParams& p, int volume_dtype, const float* pts, int n_points, float* sigma, cudaStream_t stream);
 bool tc_available();
 

@@ -1,0 +1,662 @@
+// Tensor-core render as a three-launch pipeline over a COMPACT SAMPLE LIST (needs nb_render_args.workspace):
+//
+//   1. classify_compact_kernel   every sample of the frame is classified with the cell-occupancy bitmaps (exactly as the
+//                                fused sparse kernel does, nb_render_tc_sparse.cu); occupied samples are appended to a
+//                                global list (one atomicAdd per 1024-sample block), the others get their constant
+//                                raw = (0, 0, 0, min(sigma_empty, 0)) straight away.
+//   2. render_tc_list_kernel     the decoder MLP over the list, 128 list entries per tile: every tile except the last
+//                                one is FULL, where the fused kernel pads the last tile of each 1024-sample block
+//                                (75 % fill on the 512x512 benchmark view).  Same warp-specialised tcgen05 pipeline;
+//                                the smem that held the per-block lists buys a third layer-0 operand segment.
+//   3. composite_kernel          raw2outputs (nerf_net_utils.py:6-51), one warp per ray.
+//
+// Results are bit-identical to the fused kernels: a tile row is evaluated independently of its neighbours, so the
+// (non-deterministic) order of the blocks in the list does not reach any output.
+// The raw (rgb logits, sigma) records cross HBM once each way: 32 B per sample, ~0.5 GB per 512x512x64 frame.
+#include "nb_tc_common.cuh"
+
+namespace nb {
+namespace tcl {
+
+using tcr::Quad;
+using tcr::Tracer;
+using tcr::named_bar_sync;
+using tcr::f16lo_of;
+
+constexpr int TP = 128;
+constexpr int NUM_SLOTS = 3;
+constexpr int STEP_BYTES = 8192;
+constexpr int SLOT_BYTES = 4 * STEP_BYTES;
+constexpr int CHUNK_BYTES = 2048;
+constexpr int SEG_CHUNKS = 8;
+constexpr int NUM_SEGS = 6;
+constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * CHUNK_BYTES;      // 96 KB: 3 x (hi+lo) or 6 x hi
+constexpr int MAX_SEG_BUFS = 6;
+constexpr int PE_CHUNKS = 12;
+constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
+constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;               // 704
+constexpr int PROD_THREADS = PROD_WARPS * 32;                     // 512
+constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);
+constexpr int MAXS = 1024;                                         // samples per classification block
+constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry .w = frame sample id | level bits << 28
+
+// shared-memory map (bytes)
+constexpr int OFF_SEG = 0;
+constexpr int OFF_ONES = OFF_SEG + SEG_RING_BYTES;
+constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;
+constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;
+constexpr int OFF_XF = OFF_RING + NUM_SLOTS * SLOT_BYTES;          // FrameXf
+constexpr int OFF_INFO = OFF_XF + 128;                             // TileInfo[2]
+constexpr int OFF_BAR = OFF_INFO + 64;
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + MAX_SEG_BUFS,
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_H_READY, BAR_MSG_FULL, BAR_MSG_FREE, NUM_BARS };
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+
+constexpr uint32_t TM_ACC = 0, TM_HI = 256, TM_LO = 384;
+
+struct TileInfo {
+    int nrows;       // list entries in this tile
+    int tile;        // tile index: rows [tile * 128, tile * 128 + nrows) of the list
+    int flags;       // bit2 done (no more work)
+    int pad;
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void load_frame_xf(const RenderParams& P, FrameXf* xf, int i) {
+    const int b = P.frame;
+    if (i < 9) xf->R[i] = __ldg(P.R + b * 9 + i);
+    if (i < 3) {
+        xf->Th[i] = __ldg(P.Th + b * 3 + i);
+        xf->min_dhw[i] = __ldg(P.bounds + b * 6 + (2 - i));
+        xf->voxel[i] = P.voxel_size[i];
+        xf->out_sh[i] = P.out_sh[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 1. classify + compact
+// One CTA per block of rays_per_group rays (<= 1024 samples), one sample per thread, SAMPLE-major inside the block so that
+// consecutive list entries are the same depth sample of neighbouring rays (they share their corner lines).
+__global__ void __launch_bounds__(MAXS) classify_compact_kernel(const __grid_constant__ RenderParams P) {
+    __shared__ FrameXf xf;
+    __shared__ int wcnt[MAXS / 32];
+    __shared__ unsigned int sbase;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = P.n_samples, b = P.frame;
+    const int r0 = blockIdx.x * P.rays_per_group;
+    const int nr = min(P.rays_per_group, P.n_rays - r0);
+    load_frame_xf(P, &xf, tid);
+    __syncthreads();
+    const float sigma_empty = __ldg(P.wf32 + oSigmaEmpty);
+    const bool can_skip = sigma_empty < -1e-3f;      // robustly negative => empty samples have weight exactly 0
+    const uint32_t* occ_base = reinterpret_cast<const uint32_t*>(P.volume);
+
+    const int ry = tid % P.rays_per_group, s = tid / P.rays_per_group;
+    const bool live = ry < nr && s < S;
+    bool occ = false;
+    float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t id = 0;
+    if (live) {
+        const size_t ri = (size_t)b * P.n_rays + r0 + ry;
+        const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
+        const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
+        const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+        gm.x = __fadd_rn(ox, __fmul_rn(dx, z));
+        gm.y = __fadd_rn(oy, __fmul_rn(dy, z));
+        gm.z = __fadd_rn(oz, __fmul_rn(dz, z));
+        float gx, gy, gz;
+        world_to_grid(xf, gm.x, gm.y, gm.z, gx, gy, gz);
+        uint32_t lm = 0;                               // bit l = the sample's level-l cell holds a non-zero voxel
+        const bool inside = P.mask_nv == 0 || inside_masks(P, gm.x, gm.y, gm.z);   // f-1 mask views
+        if (inside) {
+#pragma unroll
+            for (int lvl = 0; lvl < 4; ++lvl) {
+                const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+                Corners cn;
+                corner_setup(unnormalize(gx, W), unnormalize(gy, H), unnormalize(gz, D), W, H, D, cn);
+                if (cn.x0 != -2) {
+                    const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)b * P.occ_bstride[lvl];
+                    const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
+                    lm |= ((__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u) << lvl;
+                }
+            }
+        }
+        occ = inside && (lm != 0u || !can_skip);
+        id = (uint32_t)((r0 + ry) * S + s);
+        gm.w = __uint_as_float(id | (lm << 28));
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, occ);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < MAXS / 32; ++w) { const int c = wcnt[w]; base += (w < warp) ? c : 0; total += c; }
+    if (tid == 0) sbase = total ? atomicAdd(P.list_count, (unsigned int)total) : 0u;
+    __syncthreads();
+    if (occ) P.list[(size_t)sbase + base + __popc(bal & ((1u << lane) - 1))] = gm;
+    else if (live) P.raw_ws[id] = make_float4(0.f, 0.f, 0.f, fminf(sigma_empty, 0.f));   // skipped sample: weight exactly 0
+}
+
+// ------------------------------------------------------------------------------------------------ 2. decoder over the list
+template <int NP, typename VT>
+__global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+    volatile TileInfo* info = reinterpret_cast<volatile TileInfo*>(smem + OFF_INFO);
+    FrameXf* xf = reinterpret_cast<FrameXf*>(smem + OFF_XF);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = P.n_samples;
+    constexpr int NUM_SEG_BUFS = (NP == 3) ? 3 : 6;
+    constexpr int SEG_BYTES = SEG_RING_BYTES / NUM_SEG_BUFS;
+
+    if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
+    if (tid == LOAD_WARP * 32) {
+        for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], 1); }
+        for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
+        tc::mbar_init(&bars[BAR_ACC_FULL], 1);
+        tc::mbar_init(&bars[BAR_H_READY], EPI_WARPS * 32);
+        tc::mbar_init(&bars[BAR_MSG_FULL], PROD_WARPS);
+        tc::mbar_init(&bars[BAR_MSG_FREE], EPI_WARPS * 32 + 2);       // epilogue threads + MMA thread + loader thread
+        tc::fence_mbar_init();
+    }
+    if (warp >= PROD_WARP0) {
+        const int pt = tid - PROD_WARP0 * 32;
+        if (pt < TP) {
+            unsigned char* o = smem + OFF_ONES;
+            *reinterpret_cast<uint4*>(o + (pt >> 3) * 128 + (pt & 7) * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(o + CHUNK_BYTES + (pt >> 3) * 128 + (pt & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        load_frame_xf(P, xf, pt);
+        tc::fence_proxy_async();
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0 && P.stats) atomicMax(P.frame_clock + 0, ~global_ns());     // min(start) over the CTAs, as max(~start)
+    const unsigned int n_rows_total = *P.list_count;                  // written by classify_compact_kernel (previous launch)
+    const int n_tiles = (int)((n_rows_total + TP - 1) / TP);
+
+    // ================================================================== PRODUCERS
+    if (warp >= PROD_WARP0) {
+        const int pt = tid - PROD_WARP0 * 32;
+        const int pw = warp - PROD_WARP0;
+        const unsigned char* volbase = reinterpret_cast<const unsigned char*>(P.volume);
+        const int grp = pw * 4 + (lane >> 3);
+        const int t = lane & 7;
+        uint32_t msg = 0, it = 0;                      // messages sent, tiles sent
+        Tracer tr;
+        tr.init((pw == 0 && lane == 0) ? P.trace : nullptr, 0);
+        auto publish = [&](int nrows, int tile, int flags) {
+            tc::mbar_wait(&bars[BAR_MSG_FREE], (msg & 1) ^ 1);        // everybody has read the previous message
+            if (pt == 0) {
+                volatile TileInfo* ti = &info[msg & 1];
+                ti->nrows = nrows; ti->tile = tile; ti->flags = flags;
+            }
+            named_bar_sync(1, PROD_THREADS);
+            if (lane == 0) tc::mbar_arrive(&bars[BAR_MSG_FULL]);
+            ++msg;
+        };
+        const uint32_t seg_base = tc::smem_u32(smem + OFF_SEG);
+        const uint32_t so0 = (uint32_t)((((t >> 1) * 16 + (grp >> 3)) * 128) + (grp & 7) * 16 + (t & 1) * 8);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int nrows = min(TP, (int)(n_rows_total - (unsigned int)tile * TP));
+            // the list entries of this thread's rows: grid coordinates + per-level occupancy bits
+            float4 g[PTS_PER_GROUP];
+#pragma unroll
+            for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
+                const int row = grp + 64 * pp;
+                g[pp] = make_float4(-4.f, -4.f, -4.f, 0.f);
+                if (row < nrows) {
+                    const float4 e = __ldg(P.list + (size_t)tile * TP + row);
+                    world_to_grid(*xf, e.x, e.y, e.z, g[pp].x, g[pp].y, g[pp].z);
+                    g[pp].w = __int_as_float((int)(__float_as_uint(e.w) >> 28));
+                }
+            }
+            publish(nrows, tile, 0);
+            tr.ev(1);                                   // tile published
+            uint32_t coff[PTS_PER_GROUP][8];
+            float cw[PTS_PER_GROUP][8];
+            bool occupied[PTS_PER_GROUP];
+            const VT* vol = nullptr;
+            int cur_lvl = -1;
+            for (int seg = 0; seg < NUM_SEGS; ++seg) {
+                const uint32_t gseg = it * NUM_SEGS + seg;
+                const uint32_t buf = gseg % NUM_SEG_BUFS;
+                tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1);
+                tr.ev(10 + seg);
+                // this thread's (row, channel quad) slot of the hi plane; the lo plane follows SEG_CHUNKS chunks later
+                const uint32_t dst = seg_base + buf * SEG_BYTES + so0;
+                const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
+                for (int uu = 0; uu < nunits; ++uu) {
+                    const int unit = 2 * seg + uu;
+                    int lvl, c0;
+                    if (unit < 1) { lvl = 0; c0 = 0; }
+                    else if (unit < 3) { lvl = 1; c0 = (unit - 1) * 32; }
+                    else if (unit < 7) { lvl = 2; c0 = (unit - 3) * 32; }
+                    else { lvl = 3; c0 = (unit - 7) * 32; }
+                    if (lvl != cur_lvl) {
+                        cur_lvl = lvl;
+                        const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+                        vol = reinterpret_cast<const VT*>(volbase + P.lvl_off[lvl]) + (size_t)P.frame * P.lvl_bstride[lvl];
+                        // lane t of the row's 8-lane group sets up corner t; the group exchanges the 8 (weight, offset) pairs
+                        const int ddx = t & 1, ddy = (t >> 1) & 1, ddz = t >> 2;
+#pragma unroll
+                        for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
+                            Corners cn;
+                            corner_setup(unnormalize(g[pp].x, W), unnormalize(g[pp].y, H), unnormalize(g[pp].z, D), W, H, D, cn);
+                            occupied[pp] = (__float_as_int(g[pp].w) >> lvl) & 1;
+                            const bool ok = occupied[pp] && corner_valid(cn, ddx, ddy, ddz, W, H, D);
+                            const float w_own = ok ? __fmul_rn(__fmul_rn(ddx ? cn.wx[1] : cn.wx[0], ddy ? cn.wy[1] : cn.wy[0]),
+                                                               ddz ? cn.wz[1] : cn.wz[0]) : 0.f;
+                            // byte offset of the corner vector inside this frame's level; corners that do not contribute
+                            // (out of range, unoccupied cell) point at voxel 0 and are never accumulated
+                            const uint32_t o_own = ok ? (uint32_t)((((cn.z0 + ddz) * H + (cn.y0 + ddy)) * W + (cn.x0 + ddx)) * C) * (uint32_t)sizeof(VT) : 0u;
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                cw[pp][c] = __shfl_sync(0xffffffffu, w_own, c, 8);
+                                coff[pp][c] = __shfl_sync(0xffffffffu, o_own, c, 8) + (uint32_t)(4 * t * sizeof(VT));
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
+                        float a[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (occupied[pp]) {
+                            const unsigned char* ub = reinterpret_cast<const unsigned char*>(vol + c0);   // warp-uniform
+                            typename Quad<VT>::raw v[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) v[c] = Quad<VT>::load_bytes(ub + coff[pp][c]);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c)
+                                if (cw[pp][c] != 0.f) Quad<VT>::fma(a, v[c], cw[pp][c]);
+                        }
+                        uint2 hi;
+                        hi.x = tc::cvt_f16x2(a[0], a[1]); hi.y = tc::cvt_f16x2(a[2], a[3]);
+                        const uint32_t so = dst + (uint32_t)(uu * 4 * 16 * 128 + pp * 8 * 128);   // K-major core-matrix layout
+                        tcr::sts_v2(so, hi);
+                        if (NP == 3) {
+                            uint2 lo;
+                            lo.x = tc::cvt_f16x2(f16lo_of(a[0], hi.x, 0), f16lo_of(a[1], hi.x, 1));
+                            lo.y = tc::cvt_f16x2(f16lo_of(a[2], hi.y, 0), f16lo_of(a[3], hi.y, 1));
+                            tcr::sts_v2(so + SEG_CHUNKS * CHUNK_BYTES, lo);
+                        }
+                    }
+                }
+                tc::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bars[BAR_SEG_FULL + buf]);
+                tr.ev(20 + seg);
+            }
+            ++it;
+        }
+        publish(0, 0, 4);                               // done
+        if (pt == 0 && P.stats) {
+            atomicAdd(P.stats + 0, (unsigned long long)it);
+            if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)n_rows_total);
+        }
+    }
+    // ================================================================== LOADER
+    else if (warp == LOAD_WARP) {
+        if (lane == 0) {
+            uint32_t cnt = 0, msg = 0;
+            const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
+            auto push = [&](const unsigned char* src, uint32_t bytes, const unsigned char* src2 = nullptr, uint32_t bytes2 = 0) {
+                const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
+                unsigned char* dst = smem + OFF_RING + slot * SLOT_BYTES;
+                tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);
+                tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes + bytes2);
+                tc::bulk_g2s(dst, src, bytes, &bars[BAR_W_FULL + slot]);
+                if (bytes2) tc::bulk_g2s(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot]);
+                ++cnt;
+            };
+            for (;;) {
+                tc::mbar_wait(&bars[BAR_MSG_FULL], msg & 1);
+                const int flags = info[msg & 1].flags;
+                tc::mbar_arrive(&bars[BAR_MSG_FREE]);
+                ++msg;
+                if (flags & 4) break;
+                for (int layer = 0; layer < 3; ++layer) {
+                    const int nks = layer == 0 ? kKsL0 : kKsL12;
+                    const unsigned char* base = seq + 2 * (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
+                    for (int g0 = 0; g0 < nks; g0 += 4) {
+                        const int gs = (nks - g0) < 4 ? (nks - g0) : 4;
+                        push(base + 2 * step256_offset(g0, 0, nks), gs * STEP_BYTES);
+                        if (NP == 3) push(base + 2 * step256_offset(g0, 1, nks), gs * STEP_BYTES);
+                    }
+                    push(base + 2 * bias256_offset(nks), STEP_BYTES);
+                }
+                {
+                    const uint32_t sb = kStepHalves3 * 2;
+                    const unsigned char* l3 = seq + sL3 * 2;
+                    for (int g0 = 0; g0 < 20; g0 += 4) push(l3 + (size_t)g0 * sb, 4 * sb);
+                    push(l3 + (size_t)20 * sb, sb, reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb, sb);
+                }
+                push(seq + sL4 * 2, kStepsL4 * kStepHalves4 * 2);
+            }
+        }
+    }
+    // ================================================================== MMA ISSUER
+    else if (warp == MMA_WARP) {
+        if (lane == 0) {
+            uint32_t cnt = 0, hcnt = 0, msg = 0, it = 0;
+            const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
+            const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
+            constexpr uint32_t ID256 = tc::make_idesc_f16(128, 256), ID3 = tc::make_idesc_f16(128, kN3),
+                               ID4 = tc::make_idesc_f16(128, kN4);
+            auto wait_slot = [&](uint32_t& slot) {
+                slot = cnt % NUM_SLOTS;
+                tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
+                tc::tc_fence_after();
+            };
+            auto release_slot = [&](uint32_t slot) { tc::mma_commit(&bars[BAR_W_EMPTY + slot]); ++cnt; };
+            auto a_desc = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * CHUNK_BYTES, CHUNK_BYTES, 128); };
+            auto b_desc = [&](uint32_t slot, int i, int N) {
+                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32, N * 16, 128);
+            };
+            auto wait_h = [&]() { tc::mbar_wait(&bars[BAR_H_READY], hcnt & 1); ++hcnt; tc::tc_fence_after(); };
+            Tracer tr;
+            tr.init(P.trace, 1);
+            for (;;) {
+                tc::mbar_wait(&bars[BAR_MSG_FULL], msg & 1);
+                const int flags = info[msg & 1].flags;
+                tc::mbar_arrive(&bars[BAR_MSG_FREE]);
+                ++msg;
+                if (flags & 4) break;
+                uint32_t slot;
+                if (it > 0) wait_h();
+                tr.ev(1);
+                for (int seg = 0; seg < NUM_SEGS; ++seg) {
+                    const uint32_t gseg = it * NUM_SEGS + seg;
+                    const uint32_t buf = gseg % NUM_SEG_BUFS;
+                    tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
+                    tc::tc_fence_after();
+                    tr.ev(10 + seg);
+                    const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * CHUNK_BYTES;
+                    const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
+                    wait_slot(slot);
+                    for (int ks = 0; ks < nks; ++ks) {
+                        tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, ks, 256), ID256, (seg | ks) != 0);
+                        if (NP == 3) tc::mma_ss(tmem + TM_ACC, a_desc(lo_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                    }
+                    release_slot(slot);
+                    if (NP == 3) {
+                        wait_slot(slot);
+                        for (int ks = 0; ks < nks; ++ks)
+                            tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                        release_slot(slot);
+                    }
+                    tc::mma_commit(&bars[BAR_SEG_EMPTY + buf]);
+                }
+                wait_slot(slot);
+                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
+                release_slot(slot);
+                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(20);
+                for (int layer = 1; layer <= 2; ++layer) {
+                    wait_h();
+                    tr.ev(30 + layer);
+                    for (int g0 = 0; g0 < 16; g0 += 4) {
+                        wait_slot(slot);
+                        for (int i = 0; i < 4; ++i) {
+                            tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, 256), ID256, (g0 | i) != 0);
+                            if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + (g0 + i) * 8, b_desc(slot, i, 256), ID256, true);
+                        }
+                        release_slot(slot);
+                        if (NP == 3) {
+                            wait_slot(slot);
+                            for (int i = 0; i < 4; ++i)
+                                tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, 256), ID256, true);
+                            release_slot(slot);
+                        }
+                    }
+                    wait_slot(slot);
+                    tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
+                    release_slot(slot);
+                    tc::mma_commit(&bars[BAR_ACC_FULL]);
+                    tr.ev(20 + layer);
+                }
+                wait_h();
+                tr.ev(33);
+                for (int g0 = 0; g0 < 16; g0 += 4) {
+                    wait_slot(slot);
+                    for (int i = 0; i < 4; ++i) {
+                        tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, (g0 | i) != 0);
+                        if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, true);
+                    }
+                    release_slot(slot);
+                }
+                wait_slot(slot);
+                for (int i = 0; i < 4; ++i) tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, i), b_desc(slot, i, kN3), ID3, true);
+                release_slot(slot);
+                wait_slot(slot);
+                for (int i = 0; i < 2; ++i) tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, 4 + i), b_desc(slot, i, kN3), ID3, true);
+                release_slot(slot);
+                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(23);
+                wait_h();
+                tr.ev(34);
+                wait_slot(slot);
+                for (int ks = 0; ks < 8; ++ks)
+                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, ks, kN4), ID4, ks > 0);
+                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 8, kN4), ID4, true);
+                release_slot(slot);
+                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                ++it;
+            }
+        }
+    }
+    // ================================================================== EPILOGUE (thread = tile row)
+    else {
+        const int row = tid;
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        unsigned char* PE = smem + OFF_PE;
+        uint32_t acnt = 0, msg = 0;
+        auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
+        auto relu_to_h = [&](int ncols, bool with_lo) {
+            const int ng = ncols / 8;
+            uint32_t va[8], vb[8];
+            auto convert_store = [&](const uint32_t (&v)[8], int c) {
+                uint32_t h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                tc::tmem_st4(lane_base + TM_HI + c * 4, h);
+                if (NP == 3 && with_lo) {
+                    uint32_t l[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        l[i] = tc::cvt_f16x2(f16lo_of(fmaxf(__uint_as_float(v[2 * i]), 0.f), h[i], 0),
+                                             f16lo_of(fmaxf(__uint_as_float(v[2 * i + 1]), 0.f), h[i], 1));
+                    tc::tmem_st4(lane_base + TM_LO + c * 4, l);
+                }
+            };
+            tc::tmem_ld8(lane_base + TM_ACC, va);
+            tc::tmem_ld_wait();
+            for (int c = 0; c < ng; c += 2) {
+                tc::tmem_ld8(lane_base + TM_ACC + (c + 1) * 8, vb);
+                convert_store(va, c);
+                tc::tmem_ld_wait();
+                if (c + 2 < ng) tc::tmem_ld8(lane_base + TM_ACC + (c + 2) * 8, va);
+                convert_store(vb, c + 1);
+                tc::tmem_ld_wait();
+            }
+            tc::tmem_st_wait();
+        };
+        auto h_done = [&]() { tc::tc_fence_before(); tc::mbar_arrive(&bars[BAR_H_READY]); };
+
+        for (;;) {
+            tc::mbar_wait(&bars[BAR_MSG_FULL], msg & 1);
+            const int nrows = info[msg & 1].nrows, flags = info[msg & 1].flags, tile = info[msg & 1].tile;
+            tc::mbar_arrive(&bars[BAR_MSG_FREE]);
+            ++msg;
+            if (flags & 4) break;
+            float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
+            int smp = -1;
+            if (row < nrows) {
+                gm = __ldg(P.list + (size_t)tile * TP + row);
+                smp = (int)(__float_as_uint(gm.w) & ID_MASK);
+            }
+            const size_t ri = (size_t)P.frame * P.n_rays + (smp >= 0 ? smp / S : 0);
+            {
+                __half* peh = reinterpret_cast<__half*>(PE);
+                auto put = [&](int k, float v) {
+                    peh[((k >> 3) * 16 + (row >> 3)) * 64 + (row & 7) * 8 + (k & 7)] = __float2half_rn(v);
+                };
+                positional_embed_anchored<10, 5>(gm.x, gm.y, gm.z, [&](int j, float v) { put(j, v); });
+                put(63, 0.f);
+                const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
+                const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+                positional_embed_anchored<4, 4>(__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm), [&](int j, float v) { put(64 + j, v); });
+                put(91, 0.f); put(92, 1.f); put(93, 1.f); put(94, 0.f); put(95, 0.f);
+                tc::fence_proxy_async();
+            }
+            for (int layer = 0; layer < 3; ++layer) {
+                wait_acc();
+                relu_to_h(256, true);
+                h_done();
+            }
+            wait_acc();
+            float sigma;
+            {
+                uint32_t v[16];
+                tc::tmem_ld16(lane_base + TM_ACC + 128, v);
+                tc::tmem_ld_wait();
+                sigma = __uint_as_float(v[0]) + __uint_as_float(v[1]);
+            }
+            relu_to_h(128, false);
+            h_done();
+            wait_acc();
+            {
+                uint32_t v[16];
+                tc::tmem_ld16(lane_base + TM_ACC, v);
+                tc::tmem_ld_wait();
+                if (smp >= 0)
+                    P.raw_ws[smp] = make_float4(__uint_as_float(v[0]) + __uint_as_float(v[3]), __uint_as_float(v[1]) + __uint_as_float(v[4]),
+                                                __uint_as_float(v[2]) + __uint_as_float(v[5]), sigma);
+            }
+            h_done();
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0 && P.stats) atomicMax(P.frame_clock + 1, global_ns());
+    if (warp == MMA_WARP) {
+        __syncwarp();
+        tc::tmem_dealloc<512>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 3. raw2outputs
+constexpr int COMP_WARPS = 8;
+__global__ void __launch_bounds__(COMP_WARPS * 32) composite_kernel(const __grid_constant__ RenderParams P) {
+    __shared__ float zs[COMP_WARPS][TP];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ray = blockIdx.x * COMP_WARPS + warp;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && P.stats) {      // device-timed duration of the decoder launch that fed this frame
+        const unsigned long long t0 = ~P.frame_clock[0], t1 = P.frame_clock[1];
+        atomicAdd(P.stats + 2, t1 > t0 ? t1 - t0 : 0ull);
+        atomicAdd(P.stats + 3, 1ull);
+    }
+    if (ray >= P.n_rays) return;
+    const int S = P.n_samples;
+    const size_t rg = (size_t)P.frame * P.n_rays + ray;
+    const float near = __ldg(P.near + rg), far = __ldg(P.far + rg);
+    for (int s = lane; s < S; s += 32) zs[warp][s] = z_sample(near, far, P.t_vals, s, S, P.t_rand ? P.t_rand + rg * S : nullptr);
+    __syncwarp();
+    const float dx = __ldg(P.ray_d + rg * 3), dy = __ldg(P.ray_d + rg * 3 + 1), dz = __ldg(P.ray_d + rg * 3 + 2);
+    const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    float* wout = P.weights ? P.weights + rg * S : nullptr;
+    RayOut o = composite_ray(P.raw_ws + (size_t)ray * S, zs[warp], S, nrm, wout, lane);
+    if (lane == 0) {
+        const float add = P.white_bkgd ? __fsub_rn(1.f, o.acc) : 0.f;
+        P.rgb_map[rg * 3 + 0] = o.r + add;
+        P.rgb_map[rg * 3 + 1] = o.g + add;
+        P.rgb_map[rg * 3 + 2] = o.b + add;
+        P.depth_map[rg] = o.depth;
+        P.acc_map[rg] = o.acc;
+        P.disp_map[rg] = disparity(o.depth, o.acc);
+    }
+}
+
+template <int NP, typename VT>
+static cudaError_t launch_list(const RenderParams& p, int grid, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(render_tc_list_kernel<NP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    render_tc_list_kernel<NP, VT><<<grid, NT, SMEM_BYTES, stream>>>(p);
+    return cudaGetLastError();
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+constexpr size_t CTL_BYTES = 32;   // per frame: u32 list count, pad, u64 ~start, u64 end
+
+}  // namespace tcl
+
+size_t render_tc_list_workspace_bytes(int batch, int n_rays, int n_samples) {
+    const size_t per_frame = (size_t)n_rays * n_samples * sizeof(float4);
+    return tcl::align256((size_t)batch * tcl::CTL_BYTES) + 2 * tcl::align256(per_frame);
+}
+
+bool render_tc_list_supported(const RenderParams& p) {
+    return p.n_samples <= tcl::TP && (size_t)p.n_rays * p.n_samples <= (size_t)tcl::ID_MASK;
+}
+
+int launch_render_tc_list(const RenderParams& p_in, int volume_dtype, int passes, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream) {
+    RenderParams p = p_in;
+    const int S = p.n_samples;
+    if (!render_tc_list_supported(p)) {
+        set_error("the list render pipeline supports n_samples <= 128 and n_rays * n_samples < 2^28 per frame");
+        return NB_ERR_UNSUPPORTED;
+    }
+    if (!workspace || workspace_bytes < render_tc_list_workspace_bytes(p.batch, p.n_rays, S)) {
+        set_error("nb_render_fwd: workspace too small (%zu bytes, need %zu; see nb_render_fwd_workspace_bytes)", workspace_bytes,
+                  render_tc_list_workspace_bytes(p.batch, p.n_rays, S));
+        return NB_ERR_BAD_ARG;
+    }
+    p.rays_per_group = tcl::MAXS / S;
+    p.tiles_per_group = 0;
+    p.groups_per_frame = (p.n_rays + p.rays_per_group - 1) / p.rays_per_group;
+    p.n_groups = p.groups_per_frame * p.batch;
+    if (p.n_rays == 0) return NB_OK;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t per_frame = tcl::align256((size_t)p.n_rays * S * sizeof(float4));
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float4* list = reinterpret_cast<float4*>(ws + tcl::align256((size_t)p.batch * tcl::CTL_BYTES));
+    float4* raw_ws = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(list) + per_frame);
+    cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)p.batch * tcl::CTL_BYTES, stream);
+    if (e != cudaSuccess) { set_error("render_tc_list: memset failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
+    // the tile count of a frame is only known on the device: size the grid for the worst case (every sample occupied)
+    const long long max_tiles = ((long long)p.n_rays * S + tcl::TP - 1) / tcl::TP;
+    const int grid = (int)(max_tiles < sms ? max_tiles : sms);
+    for (int b = 0; b < p.batch; ++b) {
+        p.frame = b;
+        p.list = list;
+        p.list_count = reinterpret_cast<unsigned int*>(ws + (size_t)b * tcl::CTL_BYTES);
+        p.frame_clock = reinterpret_cast<unsigned long long*>(ws + (size_t)b * tcl::CTL_BYTES + 8);
+        p.raw_ws = p_in.raw ? reinterpret_cast<float4*>(p_in.raw) + (size_t)b * p.n_rays * S : raw_ws;
+        tcl::classify_compact_kernel<<<p.groups_per_frame, tcl::MAXS, 0, stream>>>(p);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) {
+            if (passes == 3) e = (volume_dtype == NB_DTYPE_F32) ? tcl::launch_list<3, float>(p, grid, stream) : tcl::launch_list<3, __half>(p, grid, stream);
+            else e = (volume_dtype == NB_DTYPE_F32) ? tcl::launch_list<1, float>(p, grid, stream) : tcl::launch_list<1, __half>(p, grid, stream);
+        }
+        if (e == cudaSuccess) {
+            tcl::composite_kernel<<<(p.n_rays + tcl::COMP_WARPS - 1) / tcl::COMP_WARPS, tcl::COMP_WARPS * 32, 0, stream>>>(p);
+            e = cudaGetLastError();
+        }
+        if (e != cudaSuccess) { set_error("render_tc_list launch failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
+    }
+    return NB_OK;
+}
+
+}  // namespace nb

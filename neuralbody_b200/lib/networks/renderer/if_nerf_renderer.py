@@ -239,6 +239,15 @@ class Renderer:
             return ret
         return self._launch(call, save=False)
 
+    def _workspace(self, nbytes, dev):
+        """Scratch for nb_render_fwd, grown on demand and reused by every later call on this device's stream."""
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        ws = cache.get(dev)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            cache[dev] = ws
+        return ws
+
     def _launch(self, call, save):
         """Pack (cached) + one nb_render_fwd on the current stream."""
         dev, B, n, S = call["dev"], call["B"], call["n"], call["S"]
@@ -290,10 +299,16 @@ class Renderer:
                 a.mask_msks, a.mask_RT, a.mask_Ks = msks.data_ptr(), RT.data_ptr(), Ks.data_ptr()
                 a.mask_nv, a.mask_H, a.mask_W = int(msks.shape[0]), int(msks.shape[1]), int(msks.shape[2])
             a.stats = call["stats"].data_ptr() if call["stats"] is not None else None
+            ws = None
+            compact = (precision != capi.NB_PRECISION_FP32 and (call["skip_empty"] or call["masks"] is not None)
+                       and bool(self._opt("render_compact_frame", True)) and S <= 128 and n * S < (1 << 28))
+            if compact:   # frame-wide sample compaction: classify -> decoder over full tiles -> composite (3 launches / frame)
+                ws = self._workspace(self.lib.nb_render_fwd_workspace_bytes(B, n, S), dev)
+                a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             a.trace = call["trace"].data_ptr() if call["trace"] is not None else None   # diagnostics (tools/trace_timeline.py)
             stream = torch.cuda.current_stream(dev).cuda_stream
             capi.check(self.lib.nb_render_fwd(C.byref(a), C.c_void_p(stream)), "nb_render_fwd")
-            self.launches += self.lib.nb_render_fwd_launches(precision)
+            self.launches += 3 * B if ws is not None else self.lib.nb_render_fwd_launches(precision)
             if save:   # everything nb_render_bwd needs stays alive with the autograd node
                 call["args"], call["save"], call["raw"] = a, sv, raw
                 call["keep"] = (vol_blob, w_blob, t_vals, out)

@@ -65,20 +65,36 @@ def test_raw_decoder_output_vs_oracle(precision):
 @pytest.mark.parametrize("precision", ["tc_fp16x3", "tc_fp16"])
 @pytest.mark.parametrize("name", ["eval_s64", "train_jitter_white", "batch2_s32", "eval_s48_seed7", "full_313"])
 def test_empty_sample_skipping_is_bit_exact(name, precision):
-    """Skipping samples whose trilinear cells are all unoccupied changes no output bit (sigma_empty < 0)."""
+    """Skipping samples whose trilinear cells are all unoccupied changes no output bit (sigma_empty < 0) -- neither in the
+    single fused kernel (compaction per 1024-sample block) nor in the frame-compacting 3-launch pipeline."""
     scene, rkw, _ = golden_case(name)
     net, ren = G.make_net_and_renderer(scene)
-    ren.stats = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ren.stats = torch.zeros(4, dtype=torch.int64, device="cuda")
     dense = G.render_product(scene, precision=precision, skip_empty=False, renderer=ren, net=net, **rkw)
     assert int(ren.stats[0]) == 0                      # the dense kernel does not count
-    sparse = G.render_product(scene, precision=precision, skip_empty=True, renderer=ren, net=net, **rkw)
     B, n = scene["ray_o"].shape[:2]
     S = rkw["n_samples"]
-    tiles, occ = int(ren.stats[0]), int(ren.stats[1])
-    assert 0 < occ < B * n * S and tiles * 128 >= occ  # some, but not all, samples were evaluated
-    print(name, precision, "evaluated %.1f%% of the samples in %d tiles" % (100.0 * occ / (B * n * S), tiles))
-    for k in ("rgb_map", "depth_map", "acc_map", "weights", "disp_map"):
-        assert torch.equal(torch.nan_to_num(dense[k], nan=-1.0), torch.nan_to_num(sparse[k], nan=-1.0)), k
+    tiles = {}
+    for compact in (False, True):
+        ren.stats.zero_()
+        sparse = G.render_product(scene, precision=precision, skip_empty=True, renderer=ren, net=net, compact=compact, **rkw)
+        tiles[compact], occ = int(ren.stats[0]), int(ren.stats[1])
+        assert 0 < occ < B * n * S and tiles[compact] * 128 >= occ  # some, but not all, samples were evaluated
+        print(name, precision, "compact" if compact else "fused", "evaluated %.1f%% of the samples in %d tiles" % (
+            100.0 * occ / (B * n * S), tiles[compact]))
+        for k in ("rgb_map", "depth_map", "acc_map", "weights", "disp_map"):
+            assert torch.equal(torch.nan_to_num(dense[k], nan=-1.0), torch.nan_to_num(sparse[k], nan=-1.0)), (k, compact)
+    assert tiles[True] <= tiles[False] and tiles[True] <= (occ + 127) // 128 + B   # full tiles but the last of each frame
+
+
+def test_frame_compaction_writes_the_same_raw_records():
+    """want_raw: the 3-launch pipeline writes its raw records straight into the caller's buffer; they equal the fused kernel's."""
+    scene, rkw, _ = golden_case("train_jitter_white")
+    net, ren = G.make_net_and_renderer(scene)
+    a = G.render_product(scene, precision="tc_fp16x3", want_raw=True, renderer=ren, net=net, compact=False, **rkw)
+    b = G.render_product(scene, precision="tc_fp16x3", want_raw=True, renderer=ren, net=net, compact=True, **rkw)
+    for k in ("raw", "rgb_map", "depth_map", "acc_map"):
+        assert torch.equal(a[k], b[k]), k
 
 
 def test_density_only_decoder_matches_oracle():

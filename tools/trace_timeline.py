@@ -28,7 +28,8 @@ def main():
     scene = synth.make_scene(H=512, W=512, scale=1.0, all_hit=True)
     net, ren = G.make_net_and_renderer(scene)
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.render_precision, cfg.render_volume_dtype = 64, 0.0, False, prec, "auto"
-    cfg.render_skip_empty = len(sys.argv) > 4 and sys.argv[4] == "sparse"
+    cfg.render_skip_empty = len(sys.argv) > 4 and sys.argv[4] in ("sparse", "list")
+    cfg.render_compact_frame = len(sys.argv) > 4 and sys.argv[4] == "list"
     net.eval()
     batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}
     sp = ren.prepare_sp_input(batch)
