@@ -73,7 +73,7 @@ __device__ __forceinline__ void world_to_grid(const FrameXf& f, float wx, float 
 
 // F.grid_sample(align_corners=True) un-normalisation: ((g + 1) / 2) * (size - 1)
 __device__ __forceinline__ float unnormalize(float g, int size) {
-    return __fmul_rn(__fdiv_rn(__fadd_rn(g, 1.f), 2.f), (float)(size - 1));
+    return __fmul_rn(__fmul_rn(__fadd_rn(g, 1.f), 0.5f), (float)(size - 1));   // x / 2 == x * 0.5 bit for bit
 }
 
 // Trilinear corner set-up for one level (ATen grid_sampler_3d, zeros padding).

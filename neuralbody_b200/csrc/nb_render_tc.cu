@@ -377,7 +377,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                     wait_slot(slot);
                     for (int i = 0; i < 4; ++i) {
                         tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, (g0 | i) != 0);
-                        if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, true);
+                        // the lo half of the activations only matters on the density path: rows 128..143 of the step (alpha_fc
+                        // hi / lo + padding) -> accumulator columns 128..143; the 128 colour columns take the hi half alone
+                        if (NP == 3)
+                            tc::mma_ts(tmem + TM_ACC + 128, tmem + TM_LO + (g0 + i) * 8,
+                                       tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * kN3 * 32 + 128 * 16, kN3 * 16, 128), ID4, true);
                     }
                     release_slot(slot);
                 }

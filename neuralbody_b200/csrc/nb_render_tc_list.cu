@@ -38,6 +38,10 @@ constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;               // 704
 constexpr int PROD_THREADS = PROD_WARPS * 32;                     // 512
 constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);
 constexpr int MAXS = 1024;                                         // samples per classification block
+#ifndef NB_LIST_CLUSTER
+#define NB_LIST_CLUSTER 2
+#endif
+constexpr int CLUSTER = NB_LIST_CLUSTER;       // CTAs that share one weight stream through TMA multicast (all tiles cost the same)
 constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry .w = frame sample id | level bits << 28
 
 // shared-memory map (bytes)
@@ -49,12 +53,13 @@ constexpr int OFF_XF = OFF_RING + NUM_SLOTS * SLOT_BYTES;          // FrameXf
 constexpr int OFF_INFO = OFF_XF + 128;                             // TileInfo[2]
 constexpr int OFF_BAR = OFF_INFO + 64;
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + MAX_SEG_BUFS,
-       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_H_READY, BAR_MSG_FULL, BAR_MSG_FREE, NUM_BARS };
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_RGB_FULL, BAR_H_READY, BAR_MSG_FULL, BAR_MSG_FREE, NUM_BARS };
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 constexpr uint32_t TM_ACC = 0, TM_HI = 256, TM_LO = 384;
+constexpr uint32_t TM_RGB = TM_LO;      // layer 4 accumulates into the (then idle) lo plane, so ACC is free for the next tile's layer 0
 
 struct TileInfo {
     int nrows;       // list entries in this tile
@@ -81,9 +86,11 @@ __device__ __forceinline__ void load_frame_xf(const RenderParams& P, FrameXf* xf
 }
 
 // ------------------------------------------------------------------------------------------------ 1. classify + compact
-// One CTA per block of rays_per_group rays (<= 1024 samples), one sample per thread, SAMPLE-major inside the block so that
-// consecutive list entries are the same depth sample of neighbouring rays (they share their corner lines).
-__global__ void __launch_bounds__(MAXS) classify_compact_kernel(const __grid_constant__ RenderParams P) {
+// One CTA per block of rays_per_group rays (<= 1024 samples), CLS_PER_THREAD samples per thread, SAMPLE-major inside the
+// block so that consecutive list entries are the same depth sample of neighbouring rays (they share their corner lines).
+// 256-thread CTAs: eight of them are resident per SM, which hides the one atomicAdd round trip each block waits for.
+constexpr int CLS_THREADS = 256, CLS_PER_THREAD = MAXS / CLS_THREADS;
+__global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __grid_constant__ RenderParams P) {
     __shared__ FrameXf xf;
     __shared__ int wcnt[MAXS / 32];
     __shared__ unsigned int sbase;
@@ -97,50 +104,63 @@ __global__ void __launch_bounds__(MAXS) classify_compact_kernel(const __grid_con
     const bool can_skip = sigma_empty < -1e-3f;      // robustly negative => empty samples have weight exactly 0
     const uint32_t* occ_base = reinterpret_cast<const uint32_t*>(P.volume);
 
-    const int ry = tid % P.rays_per_group, s = tid / P.rays_per_group;
-    const bool live = ry < nr && s < S;
-    bool occ = false;
-    float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint32_t id = 0;
-    if (live) {
-        const size_t ri = (size_t)b * P.n_rays + r0 + ry;
-        const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
-        const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
-        const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
-        gm.x = __fadd_rn(ox, __fmul_rn(dx, z));
-        gm.y = __fadd_rn(oy, __fmul_rn(dy, z));
-        gm.z = __fadd_rn(oz, __fmul_rn(dz, z));
-        float gx, gy, gz;
-        world_to_grid(xf, gm.x, gm.y, gm.z, gx, gy, gz);
-        uint32_t lm = 0;                               // bit l = the sample's level-l cell holds a non-zero voxel
-        const bool inside = P.mask_nv == 0 || inside_masks(P, gm.x, gm.y, gm.z);   // f-1 mask views
-        if (inside) {
+    float4 gm[CLS_PER_THREAD];
+    uint32_t bal[CLS_PER_THREAD];
+    bool live[CLS_PER_THREAD], occ[CLS_PER_THREAD];
 #pragma unroll
-            for (int lvl = 0; lvl < 4; ++lvl) {
-                const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
-                Corners cn;
-                corner_setup(unnormalize(gx, W), unnormalize(gy, H), unnormalize(gz, D), W, H, D, cn);
-                if (cn.x0 != -2) {
-                    const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)b * P.occ_bstride[lvl];
-                    const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
-                    lm |= ((__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u) << lvl;
+    for (int k = 0; k < CLS_PER_THREAD; ++k) {
+        const int j = k * CLS_THREADS + tid;
+        const int ry = j % P.rays_per_group, s = j / P.rays_per_group;
+        live[k] = ry < nr && s < S;
+        occ[k] = false;
+        gm[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live[k]) {
+            const size_t ri = (size_t)b * P.n_rays + r0 + ry;
+            const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
+            const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
+            const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+            gm[k].x = __fadd_rn(ox, __fmul_rn(dx, z));
+            gm[k].y = __fadd_rn(oy, __fmul_rn(dy, z));
+            gm[k].z = __fadd_rn(oz, __fmul_rn(dz, z));
+            float gx, gy, gz;
+            world_to_grid(xf, gm[k].x, gm[k].y, gm[k].z, gx, gy, gz);
+            uint32_t lm = 0;                           // bit l = the sample's level-l cell holds a non-zero voxel
+            const bool inside = P.mask_nv == 0 || inside_masks(P, gm[k].x, gm[k].y, gm[k].z);   // f-1 mask views
+            if (inside) {
+#pragma unroll
+                for (int lvl = 0; lvl < 4; ++lvl) {
+                    const int D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
+                    Corners cn;
+                    corner_setup(unnormalize(gx, W), unnormalize(gy, H), unnormalize(gz, D), W, H, D, cn);
+                    if (cn.x0 != -2) {
+                        const uint32_t* cellbits = occ_base + P.occ_off[lvl] / 4 + (size_t)b * P.occ_bstride[lvl];
+                        const uint32_t cell = ((uint32_t)(cn.z0 + 1) * (H + 1) + (cn.y0 + 1)) * (W + 1) + (cn.x0 + 1);
+                        lm |= ((__ldg(cellbits + (cell >> 5)) >> (cell & 31)) & 1u) << lvl;
+                    }
                 }
             }
+            occ[k] = inside && (lm != 0u || !can_skip);
+            gm[k].w = __uint_as_float((uint32_t)((r0 + ry) * S + s) | (lm << 28));
         }
-        occ = inside && (lm != 0u || !can_skip);
-        id = (uint32_t)((r0 + ry) * S + s);
-        gm.w = __uint_as_float(id | (lm << 28));
+        bal[k] = __ballot_sync(0xffffffffu, occ[k]);
+        if (lane == 0) wcnt[k * (CLS_THREADS / 32) + warp] = __popc(bal[k]);
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, occ);
-    if (lane == 0) wcnt[warp] = __popc(bal);
     __syncthreads();
-    int base = 0, total = 0;
+    int total = 0;
 #pragma unroll
-    for (int w = 0; w < MAXS / 32; ++w) { const int c = wcnt[w]; base += (w < warp) ? c : 0; total += c; }
+    for (int w = 0; w < MAXS / 32; ++w) total += wcnt[w];
     if (tid == 0) sbase = total ? atomicAdd(P.list_count, (unsigned int)total) : 0u;
     __syncthreads();
-    if (occ) P.list[(size_t)sbase + base + __popc(bal & ((1u << lane) - 1))] = gm;
-    else if (live) P.raw_ws[id] = make_float4(0.f, 0.f, 0.f, fminf(sigma_empty, 0.f));   // skipped sample: weight exactly 0
+    const float4 empty = make_float4(0.f, 0.f, 0.f, fminf(sigma_empty, 0.f));   // skipped sample: weight exactly 0
+#pragma unroll
+    for (int k = 0; k < CLS_PER_THREAD; ++k) {
+        const int slot = k * (CLS_THREADS / 32) + warp;     // list order = sample-major order of the block
+        int base = 0;
+#pragma unroll
+        for (int w = 0; w < MAXS / 32; ++w) base += (w < slot) ? wcnt[w] : 0;
+        if (occ[k]) P.list[(size_t)sbase + base + __popc(bal[k] & ((1u << lane) - 1))] = gm[k];
+        else if (live[k]) P.raw_ws[__float_as_uint(gm[k].w) & ID_MASK] = empty;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ 2. decoder over the list
@@ -158,9 +178,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
 
     if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
     if (tid == LOAD_WARP * 32) {
-        for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], 1); }
+        for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], CLUSTER); }
         for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
+        tc::mbar_init(&bars[BAR_RGB_FULL], 1);
         tc::mbar_init(&bars[BAR_H_READY], EPI_WARPS * 32);
         tc::mbar_init(&bars[BAR_MSG_FULL], PROD_WARPS);
         tc::mbar_init(&bars[BAR_MSG_FREE], EPI_WARPS * 32 + 2);       // epilogue threads + MMA thread + loader thread
@@ -179,6 +200,9 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    if (CLUSTER > 1) tc::cluster_sync_all();      // the peer's mbarriers are initialised before any multicast lands
+    const uint32_t crank = CLUSTER > 1 ? tc::cluster_ctarank() : 0u;
+    constexpr uint16_t CMASK = (1u << CLUSTER) - 1;
     const uint32_t tmem = *tmem_slot;
     if (tid == 0 && P.stats) atomicMax(P.frame_clock + 0, ~global_ns());     // min(start) over the CTAs, as max(~start)
     const unsigned int n_rows_total = *P.list_count;                  // written by classify_compact_kernel (previous launch)
@@ -206,8 +230,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         };
         const uint32_t seg_base = tc::smem_u32(smem + OFF_SEG);
         const uint32_t so0 = (uint32_t)((((t >> 1) * 16 + (grp >> 3)) * 128) + (grp & 7) * 16 + (t & 1) * 8);
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int nrows = min(TP, (int)(n_rows_total - (unsigned int)tile * TP));
+        // a cluster walks the tiles in lockstep (shared weight stream): CTA r of cluster c takes tile c * CLUSTER + r of every
+        // round; a tile past the end is an empty one (nrows = 0) that keeps the peer's stream going
+        uint32_t real_tiles = 0;
+        for (int tbase = (blockIdx.x / CLUSTER) * CLUSTER; tbase < n_tiles; tbase += gridDim.x) {
+            const int tile = tbase + (int)crank;
+            const int nrows = tile < n_tiles ? min(TP, (int)(n_rows_total - (unsigned int)tile * TP)) : 0;
+            real_tiles += nrows > 0;
             // the list entries of this thread's rows: grid coordinates + per-level occupancy bits
             float4 g[PTS_PER_GROUP];
 #pragma unroll
@@ -299,7 +328,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         }
         publish(0, 0, 4);                               // done
         if (pt == 0 && P.stats) {
-            atomicAdd(P.stats + 0, (unsigned long long)it);
+            atomicAdd(P.stats + 0, (unsigned long long)real_tiles);
             if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)n_rows_total);
         }
     }
@@ -313,8 +342,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 unsigned char* dst = smem + OFF_RING + slot * SLOT_BYTES;
                 tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);
                 tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes + bytes2);
-                tc::bulk_g2s(dst, src, bytes, &bars[BAR_W_FULL + slot]);
-                if (bytes2) tc::bulk_g2s(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot]);
+                if (CLUSTER == 1) {
+                    tc::bulk_g2s(dst, src, bytes, &bars[BAR_W_FULL + slot]);
+                    if (bytes2) tc::bulk_g2s(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot]);
+                } else if (cnt % CLUSTER == crank) {      // the CTAs take turns issuing the copy for everybody
+                    tc::bulk_g2s_multicast(dst, src, bytes, &bars[BAR_W_FULL + slot], CMASK);
+                    if (bytes2) tc::bulk_g2s_multicast(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot], CMASK);
+                }
                 ++cnt;
             };
             for (;;) {
@@ -356,10 +390,17 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
                 tc::tc_fence_after();
             };
-            auto release_slot = [&](uint32_t slot) { tc::mma_commit(&bars[BAR_W_EMPTY + slot]); ++cnt; };
+            auto release_slot = [&](uint32_t slot) {
+                if (CLUSTER == 1) tc::mma_commit(&bars[BAR_W_EMPTY + slot]);
+                else tc::mma_commit_multicast(&bars[BAR_W_EMPTY + slot], CMASK);   // both CTAs' loaders wait for both consumers
+                ++cnt;
+            };
             auto a_desc = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * CHUNK_BYTES, CHUNK_BYTES, 128); };
             auto b_desc = [&](uint32_t slot, int i, int N) {
                 return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32, N * 16, 128);
+            };
+            auto b_desc_rows = [&](uint32_t slot, int i, int N, int row0) {     // rows row0.. of step i (8-row groups are 128 B apart)
+                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32 + row0 * 16, N * 16, 128);
             };
             auto wait_h = [&]() { tc::mbar_wait(&bars[BAR_H_READY], hcnt & 1); ++hcnt; tc::tc_fence_after(); };
             Tracer tr;
@@ -371,7 +412,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 ++msg;
                 if (flags & 4) break;
                 uint32_t slot;
-                if (it > 0) wait_h();
+                // no wait here: the previous tile's layer 4 wrote TM_RGB, and its layer-3 accumulator was read before layer 4
+                // was issued (h_ready #4), so ACC is already free while the epilogue still reads the previous rgb columns
                 tr.ev(1);
                 for (int seg = 0; seg < NUM_SEGS; ++seg) {
                     const uint32_t gseg = it * NUM_SEGS + seg;
@@ -429,7 +471,9 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     wait_slot(slot);
                     for (int i = 0; i < 4; ++i) {
                         tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, (g0 | i) != 0);
-                        if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, true);
+                        // the lo half of the activations only matters on the density path: rows 128..143 of the step (alpha_fc
+                        // hi / lo + padding) -> accumulator columns 128..143; the 128 colour columns take the hi half alone
+                        if (NP == 3) tc::mma_ts(tmem + TM_ACC + 128, tmem + TM_LO + (g0 + i) * 8, b_desc_rows(slot, i, kN3, 128), ID4, true);
                     }
                     release_slot(slot);
                 }
@@ -445,10 +489,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 tr.ev(34);
                 wait_slot(slot);
                 for (int ks = 0; ks < 8; ++ks)
-                    tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + ks * 8, b_desc(slot, ks, kN4), ID4, ks > 0);
-                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 8, kN4), ID4, true);
+                    tc::mma_ts(tmem + TM_RGB, tmem + TM_HI + ks * 8, b_desc(slot, ks, kN4), ID4, ks > 0);
+                tc::mma_ss(tmem + TM_RGB, a_desc(ones_addr, 0), b_desc(slot, 8, kN4), ID4, true);
                 release_slot(slot);
-                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tc::mma_commit(&bars[BAR_RGB_FULL]);
                 ++it;
             }
         }
@@ -458,7 +502,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         const int row = tid;
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
         unsigned char* PE = smem + OFF_PE;
-        uint32_t acnt = 0, msg = 0;
+        uint32_t acnt = 0, rcnt = 0, msg = 0;
         auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
         auto relu_to_h = [&](int ncols, bool with_lo) {
             const int ng = ncols / 8;
@@ -532,22 +576,23 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             }
             relu_to_h(128, false);
             h_done();
-            wait_acc();
+            tc::mbar_wait(&bars[BAR_RGB_FULL], rcnt & 1); ++rcnt; tc::tc_fence_after();
             {
                 uint32_t v[16];
-                tc::tmem_ld16(lane_base + TM_ACC, v);
+                tc::tmem_ld16(lane_base + TM_RGB, v);
                 tc::tmem_ld_wait();
                 if (smp >= 0)
                     P.raw_ws[smp] = make_float4(__uint_as_float(v[0]) + __uint_as_float(v[3]), __uint_as_float(v[1]) + __uint_as_float(v[4]),
                                                 __uint_as_float(v[2]) + __uint_as_float(v[5]), sigma);
             }
-            h_done();
+            tc::tc_fence_before();      // (the next write of TM_RGB's columns is this thread's own layer-0 epilogue of the next tile)
         }
     }
 
     tc::tc_fence_before();
     __syncthreads();
     if (tid == 0 && P.stats) atomicMax(P.frame_clock + 1, global_ns());
+    if (CLUSTER > 1) tc::cluster_sync_all();      // no CTA exits while the peer may still multicast into it
     if (warp == MMA_WARP) {
         __syncwarp();
         tc::tmem_dealloc<512>(tmem);
@@ -590,8 +635,17 @@ template <int NP, typename VT>
 static cudaError_t launch_list(const RenderParams& p, int grid, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(render_tc_list_kernel<NP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    render_tc_list_kernel<NP, VT><<<grid, NT, SMEM_BYTES, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, render_tc_list_kernel<NP, VT>, p);
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -637,14 +691,16 @@ int launch_render_tc_list(const RenderParams& p_in, int volume_dtype, int passes
     if (e != cudaSuccess) { set_error("render_tc_list: memset failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
     // the tile count of a frame is only known on the device: size the grid for the worst case (every sample occupied)
     const long long max_tiles = ((long long)p.n_rays * S + tcl::TP - 1) / tcl::TP;
-    const int grid = (int)(max_tiles < sms ? max_tiles : sms);
+    int grid = (int)(max_tiles < sms ? max_tiles : sms);
+    grid = (grid + tcl::CLUSTER - 1) / tcl::CLUSTER * tcl::CLUSTER;     // whole clusters; tiles past the end are no-ops
+    if (grid > sms) grid = sms / tcl::CLUSTER * tcl::CLUSTER;
     for (int b = 0; b < p.batch; ++b) {
         p.frame = b;
         p.list = list;
         p.list_count = reinterpret_cast<unsigned int*>(ws + (size_t)b * tcl::CTL_BYTES);
         p.frame_clock = reinterpret_cast<unsigned long long*>(ws + (size_t)b * tcl::CTL_BYTES + 8);
         p.raw_ws = p_in.raw ? reinterpret_cast<float4*>(p_in.raw) + (size_t)b * p.n_rays * S : raw_ws;
-        tcl::classify_compact_kernel<<<p.groups_per_frame, tcl::MAXS, 0, stream>>>(p);
+        tcl::classify_compact_kernel<<<p.groups_per_frame, tcl::CLS_THREADS, 0, stream>>>(p);
         e = cudaGetLastError();
         if (e == cudaSuccess) {
             if (passes == 3) e = (volume_dtype == NB_DTYPE_F32) ? tcl::launch_list<3, float>(p, grid, stream) : tcl::launch_list<3, __half>(p, grid, stream);
