@@ -30,7 +30,11 @@ constexpr int SLOT_BYTES = 4 * STEP_BYTES;
 constexpr int CHUNK_BYTES = 2048;
 constexpr int SEG_CHUNKS = 8;
 constexpr int NUM_SEGS = 6;
-constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * CHUNK_BYTES;      // 96 KB: 3 x (hi+lo) or 6 x hi
+// a layer-0 operand chunk (128 rows x 8 k) is 2048 B; the chunks of a segment are laid 2080 B apart (the K-direction
+// core-matrix stride LBO is a free descriptor field), which rotates successive chunks by 8 banks: the 4 rows x 8 channel
+// quads a producer warp stores per instruction then cover every bank exactly twice instead of 8 banks eight times
+constexpr int SEG_CHUNK_STRIDE = CHUNK_BYTES + 32;
+constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * SEG_CHUNK_STRIDE;  // 97.5 KB: 3 x (hi+lo) or 6 x hi
 constexpr int MAX_SEG_BUFS = 6;
 constexpr int PE_CHUNKS = 12;
 constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
@@ -229,7 +233,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             ++msg;
         };
         const uint32_t seg_base = tc::smem_u32(smem + OFF_SEG);
-        const uint32_t so0 = (uint32_t)((((t >> 1) * 16 + (grp >> 3)) * 128) + (grp & 7) * 16 + (t & 1) * 8);
+        const uint32_t so0 = (uint32_t)((t >> 1) * SEG_CHUNK_STRIDE + (grp >> 3) * 128 + (grp & 7) * 16 + (t & 1) * 8);
         // a cluster walks the tiles in lockstep (shared weight stream): CTA r of cluster c takes tile c * CLUSTER + r of every
         // round; a tile past the end is an empty one (nrows = 0) that keeps the peer's stream going
         uint32_t real_tiles = 0;
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 const uint32_t buf = gseg % NUM_SEG_BUFS;
                 tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1);
                 tr.ev(10 + seg);
-                // this thread's (row, channel quad) slot of the hi plane; the lo plane follows SEG_CHUNKS chunks later
+                // this thread's (row, channel quad) slot of the hi plane; the lo plane follows SEG_CHUNKS chunk strides later
                 const uint32_t dst = seg_base + buf * SEG_BYTES + so0;
                 const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
                 for (int uu = 0; uu < nunits; ++uu) {
@@ -309,13 +313,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         }
                         uint2 hi;
                         hi.x = tc::cvt_f16x2(a[0], a[1]); hi.y = tc::cvt_f16x2(a[2], a[3]);
-                        const uint32_t so = dst + (uint32_t)(uu * 4 * 16 * 128 + pp * 8 * 128);   // K-major core-matrix layout
+                        const uint32_t so = dst + (uint32_t)(uu * 4 * SEG_CHUNK_STRIDE + pp * 8 * 128);   // K-major core-matrix layout
                         tcr::sts_v2(so, hi);
                         if (NP == 3) {
                             uint2 lo;
                             lo.x = tc::cvt_f16x2(f16lo_of(a[0], hi.x, 0), f16lo_of(a[1], hi.x, 1));
                             lo.y = tc::cvt_f16x2(f16lo_of(a[2], hi.y, 0), f16lo_of(a[3], hi.y, 1));
-                            tcr::sts_v2(so + SEG_CHUNKS * CHUNK_BYTES, lo);
+                            tcr::sts_v2(so + SEG_CHUNKS * SEG_CHUNK_STRIDE, lo);
                         }
                     }
                 }
@@ -396,6 +400,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 ++cnt;
             };
             auto a_desc = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * CHUNK_BYTES, CHUNK_BYTES, 128); };
+            auto a_seg = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * SEG_CHUNK_STRIDE, SEG_CHUNK_STRIDE, 128); };
             auto b_desc = [&](uint32_t slot, int i, int N) {
                 return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32, N * 16, 128);
             };
@@ -421,18 +426,18 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
                     tc::tc_fence_after();
                     tr.ev(10 + seg);
-                    const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * CHUNK_BYTES;
+                    const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * SEG_CHUNK_STRIDE;
                     const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
                     wait_slot(slot);
                     for (int ks = 0; ks < nks; ++ks) {
-                        tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, ks, 256), ID256, (seg | ks) != 0);
-                        if (NP == 3) tc::mma_ss(tmem + TM_ACC, a_desc(lo_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                        tc::mma_ss(tmem + TM_ACC, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, (seg | ks) != 0);
+                        if (NP == 3) tc::mma_ss(tmem + TM_ACC, a_seg(lo_addr, ks), b_desc(slot, ks, 256), ID256, true);
                     }
                     release_slot(slot);
                     if (NP == 3) {
                         wait_slot(slot);
                         for (int ks = 0; ks < nks; ++ks)
-                            tc::mma_ss(tmem + TM_ACC, a_desc(hi_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                            tc::mma_ss(tmem + TM_ACC, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, true);
                         release_slot(slot);
                     }
                     tc::mma_commit(&bars[BAR_SEG_EMPTY + buf]);
