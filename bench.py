@@ -37,9 +37,10 @@ S = 64
 FLOP_PER_SAMPLE_AS_WRITTEN = 859904     # 2 x 429 952 MAC, layers of latent_xyzc.py:20-28
 FLOP_PER_SAMPLE_FOLDED = 532224         # exact fold of feature_fc o latent_fc o view_fc[:, :256]
 # tensor-core FLOPs the kernel actually ISSUES per sample (dense UMMA tiles incl. bias K-steps, the
-# alpha/rgb rows and, in the 3-pass mode, the A_lo*W_hi and A_hi*W_lo correction passes)
+# alpha/rgb rows and, in the 3-pass mode, the A_lo*W_hi and A_hi*W_lo correction passes; layer 3 takes the
+# lo half of its input only on the 16-row density block)
 FLOP_PER_SAMPLE_ISSUED = {"tc_fp16": 2 * 16 * (23 * 256 + 2 * 17 * 256 + 22 * 144 + 9 * 16),
-                          "tc_fp16x3": 2 * 16 * (67 * 256 + 2 * 49 * 256 + 38 * 144 + 9 * 16), "fp32": 532224}
+                          "tc_fp16x3": 2 * 16 * (67 * 256 + 2 * 49 * 256 + 22 * 144 + 16 * 16 + 9 * 16), "fp32": 532224}
 METRIC = "rays_per_s_512x512_64spp"
 
 
