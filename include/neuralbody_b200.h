@@ -146,6 +146,9 @@ typedef struct nb_render_args {
                               instead of the single fused kernel, same results bit for bit */
     size_t workspace_bytes;
     int    trace_fused;    /* diagnostics: 1 = keep the single fused kernel even when a workspace is given */
+    const float* z_vals;   /* device (B,n,S) or NULL.  When given, sample s of a ray sits at depth z_vals[b,r,s] (ascending) and
+                              near / far / t_vals / t_rand are not read: the fine pass of hierarchical sampling (f-4; NeRF-style
+                              volume_renderer.py:82-104 renders sorted(coarse z, importance z)).  Produced by nb_sample_pdf */
 } nb_render_args;
 
 int nb_render_fwd(const nb_render_args* args, void* stream);

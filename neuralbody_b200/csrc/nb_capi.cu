@@ -440,7 +440,7 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
 
     RenderParams& p = *out;
     p.batch = a->batch; p.n_rays = a->n_rays; p.n_samples = a->n_samples;
-    p.ray_o = a->ray_o; p.ray_d = a->ray_d; p.near = a->near; p.far = a->far; p.t_vals = a->t_vals; p.t_rand = a->t_rand;
+    p.ray_o = a->ray_o; p.ray_d = a->ray_d; p.near = a->near; p.far = a->far; p.t_vals = a->t_vals; p.t_rand = a->t_rand; p.z_user = a->z_vals;
     p.R = a->R; p.Th = a->Th; p.bounds = a->bounds;
     for (int i = 0; i < 3; ++i) { p.voxel_size[i] = a->voxel_size[i]; p.inv_voxel[i] = 1.f / a->voxel_size[i]; p.out_sh[i] = (float)a->out_sh[i]; }
     for (int l = 0; l < NB_NUM_LEVELS; ++l) {

@@ -26,8 +26,11 @@ __device__ __forceinline__ float z_plain(float near, float far, float t) {
 
 // z value of sample s, including the stratified jitter of if_clight_renderer.py:16-23
 // when t_rand != nullptr (t_rand points at this ray's S uniforms).
+// z_user != nullptr (this ray's S caller-supplied depths, nb_render_args.z_vals): used as they are -- the fine pass of
+// hierarchical sampling renders sorted(coarse z + importance samples), which no (near, far, t) formula produces.
 __device__ __forceinline__ float z_sample(float near, float far, const float* __restrict__ t_vals, int s, int S,
-                                          const float* __restrict__ t_rand) {
+                                          const float* __restrict__ t_rand, const float* __restrict__ z_user = nullptr) {
+    if (z_user) return __ldg(z_user + s);
     float tc = t_vals ? __ldg(t_vals + s) : linspace01(s, S);
     float z = z_plain(near, far, tc);
     if (t_rand) {

@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...);
 struct RenderParams {
     int batch, n_rays, n_samples;
     const float *ray_o, *ray_d, *near, *far, *t_vals, *t_rand;
+    const float* z_user;       // (B,n,S) caller-supplied sample depths (nb_render_args.z_vals) or null
     const float *R, *Th, *bounds;
     float inv_voxel[3];        // not used for parity-critical math (we divide, as upstream does)
     float voxel_size[3];       // dhw

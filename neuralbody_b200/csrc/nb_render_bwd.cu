@@ -27,6 +27,8 @@ struct BwdParams {
     float* d_vol[4];                // NCDHW fp32, caller-zeroed, accumulated into
 };
 
+constexpr int kBwdMaxSamples = 256;     // coarse + importance samples of a fine pass (64 + 128) fit
+
 // ------------------------------------------------------------------------------------------ 1. composite
 __global__ void composite_bwd_kernel(const BwdParams Q) {
     const RenderParams& P = Q.f;
@@ -37,18 +39,19 @@ __global__ void composite_bwd_kernel(const BwdParams Q) {
     const float dx = P.ray_d[ri * 3], dy = P.ray_d[ri * 3 + 1], dz = P.ray_d[ri * 3 + 2];
     const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     const float* tr = P.t_rand ? P.t_rand + ri * S : nullptr;
+    const float* zu = P.z_user ? P.z_user + ri * S : nullptr;
     const float4* raw = reinterpret_cast<const float4*>(Q.raw) + ri * S;
     float dC[3] = {0.f, 0.f, 0.f};
     if (Q.d_rgb) { dC[0] = Q.d_rgb[ri * 3]; dC[1] = Q.d_rgb[ri * 3 + 1]; dC[2] = Q.d_rgb[ri * 3 + 2]; }
     const float dD = Q.d_depth ? Q.d_depth[ri] : 0.f;
     float dA = Q.d_acc ? Q.d_acc[ri] : 0.f;
     if (P.white_bkgd) dA -= dC[0] + dC[1] + dC[2];            // rgb_map += 1 - acc_map
-    float Tbuf[128];                                           // exclusive transmittance (S <= 128 checked by the host)
+    float Tbuf[kBwdMaxSamples];                                // exclusive transmittance (S <= kBwdMaxSamples checked by the host)
     float T = 1.f;
     for (int s = 0; s < S; ++s) {
         Tbuf[s] = T;
-        const float z = z_sample(near, far, P.t_vals, s, S, tr);
-        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr), z) : 1e10f) * nrm;
+        const float z = z_sample(near, far, P.t_vals, s, S, tr, zu);
+        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr, zu), z) : 1e10f) * nrm;
         const float alpha = 1.f - expf(-fmaxf(raw[s].w, 0.f) * dist);
         T *= (1.f - alpha + 1e-10f);
     }
@@ -56,8 +59,8 @@ __global__ void composite_bwd_kernel(const BwdParams Q) {
     float U = 0.f;
     for (int s = S - 1; s >= 0; --s) {
         const float4 rw = raw[s];
-        const float z = z_sample(near, far, P.t_vals, s, S, tr);
-        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr), z) : 1e10f) * nrm;
+        const float z = z_sample(near, far, P.t_vals, s, S, tr, zu);
+        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr, zu), z) : 1e10f) * nrm;
         const float sg = fmaxf(rw.w, 0.f);
         const float e = expf(-sg * dist);
         const float alpha = 1.f - e;
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(NT, 1) decoder_dgrad_kernel(const BwdParams Q)
                     fx.Th[j] = P.Th[b * 3 + j]; fx.min_dhw[j] = P.bounds[b * 6 + (2 - j)];
                     fx.voxel[j] = P.voxel_size[j]; fx.out_sh[j] = P.out_sh[j];
                 }
-                const float z = z_sample(P.near[ri], P.far[ri], P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+                const float z = z_sample(P.near[ri], P.far[ri], P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr, P.z_user ? P.z_user + ri * S : nullptr);
                 const float wx = __fadd_rn(P.ray_o[ri * 3], __fmul_rn(P.ray_d[ri * 3], z));
                 const float wy = __fadd_rn(P.ray_o[ri * 3 + 1], __fmul_rn(P.ray_d[ri * 3 + 1], z));
                 const float wz = __fadd_rn(P.ray_o[ri * 3 + 2], __fmul_rn(P.ray_d[ri * 3 + 2], z));
@@ -411,7 +414,7 @@ extern "C" int nb_render_bwd(const nb_render_bwd_args* a, void* stream) {
         set_error("nb_render_bwd: the training path runs the exact kernel (NB_PRECISION_FP32 + fp32 volume)");
         return NB_ERR_UNSUPPORTED;
     }
-    if (f->n_samples > 128) { set_error("nb_render_bwd: n_samples <= 128 supported (got %d)", f->n_samples); return NB_ERR_UNSUPPORTED; }
+    if (f->n_samples > bwd::kBwdMaxSamples) { set_error("nb_render_bwd: n_samples <= %d supported (got %d)", bwd::kBwdMaxSamples, f->n_samples); return NB_ERR_UNSUPPORTED; }
     if (a->workspace_bytes < nb_render_bwd_workspace_bytes(f->batch, f->n_rays, f->n_samples)) {
         set_error("nb_render_bwd: workspace too small");
         return NB_ERR_BAD_ARG;

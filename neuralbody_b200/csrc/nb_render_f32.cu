@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
                 if (valid) {
                     const RayInfo& r = rays[ry];
                     const size_t ri = (size_t)b * P.n_rays + r0 + ry;
-                    const float z = z_sample(r.near, r.far, P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+                    const float z = z_sample(r.near, r.far, P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr, P.z_user ? P.z_user + ri * S : nullptr);
                     zbuf[ry * S + s] = z;
                     // pts = ray_o + ray_d * z   (if_clight_renderer.py:25)
                     const float wx = __fadd_rn(r.o[0], __fmul_rn(r.d[0], z));

@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_kernel(const __grid_constant_
                     const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
                     const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
                     const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S,
-                                             P.t_rand ? P.t_rand + ri * S : nullptr);
+                                             P.t_rand ? P.t_rand + ri * S : nullptr, P.z_user ? P.z_user + ri * S : nullptr);
                     gm.x = __fadd_rn(ox, __fmul_rn(dx, z));
                     gm.y = __fadd_rn(oy, __fmul_rn(dy, z));
                     gm.z = __fadd_rn(oz, __fmul_rn(dz, z));

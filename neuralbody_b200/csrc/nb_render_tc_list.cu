@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
             const size_t ri = (size_t)b * P.n_rays + r0 + ry;
             const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
             const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
-            const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+            const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr, P.z_user ? P.z_user + ri * S : nullptr);
             gm[k].x = __fadd_rn(ox, __fmul_rn(dx, z));
             gm[k].y = __fadd_rn(oy, __fmul_rn(dy, z));
             gm[k].z = __fadd_rn(oz, __fmul_rn(dz, z));
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
 // ------------------------------------------------------------------------------------------------ 3. raw2outputs
 constexpr int COMP_WARPS = 8;
 __global__ void __launch_bounds__(COMP_WARPS * 32) composite_kernel(const __grid_constant__ RenderParams P) {
-    __shared__ float zs[COMP_WARPS][TP];
+    __shared__ float zs[COMP_WARPS][MAXS];          // rays of up to MAXS samples (the decoder itself does not care about S)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ray = blockIdx.x * COMP_WARPS + warp;
     if (blockIdx.x == 0 && threadIdx.x == 0 && P.stats) {      // device-timed duration of the decoder launch that fed this frame
@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) composite_kernel(const __grid
     const int S = P.n_samples;
     const size_t rg = (size_t)P.frame * P.n_rays + ray;
     const float near = __ldg(P.near + rg), far = __ldg(P.far + rg);
-    for (int s = lane; s < S; s += 32) zs[warp][s] = z_sample(near, far, P.t_vals, s, S, P.t_rand ? P.t_rand + rg * S : nullptr);
+    for (int s = lane; s < S; s += 32) zs[warp][s] = z_sample(near, far, P.t_vals, s, S, P.t_rand ? P.t_rand + rg * S : nullptr, P.z_user ? P.z_user + rg * S : nullptr);
     __syncwarp();
     const float dx = __ldg(P.ray_d + rg * 3), dy = __ldg(P.ray_d + rg * 3 + 1), dz = __ldg(P.ray_d + rg * 3 + 2);
     const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
@@ -664,7 +664,7 @@ size_t render_tc_list_workspace_bytes(int batch, int n_rays, int n_samples) {
 }
 
 bool render_tc_list_supported(const RenderParams& p) {
-    return p.n_samples <= tcl::TP && (size_t)p.n_rays * p.n_samples <= (size_t)tcl::ID_MASK;
+    return p.n_samples <= tcl::MAXS && (size_t)p.n_rays * p.n_samples <= (size_t)tcl::ID_MASK;
 }
 
 int launch_render_tc_list(const RenderParams& p_in, int volume_dtype, int passes, void* workspace, size_t workspace_bytes,
@@ -672,7 +672,7 @@ int launch_render_tc_list(const RenderParams& p_in, int volume_dtype, int passes
     RenderParams p = p_in;
     const int S = p.n_samples;
     if (!render_tc_list_supported(p)) {
-        set_error("the list render pipeline supports n_samples <= 128 and n_rays * n_samples < 2^28 per frame");
+        set_error("the list render pipeline supports n_samples <= %d and n_rays * n_samples < 2^28 per frame", tcl::MAXS);
         return NB_ERR_UNSUPPORTED;
     }
     if (!workspace || workspace_bytes < render_tc_list_workspace_bytes(p.batch, p.n_rays, S)) {

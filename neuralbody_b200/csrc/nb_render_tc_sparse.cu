@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                     const size_t ri = (size_t)bc.b * P.n_rays + bc.r0 + ry;
                     const float ox = __ldg(P.ray_o + ri * 3), oy = __ldg(P.ray_o + ri * 3 + 1), oz = __ldg(P.ray_o + ri * 3 + 2);
                     const float dx = __ldg(P.ray_d + ri * 3), dy = __ldg(P.ray_d + ri * 3 + 1), dz = __ldg(P.ray_d + ri * 3 + 2);
-                    const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+                    const float z = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, s, S, P.t_rand ? P.t_rand + ri * S : nullptr, P.z_user ? P.z_user + ri * S : nullptr);
                     gm.x = __fadd_rn(ox, __fmul_rn(dx, z));
                     gm.y = __fadd_rn(oy, __fmul_rn(dy, z));
                     gm.z = __fadd_rn(oz, __fmul_rn(dz, z));
@@ -522,7 +522,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_sparse_kernel(const __grid_co
                 for (int j = row; j < nsmp; j += EPI_WARPS * 32) {
                     rawb[j] = make_float4(0.f, 0.f, 0.f, fminf(sigma_empty, 0.f));   // skipped samples: weight exactly 0
                     const size_t ri = (size_t)bc.b * P.n_rays + bc.r0 + j / S;
-                    zb[j] = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, j % S, S, P.t_rand ? P.t_rand + ri * S : nullptr);
+                    zb[j] = z_sample(__ldg(P.near + ri), __ldg(P.far + ri), P.t_vals, j % S, S, P.t_rand ? P.t_rand + ri * S : nullptr, P.z_user ? P.z_user + ri * S : nullptr);
                 }
                 named_bar_sync(2, EPI_WARPS * 32);
             }

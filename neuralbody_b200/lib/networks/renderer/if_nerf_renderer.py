@@ -189,7 +189,7 @@ class Renderer:
 
     # ------------------------------------------------------------------ fused launch
     def render_rays(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, want_raw=False,
-                    out=None, trace=None, masks=None):
+                    out=None, trace=None, masks=None, z_vals=None):
         """One nb_render_fwd launch for (B,n) rays.  Returns the dict of get_pixel_value.
         When autograd is recording and any volume / decoder tensor requires grad, the call goes through
         the exact kernel and `_FusedRender` so that `loss.backward()` works as it does upstream."""
@@ -201,16 +201,20 @@ class Renderer:
         if dev.type != "cuda":
             raise RuntimeError("Renderer.render needs CUDA tensors: the render path has no CPU implementation")
         B, n = int(ray_o.shape[0]), int(ray_o.shape[1])
-        S = int(cfg.N_samples)
+        S = int(cfg.N_samples) if z_vals is None else int(z_vals.shape[-1])   # z_vals: caller-supplied depths (fine pass, f-4)
         params = self.net.decoder_tensors()
         needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in params) or
                                                   any(v.requires_grad for v in feature_volume))
         precision = capi.NB_PRECISION_FP32 if needs_grad else self._precision()
-        if S > 128 and precision != capi.NB_PRECISION_FP32:
-            # the tensor-core kernels tile whole rays into 128-row MMA tiles (N_samples <= 128, every reference config);
-            # longer rays run on the exact CUDA kernel (still one fused launch, still no PyTorch op in the ray loop)
+        skip_empty = bool(self._opt("render_skip_empty", True))
+        compact = (skip_empty or masks is not None) and bool(self._opt("render_compact_frame", True)) and n * S < (1 << 28)
+        if precision != capi.NB_PRECISION_FP32 and (S > 1024 or (S > 128 and not compact)):
+            # the single-launch tensor-core kernels tile whole rays into 128-row MMA tiles (N_samples <= 128, every reference
+            # config); the frame-compacting pipeline takes rays of up to 1024 samples; anything else runs on the exact kernel
             precision = capi.NB_PRECISION_FP32
-        if t_rand is None and float(cfg.perturb) > 0. and self.net.training:
+        if z_vals is not None:
+            t_rand = None
+        elif t_rand is None and float(cfg.perturb) > 0. and self.net.training:
             t_rand = self._draw_t_rand(B, n, S, dev)
         call = {
             "B": B, "n": n, "S": S, "dev": dev, "precision": precision, "vdtype": self._volume_dtype(precision),
@@ -219,9 +223,10 @@ class Renderer:
             "bounds": _f32c(sp_input['bounds'], dev), "latent_index": sp_input['latent_index'],
             "out_sh": [int(v) for v in sp_input['out_sh']], "voxel_size": [float(v) for v in cfg.voxel_size],
             "t_rand": None if t_rand is None else _f32c(t_rand, dev), "white_bkgd": bool(cfg.white_bkgd),
+            "z_vals": None if z_vals is None else _f32c(z_vals.detach(), dev), "compact": compact,
             "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "out": out, "trace": trace,
             "want_weights": bool(self._opt("render_return_weights", True)) or needs_grad,
-            "skip_empty": bool(self._opt("render_skip_empty", True)), "stats": getattr(self, "stats", None),
+            "skip_empty": skip_empty, "stats": getattr(self, "stats", None),
             "masks": None,
         }
         if masks is not None:   # f-1: mask views of if_clight_renderer_mmsk.py (B = 1 only, as upstream)
@@ -277,6 +282,7 @@ class Renderer:
             a.near, a.far = call["near"].data_ptr(), call["far"].data_ptr()
             a.t_vals = t_vals.data_ptr()
             a.t_rand = call["t_rand"].data_ptr() if call["t_rand"] is not None else None
+            a.z_vals = call["z_vals"].data_ptr() if call["z_vals"] is not None else None
             a.R, a.Th, a.bounds = call["R"].data_ptr(), call["Th"].data_ptr(), call["bounds"].data_ptr()
             for i in range(3):
                 a.voxel_size[i] = call["voxel_size"][i]
@@ -300,9 +306,7 @@ class Renderer:
                 a.mask_nv, a.mask_H, a.mask_W = int(msks.shape[0]), int(msks.shape[1]), int(msks.shape[2])
             a.stats = call["stats"].data_ptr() if call["stats"] is not None else None
             ws = None
-            compact = (precision != capi.NB_PRECISION_FP32 and (call["skip_empty"] or call["masks"] is not None)
-                       and bool(self._opt("render_compact_frame", True)) and S <= 128 and n * S < (1 << 28))
-            if compact:   # frame-wide sample compaction: classify -> decoder over full tiles -> composite (3 launches / frame)
+            if precision != capi.NB_PRECISION_FP32 and call["compact"]:   # frame-wide sample compaction: classify -> decoder over full tiles -> composite (3 launches / frame)
                 ws = self._workspace(self.lib.nb_render_fwd_workspace_bytes(B, n, S), dev)
                 a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             a.trace = call["trace"].data_ptr() if call["trace"] is not None else None   # diagnostics (tools/trace_timeline.py)

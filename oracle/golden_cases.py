@@ -42,3 +42,29 @@ def build_case(name):
     if name.startswith("mmsk"):
         rkw["masks"] = synth.make_mask_views(scene, nv=4, H=96, W=96, radius=2)
     return scene, rkw
+
+
+# f-4 hierarchical sampling (coarse S + n_importance fine): name -> (scene kwargs, render kwargs, ray stride)
+HIER_CASES = {
+    # eval: deterministic u = linspace(0,1,N) (det = perturb == 0), BASELINE config 3's 64 + 128
+    "hier_s64_i128": (dict(H=48, W=48, scale=0.3, all_hit=True), dict(n_samples=64, n_importance=128), 9),
+    # train mode: stratified jitter in the coarse pass and random u in sample_pdf, both supplied; white background
+    "hier_train_s32_i48": (dict(H=40, W=40, scale=0.3, all_hit=True),
+                           dict(n_samples=32, n_importance=48, perturb=1.0, training=True, white_bkgd=True), 7),
+}
+
+
+def build_hier_case(name):
+    from neuralbody_b200 import synth
+    skw, rkw, stride = HIER_CASES[name]
+    scene = synth.make_scene(**skw)
+    idx = torch.arange(0, scene["ray_o"].shape[1], stride)
+    for k in ("ray_o", "ray_d", "near", "far"):
+        scene[k] = scene[k][:, idx].contiguous()
+    rkw = dict(rkw)
+    if rkw.get("perturb", 0) > 0:
+        g = torch.Generator().manual_seed(4321)
+        B, n = scene["ray_o"].shape[:2]
+        rkw["t_rand"] = torch.rand((B, n, rkw["n_samples"]), generator=g)
+        rkw["u"] = torch.rand((B, n, rkw["n_importance"]), generator=g)
+    return scene, rkw

@@ -62,6 +62,28 @@ def grad_golden():
     print("gradient fingerprints ->", path, "|dfc_0.weight|_1 = %.4e" % float(arrays["abs:fc_0.weight"]))
 
 
+def hier_golden():
+    """f-4: coarse + importance render composed from the reference's own functions (ref_harness.reference_render_hierarchical)."""
+    import torch
+    from neuralbody_b200 import synth
+    from oracle import ref_harness, golden_cases
+    for name in golden_cases.HIER_CASES:
+        scene, rkw = golden_cases.build_hier_case(name)
+        ret = ref_harness.reference_render_hierarchical(scene, **rkw)
+        arrays = {k: v.numpy().astype(np.float32) for k, v in ret.items()}
+        arrays["input_sha256"] = np.frombuffer(synth.scene_checksum(scene).encode(), dtype=np.uint8)
+        arrays["torch_version"] = np.frombuffer(torch.__version__.encode(), dtype=np.uint8)
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        np.savez_compressed(path, **arrays)
+        print("%-22s rays=%-5d acc.mean=%.3f |rgb - rgb0|max=%.3f -> %s (%d KB)" % (
+            name, ret["acc_map"].numel(), float(ret["acc_map"].mean()), float((ret["rgb_map"] - ret["rgb0"]).abs().max()),
+            path, os.path.getsize(path) // 1024))
+
+
 if __name__ == "__main__":
-    grad_golden()
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "hier":
+        hier_golden()
+    else:
+        grad_golden()
+        main()
+        hier_golden()

@@ -237,3 +237,80 @@ def render(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False, t
             far[:, i:i + chunk], scene['volumes'], sp_input, scene['voxel_size'], n_samples,
             perturb, training, white_bkgd, tr))
     return {k: torch.cat([r[k] for r in ret_list], dim=1) for k in ret_list[0]}
+
+
+# ------------------------------------------------------------------ f-4: hierarchical (coarse + importance) sampling
+# Neural Body's own renderer has no fine pass (`N_importance` is a dead key for it); the spec is the
+# reference's NeRF-baseline renderer, whose pieces are restated here and composed with the Neural Body decoder.
+def sample_pdf(bins, weights, n_importance, det=False, u=None):
+    """lib/networks/renderer/nerf_net_utils.py:55-90.  bins (N, M), weights (N, M-1) -> samples (N, n_importance).
+    `torchsearchsorted.searchsorted(cdf, u, side='right')` is torch.searchsorted(cdf, u, right=True);
+    `u` stands for the `torch.rand` draw at :70 (det=False)."""
+    weights = weights + 1e-5
+    pdf = weights / torch.sum(weights, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    if det:
+        u = torch.linspace(0., 1., steps=n_importance).to(cdf)
+        u = u.expand(list(cdf.shape[:-1]) + [n_importance])
+    elif u is None:
+        u = torch.rand(list(cdf.shape[:-1]) + [n_importance]).to(cdf)
+    u = u.contiguous()
+    inds = torch.searchsorted(cdf, u, right=True)
+    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
+    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
+    inds_g = torch.stack([below, above], -1)
+    matched_shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
+    cdf_g = torch.gather(cdf.unsqueeze(1).expand(matched_shape), 2, inds_g)
+    bins_g = torch.gather(bins.unsqueeze(1).expand(matched_shape), 2, inds_g)
+    denom = (cdf_g[..., 1] - cdf_g[..., 0])
+    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
+    t = (u - cdf_g[..., 0]) / denom
+    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+
+
+def importance_z_vals(z_vals, weights, n_importance, det=False, u=None):
+    """lib/networks/renderer/volume_renderer.py:84-93: z_vals, weights (N, S) -> (sorted (N, S + n_importance), samples)."""
+    z_vals_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+    z_samples = sample_pdf(z_vals_mid, weights[..., 1:-1], n_importance, det=det, u=u).detach()
+    z_all, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)
+    return z_all, z_samples
+
+
+def get_pixel_value_at(w, ray_o, ray_d, z_vals, feature_volume, sp_input, voxel_size, white_bkgd=False):
+    """get_pixel_value (if_clight_renderer.py:62-92) from given depths: pts = ray_o + ray_d * z (:25), decoder, raw2outputs."""
+    wpts = ray_o[:, :, None] + ray_d[:, :, None] * z_vals[..., None]
+    viewdir = ray_d / torch.norm(ray_d, dim=2, keepdim=True)
+    n_batch, n_pixel, n_sample = wpts.shape[:3]
+    vd = viewdir[:, :, None].repeat(1, 1, n_sample, 1).contiguous().view(n_batch, n_pixel * n_sample, -1)
+    raw = calculate_density_color(w, wpts.view(n_batch, n_pixel * n_sample, -1), vd, feature_volume, sp_input, voxel_size)
+    raw = raw.reshape(-1, n_sample, 4)
+    rgb_map, disp_map, acc_map, weights, depth_map = raw2outputs(raw, z_vals.view(-1, n_sample), ray_d.reshape(-1, 3), white_bkgd)
+    return {'rgb_map': rgb_map.view(n_batch, n_pixel, -1), 'disp_map': disp_map.view(n_batch, n_pixel),
+            'acc_map': acc_map.view(n_batch, n_pixel), 'weights': weights.view(n_batch, n_pixel, -1),
+            'depth_map': depth_map.view(n_batch, n_pixel)}
+
+
+def render_hierarchical(scene, n_samples=64, n_importance=128, perturb=0.0, training=False, white_bkgd=False,
+                        t_rand=None, u=None, chunk=2048):
+    """volume_renderer.py:60-118 with the Neural Body decoder in place of `self.net`: coarse pass, sample_pdf on its
+    weights (det = (perturb == 0)), sort-merge, fine pass over the S + n_importance depths with the SAME network.
+    Returns the fine maps plus rgb0 / disp0 / acc0 / z_std like the reference dict (:105-118); `u` (B,n,n_importance)."""
+    sp_input = prepare_sp_input(scene)
+    w, vols, vs = scene['weights'], scene['volumes'], scene['voxel_size']
+    outs = []
+    for i in range(0, scene['ray_o'].shape[1], chunk):
+        ro, rd = scene['ray_o'][:, i:i + chunk], scene['ray_d'][:, i:i + chunk]
+        near, far = scene['near'][:, i:i + chunk], scene['far'][:, i:i + chunk]
+        tr = None if t_rand is None else t_rand[:, i:i + chunk]
+        _, z_vals = get_sampling_points(ro, rd, near, far, n_samples, perturb, training, tr)
+        coarse = get_pixel_value_at(w, ro, rd, z_vals, vols, sp_input, vs, white_bkgd)
+        B, n = z_vals.shape[:2]
+        uu = None if u is None else u[:, i:i + chunk].reshape(B * n, -1)
+        z_all, z_samples = importance_z_vals(z_vals.view(B * n, -1), coarse['weights'].view(B * n, -1), n_importance,
+                                             det=(perturb == 0.), u=uu)
+        fine = get_pixel_value_at(w, ro, rd, z_all.view(B, n, -1), vols, sp_input, vs, white_bkgd)
+        fine.update({'rgb0': coarse['rgb_map'], 'disp0': coarse['disp_map'], 'acc0': coarse['acc_map'],
+                     'z_std': torch.std(z_samples, dim=-1, unbiased=False).view(B, n), 'z_vals': z_all.view(B, n, -1)})
+        outs.append(fine)
+    return {k: torch.cat([r[k] for r in outs], dim=1) for k in outs[0]}

@@ -152,3 +152,74 @@ def reference_render(scene, n_samples=64, perturb=0.0, training=False, white_bkg
     if grad:
         return ret, net, volumes
     return {k: v.detach() for k, v in ret.items()}
+
+
+def reference_render_hierarchical(scene, n_samples=64, n_importance=128, perturb=0.0, training=False, white_bkgd=False,
+                                  t_rand=None, u=None, chunk=2048):
+    """f-4 golden generator.  Neural Body has no fine pass of its own, so this composes UNMODIFIED reference
+    functions exactly the way the reference's NeRF-baseline renderer does (lib/networks/renderer/volume_renderer.py:60-118):
+    Renderer.get_sampling_points / get_density_color (if_clight_renderer.py:11-27,54-60) and Network.calculate_density_color
+    for the network, nerf_net_utils.raw2outputs (:6-51) and nerf_net_utils.sample_pdf (:55-90) for the rest.
+    `torchsearchsorted` (absent; nerf_net_utils.py:56) is stubbed with torch.searchsorted, which has the same semantics;
+    torch.rand is patched so the reference's own draws consume `t_rand` (B,n,S) and `u` (B,n,n_importance)."""
+    import torch
+    cfg, latent_xyzc, if_clight_renderer, nerf_net_utils = load_reference()
+    if "torchsearchsorted" not in sys.modules:
+        tss = types.ModuleType("torchsearchsorted")
+        tss.searchsorted = lambda a, v, side="left": torch.searchsorted(a, v, right=(side == "right"))
+        sys.modules["torchsearchsorted"] = tss
+    cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.raw_noise_std = int(n_samples), float(perturb), bool(white_bkgd), 0
+    cfg.voxel_size = [float(v) for v in scene["voxel_size"]]
+    cfg.num_train_frame = int(scene["weights"]["latent.weight"].shape[0])
+    net = latent_xyzc.Network()
+    missing, unexpected = net.load_state_dict(scene["weights"], strict=False)
+    assert not unexpected and all(k.startswith("xyzc_net") or k.startswith("c.") for k in missing)
+    net.train(training)
+    renderer = if_clight_renderer.Renderer(net)
+    batch = {k: scene[k] for k in ("coord", "out_sh", "bounds", "R", "Th", "latent_index")}
+    sp_input = renderer.prepare_sp_input(batch)
+    vols = scene["volumes"]
+    decoder = lambda x, vd: net.calculate_density_color(x, vd, vols, sp_input)
+    draws = []
+    real_rand = torch.rand
+
+    def fake_rand(shape, *a, **k):
+        out = draws.pop(0)
+        assert tuple(out.shape) == tuple(shape), (tuple(out.shape), tuple(shape))
+        return out.clone()
+
+    outs = []
+    assert chunk == 2048
+    try:
+        torch.rand = fake_rand
+        with torch.no_grad():
+            for i in range(0, scene["ray_o"].shape[1], chunk):
+                ro, rd = scene["ray_o"][:, i:i + chunk], scene["ray_d"][:, i:i + chunk]
+                near, far = scene["near"][:, i:i + chunk], scene["far"][:, i:i + chunk]
+                B, n = ro.shape[:2]
+                if perturb > 0 and training:
+                    draws.append(t_rand[:, i:i + chunk])
+                wpts, z_vals = renderer.get_sampling_points(ro, rd, near, far)
+                viewdir = rd / torch.norm(rd, dim=2, keepdim=True)
+                raw = renderer.get_density_color(wpts, viewdir, decoder).reshape(-1, n_samples, 4)
+                z_vals = z_vals.view(-1, n_samples)
+                rays_d = rd.reshape(-1, 3)
+                rgb0, disp0, acc0, weights, _ = nerf_net_utils.raw2outputs(raw, z_vals, rays_d, cfg.raw_noise_std, cfg.white_bkgd)
+                # volume_renderer.py:84-93
+                z_vals_mid = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+                if perturb != 0.:
+                    draws.append(u[:, i:i + chunk].reshape(B * n, n_importance))
+                z_samples = nerf_net_utils.sample_pdf(z_vals_mid, weights[..., 1:-1], n_importance, det=(perturb == 0.)).detach()
+                z_all, _ = torch.sort(torch.cat([z_vals, z_samples], -1), -1)
+                S2 = n_samples + n_importance
+                pts = ro[:, :, None] + rd[:, :, None] * z_all.view(B, n, S2)[..., None]
+                raw = renderer.get_density_color(pts, viewdir, decoder).reshape(-1, S2, 4)
+                rgb, disp, acc, w2, depth = nerf_net_utils.raw2outputs(raw, z_all, rays_d, cfg.raw_noise_std, cfg.white_bkgd)
+                outs.append({"rgb_map": rgb.view(B, n, 3), "disp_map": disp.view(B, n), "acc_map": acc.view(B, n),
+                             "weights": w2.view(B, n, S2), "depth_map": depth.view(B, n), "rgb0": rgb0.view(B, n, 3),
+                             "disp0": disp0.view(B, n), "acc0": acc0.view(B, n),
+                             "z_std": torch.std(z_samples, dim=-1, unbiased=False).view(B, n), "z_vals": z_all.view(B, n, S2)})
+    finally:
+        torch.rand = real_rand
+    assert not draws
+    return {k: torch.cat([o[k] for o in outs], dim=1).detach() for k in outs[0]}

@@ -42,6 +42,19 @@ def golden_case(name):
     return _case_cache[name]
 
 
+def hier_golden_case(name):
+    """f-4 cases (oracle/golden_cases.HIER_CASES): (scene, render kwargs incl. t_rand / u, golden dict)."""
+    key = "hier:" + name
+    if key not in _case_cache:
+        from neuralbody_b200 import synth
+        from oracle import golden_cases
+        scene, rkw = golden_cases.build_hier_case(name)
+        gold = load_golden(name)
+        assert synth.scene_checksum(scene) == gold["input_sha256"], "rebuilt inputs differ from the golden generator's"
+        _case_cache[key] = (scene, rkw, gold)
+    return _case_cache[key]
+
+
 @pytest.fixture(scope="session")
 def built_lib():
     """Make sure the in-tree shared library exists (nvcc cross-compiles without a GPU)."""

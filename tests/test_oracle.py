@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_case
+from conftest import golden_case, hier_golden_case
 from oracle import golden_cases, neuralbody_oracle as O
 
 KEYS = ("rgb_map", "disp_map", "acc_map", "weights", "depth_map")
@@ -22,6 +22,32 @@ def test_oracle_matches_reference_golden(name):
         # same torch ops in the same order => bit-identical, NaNs (acc == 0 rays) included
         np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
         np.testing.assert_allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=0, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize("name", list(golden_cases.HIER_CASES))
+def test_hierarchical_oracle_matches_reference_pieces(name):
+    """f-4: the restated sample_pdf / sort-merge / fine pass against the composition of the reference's own functions."""
+    scene, rkw, gold = hier_golden_case(name)
+    out = O.render_hierarchical(scene, **rkw)
+    for k in KEYS + ("rgb0", "disp0", "acc0", "z_std", "z_vals"):
+        a, b = out[k].numpy(), gold[k]
+        assert a.shape == b.shape, k
+        np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=0, atol=1e-6, err_msg=k)
+    S, Ni = rkw["n_samples"], rkw["n_importance"]
+    assert gold["z_vals"].shape[-1] == S + Ni and (np.diff(gold["z_vals"], axis=-1) >= 0).all()
+    assert np.abs(gold["rgb_map"] - gold["rgb0"]).max() > 1e-3      # the fine pass is not a no-op on these scenes
+
+
+def test_sample_pdf_known_answers():
+    """nerf_net_utils.py:55-90 on hand-checkable inputs: uniform weights => the inverse CDF is the identity on the bins."""
+    bins = torch.linspace(0., 1., 5)[None]                      # 5 bin edges, 4 equal weights
+    s = O.sample_pdf(bins, torch.ones(1, 4), 9, det=True)
+    np.testing.assert_allclose(s.numpy()[0], np.linspace(0., 1., 9), atol=1e-6)
+    # all the mass in the 2nd interval: every sample (u strictly inside (0,1)) lands in [0.25, 0.5]
+    w = torch.tensor([[0., 1., 0., 0.]])
+    s = O.sample_pdf(bins, w, 7, det=False, u=torch.linspace(0.01, 0.99, 7)[None])
+    assert float(s.min()) >= 0.25 - 1e-4 and float(s.max()) <= 0.5 + 1e-4
 
 
 def test_golden_scenes_are_not_vacuous():
