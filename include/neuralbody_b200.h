@@ -158,6 +158,28 @@ int nb_render_fwd(const nb_render_args* args, void* stream);
  * later calls on the same stream. */
 size_t nb_render_fwd_workspace_bytes(int batch, int n_rays, int n_samples);
 
+/* f-4: importance sampling between the coarse and the fine pass of a hierarchical (coarse + fine) render.  Neural Body's
+ * own renderer has no fine pass; the spec is the reference's NeRF-baseline renderer: z_vals_mid, sample_pdf
+ * (lib/networks/renderer/nerf_net_utils.py:55-90, det = (cfg.perturb == 0)) and the sort-merge of
+ * lib/networks/renderer/volume_renderer.py:84-93.  The coarse depths are re-derived from (near, far, t_vals, t_rand)
+ * exactly as nb_render_fwd derived them.  z_out then goes into nb_render_args.z_vals with n_samples = S + n_importance. */
+typedef struct nb_importance_args {
+    int n_rays_total;      /* B * n rays */
+    int n_samples;         /* S of the coarse pass (3..256) */
+    int n_importance;      /* cfg.N_importance (S + n_importance <= 512) */
+    const float* near;     /* device (B*n) */
+    const float* far;      /* device (B*n) */
+    const float* t_vals;   /* device (S) or NULL, as in nb_render_args */
+    const float* t_rand;   /* device (B*n,S) or NULL: the coarse pass's jitter */
+    const float* weights;  /* device (B*n,S): the coarse pass's compositing weights */
+    const float* u;        /* device (B*n,n_importance) uniforms [0,1) (the torch.rand of nerf_net_utils.py:70), or NULL for the
+                              deterministic torch.linspace(0,1,n_importance) of the det branch */
+    float* z_out;          /* device (B*n, S + n_importance): sorted(coarse z, importance z) */
+    float* z_samples;      /* device (B*n, n_importance) or NULL: the importance samples alone (the reference's z_std input) */
+} nb_importance_args;
+
+int nb_sample_pdf(const nb_importance_args* args, void* stream);
+
 /* f-3: density on arbitrary world points.  Replaces Network.calculate_density (lib/networks/latent_xyzc.py:74-89), the
  * alpha decoder of the mesh renderer (lib/networks/renderer/if_mesh_renderer.py:36-41).  Only the frame fields of `frame`
  * are read (batch, R, Th, bounds, voxel_size, out_sh, level_dims, volume_blob/dtype, weights_blob); exact fp32 arithmetic.

@@ -14,7 +14,7 @@ NB_NUM_LEVELS = 4
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
            "nb_render_fwd_launches", "nb_render_fwd_workspace_bytes", "nb_debug_tc_probe", "nb_render_bwd", "nb_render_save_bytes",
-           "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays"]
+           "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays", "nb_sample_pdf"]
 
 
 class nb_volume_level(C.Structure):
@@ -52,6 +52,12 @@ class nb_render_args(C.Structure):
         ("mask_nv", C.c_int), ("mask_H", C.c_int), ("mask_W", C.c_int), ("skip_empty", C.c_int), ("stats", C.c_void_p), ("save", C.c_void_p),
         ("trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("trace_fused", C.c_int), ("z_vals", C.c_void_p),
     ]
+
+
+class nb_importance_args(C.Structure):
+    _fields_ = [("n_rays_total", C.c_int), ("n_samples", C.c_int), ("n_importance", C.c_int),
+                ("near", C.c_void_p), ("far", C.c_void_p), ("t_vals", C.c_void_p), ("t_rand", C.c_void_p),
+                ("weights", C.c_void_p), ("u", C.c_void_p), ("z_out", C.c_void_p), ("z_samples", C.c_void_p)]
 
 
 class nb_render_bwd_args(C.Structure):
@@ -107,6 +113,8 @@ def load(path=None):
     lib.nb_decode_density.argtypes = [C.POINTER(nb_render_args), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.nb_gen_rays.restype = C.c_int
     lib.nb_gen_rays.argtypes = [C.POINTER(nb_camera)] + [C.c_void_p] * 6
+    lib.nb_sample_pdf.restype = C.c_int
+    lib.nb_sample_pdf.argtypes = [C.POINTER(nb_importance_args), C.c_void_p]
     lib.nb_debug_tc_probe.restype = C.c_int
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     if lib.nb_abi_version() != 2:

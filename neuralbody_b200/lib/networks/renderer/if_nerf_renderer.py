@@ -189,7 +189,7 @@ class Renderer:
 
     # ------------------------------------------------------------------ fused launch
     def render_rays(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, want_raw=False,
-                    out=None, trace=None, masks=None, z_vals=None):
+                    out=None, trace=None, masks=None, z_vals=None, want_weights=None):
         """One nb_render_fwd launch for (B,n) rays.  Returns the dict of get_pixel_value.
         When autograd is recording and any volume / decoder tensor requires grad, the call goes through
         the exact kernel and `_FusedRender` so that `loss.backward()` works as it does upstream."""
@@ -225,7 +225,8 @@ class Renderer:
             "t_rand": None if t_rand is None else _f32c(t_rand, dev), "white_bkgd": bool(cfg.white_bkgd),
             "z_vals": None if z_vals is None else _f32c(z_vals.detach(), dev), "compact": compact,
             "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "out": out, "trace": trace,
-            "want_weights": bool(self._opt("render_return_weights", True)) or needs_grad,
+            "want_weights": (bool(self._opt("render_return_weights", True)) if want_weights is None else bool(want_weights))
+                            or needs_grad,
             "skip_empty": skip_empty, "stats": getattr(self, "stats", None),
             "masks": None,
         }
@@ -406,8 +407,58 @@ class Renderer:
         return sigma
 
     def get_pixel_value(self, ray_o, ray_d, near, far, feature_volume, sp_input, batch):
-        """if_clight_renderer.py:62-92: same signature, same returned dict."""
+        """if_clight_renderer.py:62-92: same signature, same returned dict.  With `cfg.render_importance > 0` the call runs the
+        coarse + fine passes of `render_rays_hierarchical` and the dict also carries rgb0 / disp0 / acc0 / z_std."""
+        if int(self._opt("render_importance", 0)) > 0:
+            return self.render_rays_hierarchical(ray_o, ray_d, near, far, feature_volume, sp_input)
         return self.render_rays(ray_o, ray_d, near, far, feature_volume, sp_input)
+
+    # ------------------------------------------------------------------ f-4: hierarchical (coarse + importance) sampling
+    def importance_z_vals(self, near, far, weights, n_samples, n_importance, t_rand=None, u=None):
+        """z_vals_mid + sample_pdf + sort-merge (volume_renderer.py:84-93, nerf_net_utils.py:55-90) as one nb_sample_pdf launch.
+        weights (B,n,S) from the coarse pass; t_rand its jitter (or None); u (B,n,n_importance) uniforms or None for the
+        deterministic branch.  Returns (z_all (B,n,S+n_importance) ascending, z_samples (B,n,n_importance))."""
+        dev = weights.device
+        B, n, S = int(weights.shape[0]), int(weights.shape[1]), int(n_samples)
+        Ni = int(n_importance)
+        with torch.cuda.device(dev), torch.no_grad():
+            z_all = torch.empty((B, n, S + Ni), dtype=torch.float32, device=dev)
+            z_smp = torch.empty((B, n, Ni), dtype=torch.float32, device=dev)
+            keep = [_f32c(near, dev), _f32c(far, dev), self._t_vals(S, dev), _f32c(weights.detach(), dev),
+                    None if t_rand is None else _f32c(t_rand, dev), None if u is None else _f32c(u, dev)]
+            a = capi.nb_importance_args()
+            a.n_rays_total, a.n_samples, a.n_importance = B * n, S, Ni
+            a.near, a.far, a.t_vals, a.weights = keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr()
+            a.t_rand = keep[4].data_ptr() if keep[4] is not None else None
+            a.u = keep[5].data_ptr() if keep[5] is not None else None
+            a.z_out, a.z_samples = z_all.data_ptr(), z_smp.data_ptr()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            capi.check(self.lib.nb_sample_pdf(C.byref(a), C.c_void_p(stream)), "nb_sample_pdf")
+            self.launches += 1
+        return z_all, z_smp
+
+    def render_rays_hierarchical(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, u=None):
+        """Coarse pass (cfg.N_samples) -> importance samples from its weights -> fine pass over the merged depths with the SAME
+        network, as the reference's NeRF-baseline renderer does (volume_renderer.py:60-118; Neural Body's own renderer has no
+        fine pass).  `cfg.render_importance` = N_importance; det = (cfg.perturb == 0) as upstream.
+        Both passes are nb_render_fwd launches (the fine one with nb_render_args.z_vals); under autograd each is a
+        `_FusedRender` node and the importance samples are detached, as upstream."""
+        cfg = get_active_cfg()
+        Ni = int(self._opt("render_importance", 0))
+        S = int(cfg.N_samples)
+        dev = ray_o.device
+        B, n = int(ray_o.shape[0]), int(ray_o.shape[1])
+        if t_rand is None and float(cfg.perturb) > 0. and self.net.training:
+            t_rand = self._draw_t_rand(B, n, S, dev)
+        if u is None and float(cfg.perturb) != 0.:
+            u = torch.rand((B * n, Ni)).view(B, n, Ni).to(dev)          # nerf_net_utils.py:70 (CPU generator, like upstream)
+        coarse = self.render_rays(ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=t_rand,
+                                  want_weights=True)          # the coarse weights drive the importance sampling
+        z_all, z_smp = self.importance_z_vals(near, far, coarse['weights'], S, Ni, t_rand=t_rand, u=u)
+        fine = dict(self.render_rays(ray_o, ray_d, near, far, feature_volume, sp_input, z_vals=z_all))
+        fine['rgb0'], fine['disp0'], fine['acc0'] = coarse['rgb_map'], coarse['disp_map'], coarse['acc_map']
+        fine['z_std'] = torch.std(z_smp, dim=-1, unbiased=False)
+        return fine
 
     # ------------------------------------------------------------------ a1
     def render(self, batch):

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import golden_case
+from conftest import golden_case, hier_golden_case
 from oracle import golden_cases, neuralbody_oracle as O
 import gpu_utils as G
 
@@ -114,14 +114,24 @@ def test_density_only_decoder_matches_oracle():
     assert float(want.max()) > 5.0 and float(want.min()) < -5.0          # not vacuous
 
 
-def test_long_rays_run_on_the_exact_kernel():
-    """N_samples > 128 (e.g. 64 coarse + 128 importance merged) is served by the exact fused kernel."""
+def test_long_rays():
+    """N_samples > 128 (e.g. 64 coarse + 128 importance merged): the frame-compacting pipeline keeps such rays
+    on the tensor cores (its decoder works on a sample list and does not care about S); the single fused launch tiles
+    whole rays into 128-row tiles and hands them to the exact kernel instead."""
     scene, rkw, _ = golden_case("eval_s64")
     sub = dict(scene)
     for k in ("ray_o", "ray_d", "near", "far"):
         sub[k] = scene[k][:, :64].contiguous()
-    out = G.render_product(sub, precision="tc_fp16x3", n_samples=192)
     ref = O.render(sub, n_samples=192)
+    net, ren = G.make_net_and_renderer(sub)
+    ren.stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    out = G.render_product(sub, precision="tc_fp16x3", n_samples=192, renderer=ren, net=net)
+    assert int(ren.stats[3]) == 1 and int(ren.stats[0]) > 0          # one decoder launch of the list pipeline ran
+    for k in ("rgb_map", "depth_map", "acc_map"):
+        assert float((out[k] - ref[k]).abs().max()) < 1e-3, k
+    ren.stats.zero_()
+    out = G.render_product(sub, precision="tc_fp16x3", n_samples=192, compact=False, renderer=ren, net=net)
+    assert int(ren.stats[0]) == 0                                      # exact kernel: no tensor-core tiles
     for k in ("rgb_map", "depth_map", "acc_map"):
         assert float((out[k] - ref[k]).abs().max()) < 1e-4, k
 
@@ -192,3 +202,77 @@ def test_product_path_fails_loudly_on_cpu_tensors():
     with pytest.raises(RuntimeError):
         with torch.no_grad():
             ren.render(batch)
+
+
+# ---------------------------------------------------------------------------------------------- f-4 hierarchical sampling
+@pytest.mark.parametrize("name", list(golden_cases.HIER_CASES))
+@pytest.mark.parametrize("precision", ["fp32", "tc_fp16x3"])
+def test_hierarchical_render_matches_reference_pieces(name, precision):
+    """Coarse pass -> nb_sample_pdf -> fine pass (nb_render_args.z_vals, S + N_importance samples per ray, on the tensor
+    cores through the frame-compacting pipeline) against the composition of the reference's own functions."""
+    from neuralbody_b200.lib.config import cfg
+    scene, rkw, gold = hier_golden_case(name)
+    net, ren = G.make_net_and_renderer(scene)
+    cfg.N_samples, cfg.perturb, cfg.white_bkgd = rkw["n_samples"], float(rkw.get("perturb", 0.)), bool(rkw.get("white_bkgd", False))
+    cfg.raw_noise_std, cfg.render_precision, cfg.render_volume_dtype, cfg.chunk = 0, precision, "auto", 0
+    cfg.render_skip_empty, cfg.render_compact_frame, cfg.render_importance = True, True, rkw["n_importance"]
+    net.train(bool(rkw.get("training", False)))
+    try:
+        batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}
+        sp = ren.prepare_sp_input(batch)
+        vol = net.encode_sparse_voxels(sp)
+        tr = rkw.get("t_rand")
+        u = rkw.get("u")
+        with torch.no_grad():
+            # the depths first: bit-for-bit the reference's sort(cat(z_vals, sample_pdf(...))) up to the summation order of the pdf
+            coarse = ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp,
+                                     t_rand=None if tr is None else tr.cuda(), want_weights=True)
+            z_all, z_smp = ren.importance_z_vals(batch["near"], batch["far"], coarse["weights"], rkw["n_samples"],
+                                                 rkw["n_importance"], t_rand=None if tr is None else tr.cuda(),
+                                                 u=None if u is None else u.cuda())
+            out = ren.render_rays_hierarchical(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp,
+                                               t_rand=None if tr is None else tr.cuda(), u=None if u is None else u.cuda())
+        torch.cuda.synchronize()
+    finally:
+        cfg.render_importance = 0
+    zg = torch.from_numpy(gold["z_vals"])
+    assert torch.all(z_all[..., 1:] >= z_all[..., :-1])
+    # The depths follow the reference's sort(cat(z_vals, sample_pdf(...))).  The inverse CDF is ill-conditioned where the
+    # coarse weights vanish (pdf = 1e-5 / sum: dz/du ~ 300 m), so a 1e-6 difference in a weight moves a sample that sits in
+    # EMPTY space by up to ~1e-3 m without touching any output; everywhere else the depths agree to rounding.
+    dz = (z_all.cpu() - zg).abs()
+    ztol = 2e-5 if precision == "fp32" else 2e-3
+    assert float((dz < ztol).float().mean()) > 0.97, float((dz < ztol).float().mean())
+    assert float(dz.max()) < (5e-3 if precision == "fp32" else 5e-2), float(dz.max())
+    out = {k: v.detach().cpu() for k, v in out.items()}
+    tol = TOL[precision]
+    for k in ("rgb_map", "depth_map", "acc_map", "rgb0", "acc0"):
+        d = float((out[k] - torch.from_numpy(gold[k])).abs().max())
+        assert d < tol, (k, d)
+    assert float((out["z_std"] - torch.from_numpy(gold["z_std"])).abs().max()) < (1e-3 if precision == "fp32" else 1e-2)
+    assert out["weights"].shape[-1] == rkw["n_samples"] + rkw["n_importance"]
+
+
+def test_sample_pdf_kernel_vs_oracle_random():
+    """nb_sample_pdf alone on random weights / jitter / uniforms against oracle.importance_z_vals (no rendering involved)."""
+    torch.manual_seed(5)
+    from neuralbody_b200 import synth
+    scene = synth.make_scene(H=8, W=8, scale=0.25)
+    net, ren = G.make_net_and_renderer(scene)
+    B, n, S, Ni = 2, 300, 48, 77
+    near = torch.rand(B, n) + 1.0
+    far = near + 1.0 + torch.rand(B, n)
+    # every bin carries mass, so the inverse CDF is well conditioned (where weights vanish the reference's formula jumps by
+    # a whole bin on a 1-ulp change of the CDF: `denom < 1e-5 -> 1`), plus rays without any weight (uniform pdf: the +1e-5)
+    w = torch.rand(B, n, S) * 0.9 + 0.1
+    w[:, ::7] = 0.
+    t_rand, u = torch.rand(B, n, S), torch.rand(B, n, Ni)
+    ro, rd = torch.zeros(B, n, 3), torch.ones(B, n, 3)
+    for det in (True, False):
+        _, z = O.get_sampling_points(ro, rd, near, far, S, perturb=0.0 if det else 1.0, training=not det, t_rand=None if det else t_rand)
+        z_ref, s_ref = O.importance_z_vals(z.view(B * n, S), w.view(B * n, S), Ni, det=det, u=None if det else u.view(B * n, Ni))
+        z_all, z_smp = ren.importance_z_vals(near.cuda(), far.cuda(), w.cuda(), S, Ni, t_rand=None if det else t_rand.cuda(),
+                                             u=None if det else u.cuda())
+        torch.cuda.synchronize()
+        assert float((z_all.cpu().view(B * n, -1) - z_ref).abs().max()) < 2e-5
+        assert float((z_smp.cpu().view(B * n, -1) - s_ref).abs().max()) < 2e-5
