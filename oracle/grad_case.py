@@ -37,3 +37,34 @@ def oracle_grads(scene, t_rand, G):
     ret = O.render(sc, n_samples=N_SAMPLES, perturb=1.0, training=True, white_bkgd=True, t_rand=t_rand)
     loss_of(ret, G).backward()
     return {k: sc["weights"][k].grad for k in GRAD_KEYS}, [v.grad for v in sc["volumes"]], ret
+
+
+# ---------------------------------------------------------------------------- f-4: coarse + fine pass under autograd
+N_IMPORTANCE = 48
+
+
+def hier_build():
+    """Same scene / jitter as build(), plus the uniforms of sample_pdf and a cotangent for the coarse image (the trainer adds
+    img_loss0 on rgb0, lib/train/trainers/if_nerf_clight.py:29-32)."""
+    scene, t_rand, G = build()
+    B, n = scene["ray_o"].shape[:2]
+    g = torch.Generator().manual_seed(100)
+    u = torch.rand((B, n, N_IMPORTANCE), generator=g)
+    G = dict(G)
+    G["rgb0"] = torch.randn((B, n, 3), generator=g)
+    return scene, t_rand, u, G
+
+
+def hier_loss_of(ret, G):
+    return loss_of(ret, G) + (ret["rgb0"] * G["rgb0"]).sum()
+
+
+def oracle_hier_grads(scene, t_rand, u, G):
+    from oracle import neuralbody_oracle as O
+    sc = dict(scene)
+    sc["weights"] = {k: v.clone().requires_grad_(True) for k, v in scene["weights"].items()}
+    sc["volumes"] = [v.clone().requires_grad_(True) for v in scene["volumes"]]
+    ret = O.render_hierarchical(sc, n_samples=N_SAMPLES, n_importance=N_IMPORTANCE, perturb=1.0, training=True,
+                                white_bkgd=True, t_rand=t_rand, u=u)
+    hier_loss_of(ret, G).backward()
+    return {k: sc["weights"][k].grad for k in GRAD_KEYS}, [v.grad for v in sc["volumes"]], ret

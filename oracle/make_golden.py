@@ -80,10 +80,36 @@ def hier_golden():
             path, os.path.getsize(path) // 1024))
 
 
+def hier_grad_golden():
+    """f-4 gradient fingerprints: autograd of the reference's own functions through coarse pass, detached sample_pdf, fine pass."""
+    from neuralbody_b200 import synth
+    from oracle import ref_harness, grad_case
+    scene, t_rand, u, G = grad_case.hier_build()
+    ret, net, vols = ref_harness.reference_render_hierarchical(
+        scene, n_samples=grad_case.N_SAMPLES, n_importance=grad_case.N_IMPORTANCE, perturb=1.0, training=True, white_bkgd=True,
+        t_rand=t_rand, u=u, grad=True)
+    grad_case.hier_loss_of(ret, G).backward()
+    sd = dict(net.named_parameters())
+    arrays = {"input_sha256": np.frombuffer(synth.scene_checksum(scene).encode(), dtype=np.uint8)}
+    for k in grad_case.GRAD_KEYS:
+        g = sd[k].grad
+        arrays["sum:" + k] = np.float64(g.double().sum())
+        arrays["abs:" + k] = np.float64(g.double().abs().sum())
+        arrays["head:" + k] = g.reshape(-1)[:64].numpy().astype(np.float32)
+    for l, v in enumerate(vols):
+        arrays["sum:vol%d" % l] = np.float64(v.grad.double().sum())
+        arrays["abs:vol%d" % l] = np.float64(v.grad.double().abs().sum())
+    path = os.path.join(ROOT, "tests", "golden", "grad_hier_s32_i48.npz")
+    np.savez_compressed(path, **arrays)
+    print("hierarchical gradient fingerprints ->", path, "|dfc_0.weight|_1 = %.4e" % float(arrays["abs:fc_0.weight"]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "hier":
         hier_golden()
+        hier_grad_golden()
     else:
         grad_golden()
         main()
         hier_golden()
+        hier_grad_golden()

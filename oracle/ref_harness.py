@@ -155,7 +155,7 @@ def reference_render(scene, n_samples=64, perturb=0.0, training=False, white_bkg
 
 
 def reference_render_hierarchical(scene, n_samples=64, n_importance=128, perturb=0.0, training=False, white_bkgd=False,
-                                  t_rand=None, u=None, chunk=2048):
+                                  t_rand=None, u=None, chunk=2048, grad=False):
     """f-4 golden generator.  Neural Body has no fine pass of its own, so this composes UNMODIFIED reference
     functions exactly the way the reference's NeRF-baseline renderer does (lib/networks/renderer/volume_renderer.py:60-118):
     Renderer.get_sampling_points / get_density_color (if_clight_renderer.py:11-27,54-60) and Network.calculate_density_color
@@ -178,7 +178,7 @@ def reference_render_hierarchical(scene, n_samples=64, n_importance=128, perturb
     renderer = if_clight_renderer.Renderer(net)
     batch = {k: scene[k] for k in ("coord", "out_sh", "bounds", "R", "Th", "latent_index")}
     sp_input = renderer.prepare_sp_input(batch)
-    vols = scene["volumes"]
+    vols = [v.clone().requires_grad_(grad) for v in scene["volumes"]]
     decoder = lambda x, vd: net.calculate_density_color(x, vd, vols, sp_input)
     draws = []
     real_rand = torch.rand
@@ -192,7 +192,7 @@ def reference_render_hierarchical(scene, n_samples=64, n_importance=128, perturb
     assert chunk == 2048
     try:
         torch.rand = fake_rand
-        with torch.no_grad():
+        with (torch.enable_grad() if grad else torch.no_grad()):
             for i in range(0, scene["ray_o"].shape[1], chunk):
                 ro, rd = scene["ray_o"][:, i:i + chunk], scene["ray_d"][:, i:i + chunk]
                 near, far = scene["near"][:, i:i + chunk], scene["far"][:, i:i + chunk]
@@ -222,4 +222,7 @@ def reference_render_hierarchical(scene, n_samples=64, n_importance=128, perturb
     finally:
         torch.rand = real_rand
     assert not draws
-    return {k: torch.cat([o[k] for o in outs], dim=1).detach() for k in outs[0]}
+    ret = {k: torch.cat([o[k] for o in outs], dim=1) for k in outs[0]}
+    if grad:
+        return ret, net, vols
+    return {k: v.detach() for k, v in ret.items()}
