@@ -245,6 +245,22 @@ class Renderer:
             return ret
         return self._launch(call, save=False)
 
+    def _pool_take(self, tag, numel, dtype, dev):
+        """A buffer of >= numel elements from the renderer's pool (several can be out at once: the coarse and the fine pass of
+        a hierarchical step each hold an activation record until their backward ran)."""
+        free = self.__dict__.setdefault("_pool", {}).setdefault((tag, dtype, str(dev)), [])
+        for i, t in enumerate(free):
+            if t.numel() >= numel:
+                return free.pop(i)
+        if free:                      # too small for this call: let the allocator have the smallest one back
+            free.sort(key=lambda t: t.numel())
+            free.pop(0)
+        return torch.empty(int(numel), dtype=dtype, device=dev)
+
+    def _pool_give(self, tag, t):
+        if t is not None:
+            self.__dict__.setdefault("_pool", {}).setdefault((tag, t.dtype, str(t.device)), []).append(t)
+
     def _workspace(self, nbytes, dev):
         """Scratch for nb_render_fwd, grown on demand and reused by every later call on this device's stream."""
         cache = self.__dict__.setdefault("_ws_cache", {})
@@ -275,7 +291,9 @@ class Renderer:
             raw = torch.empty((B, n, S, 4), dtype=torch.float32, device=dev) if call["want_raw"] else None
             sv = None
             if save:
-                sv = torch.empty(self.lib.nb_render_save_bytes(B, n, S) // 4, dtype=torch.float32, device=dev)
+                # the activation record (5.2 KB per sample) and the backward scratch are hundreds of MB per training chunk:
+                # they are recycled through a small per-renderer pool instead of going back to the allocator every step
+                sv = self._pool_take("save", self.lib.nb_render_save_bytes(B, n, S) // 4, torch.float32, dev)
 
             a = capi.nb_render_args()
             a.batch, a.n_rays, a.n_samples = B, n, S
@@ -325,6 +343,9 @@ class Renderer:
     def _launch_bwd(self, call, d_rgb, d_depth, d_acc, needs):
         """nb_render_bwd: gradients for (volumes..., decoder tensors...) in the order of _FusedRender.apply."""
         dev, B, n, S = call["dev"], call["B"], call["n"], call["S"]
+        if call.get("save") is None:
+            raise RuntimeError("the activation record of this render call was already consumed by a backward pass "
+                               "(backward twice through the same nb_render_fwd is not supported)")
         params = self.net.decoder_tensors()
         vols = call["feature_volume"]
         with torch.cuda.device(dev), torch.no_grad():
@@ -341,7 +362,7 @@ class Renderer:
             want_vol = any(needs[:len(vols)])
             gvols = [torch.zeros_like(v, dtype=torch.float32, device=dev) for v in vols] if want_vol else [None] * len(vols)
             nbytes = self.lib.nb_render_bwd_workspace_bytes(B, n, S)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = self._pool_take("bwd_ws", nbytes, torch.uint8, dev)
             ba = capi.nb_render_bwd_args()
             ba.fwd = C.pointer(call["args"])
             ba.save, ba.raw = call["save"].data_ptr(), call["raw"].data_ptr()
@@ -354,6 +375,9 @@ class Renderer:
             ba.workspace, ba.workspace_bytes = ws.data_ptr(), nbytes
             stream = torch.cuda.current_stream(dev).cuda_stream
             capi.check(self.lib.nb_render_bwd(C.byref(ba), C.c_void_p(stream)), "nb_render_bwd")
+            # stream-ordered reuse: the next forward / backward on this stream runs after the kernels just enqueued
+            self._pool_give("bwd_ws", ws)
+            self._pool_give("save", call.pop("save"))
         grads = list(gvols) + [gp.view_as(t) for gp, t in zip(gparams, params)]
         return [gr if need else None for gr, need in zip(grads, needs)]
 
