@@ -249,12 +249,11 @@ class Renderer:
         """A buffer of >= numel elements from the renderer's pool (several can be out at once: the coarse and the fine pass of
         a hierarchical step each hold an activation record until their backward ran)."""
         free = self.__dict__.setdefault("_pool", {}).setdefault((tag, dtype, str(dev)), [])
-        for i, t in enumerate(free):
-            if t.numel() >= numel:
-                return free.pop(i)
-        if free:                      # too small for this call: let the allocator have the smallest one back
-            free.sort(key=lambda t: t.numel())
-            free.pop(0)
+        fits = [i for i, t in enumerate(free) if t.numel() >= numel]
+        if fits:                      # best fit: the coarse pass must not grab the fine pass's (3x larger) record
+            return free.pop(min(fits, key=lambda i: free[i].numel()))
+        if len(free) >= 4:            # nothing fits and the pool is full: let the allocator have the smallest one back
+            free.pop(min(range(len(free)), key=lambda i: free[i].numel()))
         return torch.empty(int(numel), dtype=dtype, device=dev)
 
     def _pool_give(self, tag, t):
