@@ -243,30 +243,31 @@ def render(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False, t
 # Neural Body's own renderer has no fine pass (`N_importance` is a dead key for it); the spec is the
 # reference's NeRF-baseline renderer, whose pieces are restated here and composed with the Neural Body decoder.
 def sample_pdf(bins, weights, n_importance, det=False, u=None):
-    """lib/networks/renderer/nerf_net_utils.py:55-90.  bins (N, M), weights (N, M-1) -> samples (N, n_importance).
-    `torchsearchsorted.searchsorted(cdf, u, side='right')` is torch.searchsorted(cdf, u, right=True);
-    `u` stands for the `torch.rand` draw at :70 (det=False)."""
-    weights = weights + 1e-5
-    pdf = weights / torch.sum(weights, -1, keepdim=True)
-    cdf = torch.cumsum(pdf, -1)
-    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    """Inverse-CDF sampling of lib/networks/renderer/nerf_net_utils.py:55-90, same fp32 operations in the same order.
+    bins (N, M) interval mid-points, weights (N, M-1) -> samples (N, n_importance).
+      :59-63  pdf = (w + 1e-5) / sum, cdf = [0, cumsum(pdf)]                         (N, M)
+      :66-70  u = linspace(0, 1, n) if det else rand(N, n)   (`u` stands for that draw)
+      :74-77  hi = searchsorted(cdf, u, side='right') (torchsearchsorted == torch.searchsorted(right=True)),
+              lo = max(hi - 1, 0), hi = min(hi, M - 1)
+      :82-88  t = (u - cdf[lo]) / (cdf[hi] - cdf[lo], or 1 where that is < 1e-5); sample = bins[lo] + t * (bins[hi] - bins[lo])"""
+    w = weights + 1e-5
+    pdf = w / torch.sum(w, -1, keepdim=True)
+    cdf = torch.cat([torch.zeros_like(pdf[..., :1]), torch.cumsum(pdf, -1)], -1)
+    lead = list(cdf.shape[:-1])
     if det:
-        u = torch.linspace(0., 1., steps=n_importance).to(cdf)
-        u = u.expand(list(cdf.shape[:-1]) + [n_importance])
+        u = torch.linspace(0., 1., steps=n_importance).to(cdf).expand(lead + [n_importance])
     elif u is None:
-        u = torch.rand(list(cdf.shape[:-1]) + [n_importance]).to(cdf)
+        u = torch.rand(lead + [n_importance]).to(cdf)
     u = u.contiguous()
-    inds = torch.searchsorted(cdf, u, right=True)
-    below = torch.max(torch.zeros_like(inds - 1), inds - 1)
-    above = torch.min((cdf.shape[-1] - 1) * torch.ones_like(inds), inds)
-    inds_g = torch.stack([below, above], -1)
-    matched_shape = [inds_g.shape[0], inds_g.shape[1], cdf.shape[-1]]
-    cdf_g = torch.gather(cdf.unsqueeze(1).expand(matched_shape), 2, inds_g)
-    bins_g = torch.gather(bins.unsqueeze(1).expand(matched_shape), 2, inds_g)
-    denom = (cdf_g[..., 1] - cdf_g[..., 0])
-    denom = torch.where(denom < 1e-5, torch.ones_like(denom), denom)
-    t = (u - cdf_g[..., 0]) / denom
-    return bins_g[..., 0] + t * (bins_g[..., 1] - bins_g[..., 0])
+    hi = torch.searchsorted(cdf, u, right=True)
+    lo = torch.clamp(hi - 1, min=0)
+    hi = torch.clamp(hi, max=cdf.shape[-1] - 1)
+    c_lo, c_hi = torch.gather(cdf, -1, lo), torch.gather(cdf, -1, hi)
+    b_lo, b_hi = torch.gather(bins, -1, lo), torch.gather(bins, -1, hi)
+    span = c_hi - c_lo
+    span = torch.where(span < 1e-5, torch.ones_like(span), span)
+    t = (u - c_lo) / span
+    return b_lo + t * (b_hi - b_lo)
 
 
 def importance_z_vals(z_vals, weights, n_importance, det=False, u=None):
