@@ -16,7 +16,5 @@ def load_source(module_name, path):
 
 
 def make_network(cfg):
-    module = cfg.network_module
-    path = cfg.network_path
-    network = load_source(module, path).Network()
-    return network
+    plugin = load_source(cfg.network_module, cfg.network_path)
+    return plugin.Network()
