@@ -39,7 +39,8 @@ def test_struct_layouts_match_header(built_lib):
     import subprocess
     import tempfile
     from neuralbody_b200 import capi
-    src = '#include <stdio.h>\n#include "neuralbody_b200.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(nb_volume_level), sizeof(nb_decoder_weights), sizeof(nb_render_args));return 0;}\n'
+    src = ('#include <stdio.h>\n#include "neuralbody_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(nb_volume_level), '
+           'sizeof(nb_decoder_weights), sizeof(nb_render_args), sizeof(nb_importance_args), sizeof(nb_camera));return 0;}\n')
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c")
         open(c, "w").write(src)
@@ -47,7 +48,7 @@ def test_struct_layouts_match_header(built_lib):
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     assert sizes == [ctypes.sizeof(capi.nb_volume_level), ctypes.sizeof(capi.nb_decoder_weights),
-                     ctypes.sizeof(capi.nb_render_args)]
+                     ctypes.sizeof(capi.nb_render_args), ctypes.sizeof(capi.nb_importance_args), ctypes.sizeof(capi.nb_camera)]
 
 
 def test_size_queries_without_gpu(built_lib):
@@ -65,6 +66,34 @@ def test_size_queries_without_gpu(built_lib):
     # argument validation happens before any CUDA call
     assert lib.nb_render_fwd(None, None) < 0
     assert b"null" in lib.nb_last_error()
+    # scratch of the frame-compacting pipeline: a 32-byte control block per frame + 2 x 16 B per sample of ONE frame
+    ws = lib.nb_render_fwd_workspace_bytes
+    per_frame = 512 * 512 * 64 * 16
+    assert ws(1, 512 * 512, 64) == 256 + 2 * per_frame and ws(3, 512 * 512, 64) == ws(1, 512 * 512, 64)
+    assert ws(0, 10, 10) == 0 and ws(1, 1000, 192) >= 2 * 1000 * 192 * 16
+    # f-4: nb_sample_pdf validates its sizes before it touches the device
+    a = capi.nb_importance_args()
+    a.n_rays_total, a.n_samples, a.n_importance = 10, 2, 8
+    assert lib.nb_sample_pdf(ctypes.byref(a), None) < 0 and b"n_samples >= 3" in lib.nb_last_error()
+    a.n_samples, a.n_importance = 300, 8
+    assert lib.nb_sample_pdf(ctypes.byref(a), None) < 0 and b"supported" in lib.nb_last_error()
+    a.n_samples, a.n_importance = 64, 128
+    assert lib.nb_sample_pdf(ctypes.byref(a), None) < 0 and b"null" in lib.nb_last_error()
+
+
+def test_training_buffer_pool_is_best_fit():
+    """The renderer recycles the activation record / backward scratch (host logic, device-agnostic): a small request must not
+    take the large buffer a later, larger request needs (coarse vs fine pass of a hierarchical step)."""
+    from neuralbody_b200.lib.networks.renderer.if_nerf_renderer import Renderer
+    r = Renderer.__new__(Renderer)
+    big = r._pool_take("save", 3000, torch.float32, torch.device("cpu"))
+    small = r._pool_take("save", 1000, torch.float32, torch.device("cpu"))
+    r._pool_give("save", big)
+    r._pool_give("save", small)
+    assert r._pool_take("save", 900, torch.float32, torch.device("cpu")) is small
+    assert r._pool_take("save", 2500, torch.float32, torch.device("cpu")) is big
+    fresh = r._pool_take("save", 10, torch.float32, torch.device("cpu"))
+    assert fresh is not small and fresh is not big and fresh.numel() == 10
 
 
 def test_config_surface_and_overrides(tmp_path):
