@@ -6,8 +6,9 @@ so reference checkpoints load with `load_state_dict(..., strict=False)`.
 
 What is NOT here, by the scope contract (north star): the SparseConvNet
 encode (`xyzc_net`, latent_xyzc.py:166-274) stays on the reference path.  Attach the
-reference's own module as `net.xyzc_net` when spconv is installed, or hand the dense
-volumes in with `set_feature_volume()` (what the synthetic scenes do).
+reference's own module as `net.xyzc_net` when spconv is installed, hand the dense
+volumes in with `set_feature_volume()` (what the synthetic scenes do), or opt into the
+dense-PyTorch emulation with `attach_dense_encoder()` (f-2(ii), parity unpinned).
 
 The decoder arithmetic itself (`calculate_density_color`, :91-126) is not evaluated by
 PyTorch modules here: the Renderer packs these parameters and runs the fused CUDA kernel.
@@ -43,10 +44,22 @@ class Network(nn.Module):
         """Supply the four dense NCDHW fp32 volumes `encode_sparse_voxels` should return."""
         self._feature_volume = None if volumes is None else list(volumes)
 
+    def attach_dense_encoder(self):
+        """f-2(ii), opt-in: run the encode with the dense-PyTorch emulation of the reference's SparseConvNet
+        (lib/networks/sparse_encode.py; same parameter names, so `xyzc_net.*` of a reference checkpoint loads).  Parity
+        against spconv is unpinned (spconv is absent from this image) -- see that module's header."""
+        from neuralbody_b200.lib.networks.sparse_encode import DenseSparseConvNet
+        self.xyzc_net = DenseSparseConvNet().to(self.c.weight.device)
+        return self.xyzc_net
+
     def encode_sparse_voxels(self, sp_input):
         """latent_xyzc.py:30-39."""
         if self._feature_volume is not None:
             return self._feature_volume
+        if type(self.xyzc_net).__name__ == "DenseSparseConvNet":
+            coord = sp_input['coord']
+            code = self.c(torch.arange(0, 6890).to(coord.device))
+            return self.xyzc_net.encode(code, coord, sp_input['out_sh'], sp_input['batch_size'])
         if self.xyzc_net is None:
             raise RuntimeError(
                 "SparseConvNet encode is outside this package (it stays on the reference's spconv path): "
