@@ -6,13 +6,17 @@
 //                                raw = (0, 0, 0, min(sigma_empty, 0)) straight away.
 //   2. render_tc_list_kernel     the decoder MLP over the list, 128 list entries per tile: every tile except the last
 //                                one is FULL, where the fused kernel pads the last tile of each 1024-sample block
-//                                (75 % fill on the 512x512 benchmark view).  Same warp-specialised tcgen05 pipeline;
-//                                the smem that held the per-block lists buys a third layer-0 operand segment.
+//                                (86 % fill on the 512x512 benchmark view).  Same warp-specialised tcgen05 pipeline;
+//                                the smem that held the per-block lists buys a third layer-0 operand segment, the
+//                                uniform tiles let CTA pairs share the weight stream by TMA multicast again, and layer 4
+//                                accumulates into the idle lo plane so the next tile's layer 0 starts at once.  The
+//                                decoder does not care how many samples a ray has (up to 1024).
 //   3. composite_kernel          raw2outputs (nerf_net_utils.py:6-51), one warp per ray.
 //
 // Results are bit-identical to the fused kernels: a tile row is evaluated independently of its neighbours, so the
 // (non-deterministic) order of the blocks in the list does not reach any output.
-// The raw (rgb logits, sigma) records cross HBM once each way: 32 B per sample, ~0.5 GB per 512x512x64 frame.
+// The list and the raw (rgb logits, sigma) records cross HBM once each way: ~0.2 GB of DRAM traffic per decoder launch on
+// the 512x512x64 benchmark frame (measured, profiles/traffic_tc_fp16x3.json).
 #include "nb_tc_common.cuh"
 
 namespace nb {
