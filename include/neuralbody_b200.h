@@ -202,7 +202,8 @@ int nb_gen_rays(const nb_camera* cam, float* ray_o /* device (H*W,3) */, float* 
                 float* near /* device (H*W) */, float* far /* device (H*W) */, unsigned char* mask_at_box /* device (H*W) */,
                 void* stream);
 
-/* number of kernels nb_render_fwd enqueues per call for the given precision (for launch accounting) */
+/* number of kernels nb_render_fwd enqueues per call WITHOUT a workspace (the single fused launch: 1 for every precision).
+ * With nb_render_args.workspace and skip_empty / mask views it is 3 per frame (classify, decoder, composite) + one memset. */
 int nb_render_fwd_launches(int precision);
 
 /* ------------------------------------------------------------------------------------------
