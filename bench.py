@@ -182,7 +182,6 @@ def run_product(args, rank, world, local_rank):
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.raw_noise_std = S, 0.0, False, 0
     cfg.render_precision, cfg.render_volume_dtype, cfg.chunk = precision, "auto", 0
     cfg.render_skip_empty = not args.dense
-    cfg.render_compact_frame = not args.fused
     cfg.render_return_weights = False     # `weights` (B,n,S) is unused downstream; rgb/depth/acc/disp are written
     cfg.num_train_frame = int(scene["weights"]["latent.weight"].shape[0])
     net = make_network(cfg)
@@ -285,13 +284,13 @@ def run_product(args, rank, world, local_rank):
     kernel_launches = launches
     samples_per_launch = n_local * S
     skipping = precision != "fp32" and not args.dense
-    if skipping and stats[3] > 0:
+    if precision != "fp32" and stats[3] > 0:
         # frame-compacting pipeline: 3 launches per view (classify, decoder, composite).  The decoder kernel is the dominant
         # one; it times itself on the device (%globaltimer: first CTA start -> last CTA end, accumulated in stats[2])
         kernel_launches = stats[3]
         kernel_ms = stats[2] * 1e-6 / stats[3]
         kernel_ms_source = "%globaltimer, first CTA start to last CTA end of render_tc_list_kernel, mean over the timed launches"
-    if skipping and kernel_launches:
+    if precision != "fp32" and kernel_launches:
         # only EXECUTED work is credited: 128-row tiles the kernel actually ran (padding rows included), per launch
         samples_per_launch = stats[0] * 128 / kernel_launches
     if kernel_ms:
@@ -317,8 +316,7 @@ def run_product(args, rank, world, local_rank):
         "tensor_issued_frac_of_sustained": (tflops_exec * FLOP_PER_SAMPLE_ISSUED[precision] / FLOP_PER_SAMPLE_FOLDED)
                                            / peaks["tf_sustained"],
         "achieved_if_counted_as_written": tflops_written,
-        "kernel": ("%s<%d>" % ("render_tc_list_kernel" if stats[3] > 0 else "render_tc_sparse_kernel" if skipping else "render_tc_kernel",
-                               3 if precision == "tc_fp16x3" else 1)) if precision != "fp32"
+        "kernel": ("render_tc_list_kernel<%d>" % (3 if precision == "tc_fp16x3" else 1)) if precision != "fp32"
                   else "render_f32_kernel (fp32 FFMA pipe, no tensor cores)",
         "kernel_ms": kernel_ms, "kernel_ms_source": kernel_ms_source,
         "kernel_share_of_step": (kernel_ms * kernel_launches / total_ms) if kernel_ms else None,
@@ -364,7 +362,7 @@ def run_product(args, rank, world, local_rank):
         "frames_per_s_512x512": value / (H * W),
         "config": {"workload": "synth-313 512x512 all-hit view x %d per step, 64 samples/ray, eval, perturb=0 "
                                "(BASELINE configs[1])" % n_views,
-                   "precision": precision, "skip_empty": (precision != "fp32" and not args.dense), "pipeline": ("fused single kernel" if (args.fused or args.dense or precision == "fp32") else "classify -> decoder over the frame's compact sample list -> composite (3 launches per view)"), "rays_per_step": rays_per_step, "samples_per_ray": S,
+                   "precision": precision, "skip_empty": (precision != "fp32" and not args.dense), "pipeline": ("fused single kernel" if precision == "fp32" else "classify -> decoder over the frame's sample list -> composite (3 launches per view)"), "rays_per_step": rays_per_step, "samples_per_ray": S,
                    "parallelism": "ray-sharded x%d (interleaved 256-ray chunks), one all-gather per view" % world if world > 1 else "single GPU",
                    "l2": "256 MiB written between timed steps (untimed) to flush the 126 MB L2",
                    "volume": "fp16 channels-last 69 MB, packed once (cached across views of the frame)"
@@ -390,8 +388,6 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=4096, help="rays per step of the CPU arm / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dense", action="store_true", help="disable the exact empty-sample skipping of the tensor-core kernels")
-    ap.add_argument("--fused", action="store_true", help="single fused kernel (compaction per 1024-sample block) instead of the "
-                                                         "frame-compacting classify/decoder/composite pipeline")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(1, args.warmup)
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NB_ABI_VERSION 2
+#define NB_ABI_VERSION 3
 
 #define NB_OK               0
 #define NB_ERR_BAD_ARG     (-1)
@@ -132,20 +132,21 @@ typedef struct nb_render_args {
     const float* mask_Ks;            /* device (nv,3,3) */
     int   mask_nv, mask_H, mask_W;
     int   skip_empty;      /* tensor-core precisions: 1 = exact empty-sample skipping (samples whose trilinear cells are all
-                              unoccupied have weight exactly 0 when sigma(empty) < 0; their MLP evaluation is skipped) */
+                              unoccupied have weight exactly 0 when sigma(empty) < 0; their MLP evaluation is skipped and `raw`,
+                              if requested, holds (0, 0, 0, min(sigma_empty, 0)) for them instead of the decoder's rgb logits);
+                              0 = every sample goes through the decoder (same maps bit for bit) */
     unsigned long long* stats; /* device u64[4] or NULL: [0] += 128-sample tiles executed, [1] += occupied samples,
                                   [2] += ns spent in the decoder kernel (%globaltimer, first CTA start to last CTA end) and
-                                  [3] += decoder launches -- [2], [3] only with a workspace */
+                                  [3] += decoder launches (tensor-core precisions) */
     float* save;           /* device (B,n,S,1312) activation record for nb_render_bwd, or NULL (NB_PRECISION_FP32 only);
                               size from nb_render_save_bytes() */
     unsigned long long* trace; /* device, 4 x 4096 u64, or NULL: per-role (code<<48 | SM clock) timeline of CTA 0
                                   (tensor-core kernel only; diagnostics, see tools/trace_timeline.py) */
-    void*  workspace;      /* device scratch of nb_render_fwd_workspace_bytes() bytes, or NULL.  With it (tensor-core precisions,
-                              skip_empty or mask views) the occupied samples of a whole frame are compacted into one list and
-                              the decoder runs over full 128-sample tiles: 3 launches per frame (classify, decoder, composite)
-                              instead of the single fused kernel, same results bit for bit */
+    void*  workspace;      /* device scratch of nb_render_fwd_workspace_bytes() bytes; REQUIRED by the tensor-core precisions (NULL
+                              is fine for NB_PRECISION_FP32).  The samples of a frame that need the decoder (all of them with
+                              skip_empty = 0) are compacted into one list and the decoder runs over full 128-sample tiles:
+                              3 launches per frame (classify, decoder, composite) */
     size_t workspace_bytes;
-    int    trace_fused;    /* diagnostics: 1 = keep the single fused kernel even when a workspace is given */
     const float* z_vals;   /* device (B,n,S) or NULL.  When given, sample s of a ray sits at depth z_vals[b,r,s] (ascending) and
                               near / far / t_vals / t_rand are not read: the fine pass of hierarchical sampling (f-4; NeRF-style
                               volume_renderer.py:82-104 renders sorted(coarse z, importance z)).  Produced by nb_sample_pdf */
@@ -202,8 +203,8 @@ int nb_gen_rays(const nb_camera* cam, float* ray_o /* device (H*W,3) */, float* 
                 float* near /* device (H*W) */, float* far /* device (H*W) */, unsigned char* mask_at_box /* device (H*W) */,
                 void* stream);
 
-/* number of kernels nb_render_fwd enqueues per call WITHOUT a workspace (the single fused launch: 1 for every precision).
- * With nb_render_args.workspace and skip_empty / mask views it is 3 per frame (classify, decoder, composite) + one memset. */
+/* number of kernels nb_render_fwd enqueues per FRAME of a call: 1 for NB_PRECISION_FP32 (the single fused exact kernel),
+ * 3 for the tensor-core precisions (classify, decoder, composite; plus one 32-byte memset per call). */
 int nb_render_fwd_launches(int precision);
 
 /* ------------------------------------------------------------------------------------------

@@ -9,9 +9,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libneuralbody_b200.so")
-SOURCES = ["nb_capi.cu", "nb_render_f32.cu", "nb_render_tc.cu", "nb_render_tc_sparse.cu", "nb_render_tc_list.cu", "nb_tc_probe.cu", "nb_render_bwd.cu", "nb_sample_pdf.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC"]
+SOURCES = ["nb_capi.cu", "nb_render_f32.cu", "nb_render_tc_list.cu", "nb_tc_probe.cu", "nb_render_bwd.cu", "nb_sample_pdf.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def find_nvcc():
@@ -31,14 +31,27 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source of the package for sm_100a into one shared library."""
+    """Compile every CUDA source of the package for sm_100a (one nvcc per file, in parallel) and link one shared library."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+    nvcc = find_nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        done = list(ex.map(compile_one, SOURCES))
     if verbose:
-        print(res.stderr)
+        for _, log in done:
+            print(log)
+    res = subprocess.run([nvcc, "--shared", "-o", LIB_PATH] + [o for o, _ in done], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH

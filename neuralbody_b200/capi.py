@@ -50,7 +50,7 @@ class nb_render_args(C.Structure):
         ("depth_map", C.c_void_p), ("raw", C.c_void_p),
         ("mask_msks", C.c_void_p), ("mask_RT", C.c_void_p), ("mask_Ks", C.c_void_p),
         ("mask_nv", C.c_int), ("mask_H", C.c_int), ("mask_W", C.c_int), ("skip_empty", C.c_int), ("stats", C.c_void_p), ("save", C.c_void_p),
-        ("trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("trace_fused", C.c_int), ("z_vals", C.c_void_p),
+        ("trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("z_vals", C.c_void_p),
     ]
 
 
@@ -117,7 +117,7 @@ def load(path=None):
     lib.nb_sample_pdf.argtypes = [C.POINTER(nb_importance_args), C.c_void_p]
     lib.nb_debug_tc_probe.restype = C.c_int
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
-    if lib.nb_abi_version() != 2:
+    if lib.nb_abi_version() != 3:
         raise RuntimeError("libneuralbody_b200.so ABI version mismatch")
     if path in (_build.LIB_PATH, os.environ.get("NB_LIB_PATH")):
         _lib = lib

@@ -410,7 +410,7 @@ int nb_pack_weights(const nb_decoder_weights* w, void* out_blob, size_t out_byte
     return NB_OK;
 }
 
-int nb_render_fwd_launches(int precision) { (void)precision; return 1; }
+int nb_render_fwd_launches(int precision) { return precision == NB_PRECISION_FP32 ? 1 : 3; }
 
 size_t nb_render_fwd_workspace_bytes(int batch, int n_rays, int n_samples) {
     if (batch <= 0 || n_rays <= 0 || n_samples <= 0) return 0;
@@ -457,6 +457,7 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
     p.bc = (const float*)(wb + kBcByteOffset);
     p.wframe = (const __half*)(wb + frame_step_byte_offset(a->batch));
     p.white_bkgd = a->white_bkgd;
+    p.skip_empty = a->skip_empty ? 1 : 0;
     p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace; p.save = a->save; p.stats = a->stats;
     p.mask_msks = a->mask_msks; p.mask_RT = a->mask_RT; p.mask_Ks = a->mask_Ks;
     p.mask_nv = a->mask_msks ? a->mask_nv : 0; p.mask_H = a->mask_H; p.mask_W = a->mask_W;
@@ -512,13 +513,9 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     if (a->precision == NB_PRECISION_FP32) return launch_render_f32(p, a->volume_dtype, st);
     if (a->precision == NB_PRECISION_TC_FP16 || a->precision == NB_PRECISION_TC_FP16X3) {
         const int passes = a->precision == NB_PRECISION_TC_FP16X3 ? 3 : 1;
-        // mask views are a per-sample predicate: they live in the sample classifier of the sparse kernel
-        if (!(a->skip_empty || a->mask_msks)) return launch_render_tc(p, a->volume_dtype, passes, st);
-        // with a workspace the samples are compacted across the whole frame (classify -> decoder over full tiles -> composite);
-        // without one the single fused kernel compacts inside each 1024-sample block
-        if (a->workspace && !a->trace_fused && render_tc_list_supported(p))
-            return launch_render_tc_list(p, a->volume_dtype, passes, a->workspace, a->workspace_bytes, st);
-        return launch_render_tc_sparse(p, a->volume_dtype, passes, st);
+        // one pipeline for every tensor-core call: classify (+ mask views) -> decoder over the frame's sample list -> composite;
+        // skip_empty = 0 lists every sample (dense evaluation), bit-identical to the skipping run
+        return launch_render_tc_list(p, a->volume_dtype, passes, a->workspace, a->workspace_bytes, st);
     }
     set_error("nb_render_fwd: unknown precision %d", a->precision);
     return NB_ERR_BAD_ARG;

@@ -30,12 +30,13 @@ struct RenderParams {
     const __half* wframe;      // per-frame L3 step [B][144*16]
     const float* bc;           // [B][128]
     int white_bkgd;
+    int skip_empty;            // tensor-core path: 1 = samples with all-zero features and sigma(empty) < 0 are not evaluated
     float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *raw;
     unsigned long long* trace;
     const unsigned char* mask_msks; const float* mask_RT; const float* mask_Ks;   // f-1 mask views (null = none)
     int mask_nv, mask_H, mask_W;
-    unsigned long long* stats; // u64[4] or null: [0] += tiles executed, [1] += occupied samples (sparse / list kernels),
-                               // [2] += decoder-kernel ns, [3] += decoder launches (list pipeline)
+    unsigned long long* stats; // u64[4] or null: [0] += tiles executed, [1] += listed samples,
+                               // [2] += decoder-kernel ns, [3] += decoder launches
     float* save;               // (B,n,S,kSaveDim) activation record for nb_render_bwd (exact kernel only) or null
     int rays_per_group;        // rays handled together by one CTA work item
     int tiles_per_group;       // point tiles per group
@@ -50,8 +51,6 @@ struct RenderParams {
 };
 
 int launch_render_f32(const RenderParams& p, int volume_dtype, cudaStream_t stream);
-int launch_render_tc(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
-int launch_render_tc_sparse(const RenderParams& p, int volume_dtype, int passes, cudaStream_t stream);
 int launch_render_tc_list(const RenderParams& p, int volume_dtype, int passes, void* workspace, size_t workspace_bytes, cudaStream_t stream);
 size_t render_tc_list_workspace_bytes(int batch, int n_rays, int n_samples);
 bool render_tc_list_supported(const RenderParams& p);

@@ -1,22 +1,29 @@
-// Tensor-core render as a three-launch pipeline over a COMPACT SAMPLE LIST (needs nb_render_args.workspace):
+// The tensor-core render path: three launches over a frame's COMPACT SAMPLE LIST (nb_render_args.workspace).
 //
-//   1. classify_compact_kernel   every sample of the frame is classified with the cell-occupancy bitmaps (exactly as the
-//                                fused sparse kernel does, nb_render_tc_sparse.cu); occupied samples are appended to a
-//                                global list (one atomicAdd per 1024-sample block), the others get their constant
-//                                raw = (0, 0, 0, min(sigma_empty, 0)) straight away.
-//   2. render_tc_list_kernel     the decoder MLP over the list, 128 list entries per tile: every tile except the last
-//                                one is FULL, where the fused kernel pads the last tile of each 1024-sample block
-//                                (86 % fill on the 512x512 benchmark view).  Same warp-specialised tcgen05 pipeline;
-//                                the smem that held the per-block lists buys a third layer-0 operand segment, the
-//                                uniform tiles let CTA pairs share the weight stream by TMA multicast again, and layer 4
-//                                accumulates into the idle lo plane so the next tile's layer 0 starts at once.  The
-//                                decoder does not care how many samples a ray has (up to 1024).
+//   1. classify_compact_kernel   every sample of the frame is classified with the four cell-occupancy bitmaps; occupied
+//                                samples are appended to the frame's list (one atomicAdd per 1024-sample block), the others
+//                                get their constant raw record (0, 0, 0, min(sigma_empty, 0)) at once.  With
+//                                skip_empty = 0 every sample is listed (dense evaluation through the same decoder).
+//   2. render_tc_list_kernel     the decoder MLP (latent_xyzc.py:91-126) over the list, 128 entries per tile, as a
+//                                warp-specialised tcgen05 pipeline (roles below).
 //   3. composite_kernel          raw2outputs (nerf_net_utils.py:6-51), one warp per ray.
 //
-// Results are bit-identical to the fused kernels: a tile row is evaluated independently of its neighbours, so the
-// (non-deterministic) order of the blocks in the list does not reach any output.
-// The list and the raw (rgb logits, sigma) records cross HBM once each way: ~0.2 GB of DRAM traffic per decoder launch on
-// the 512x512x64 benchmark frame (measured, profiles/traffic_tc_fp16x3.json).
+// Decoder pipeline, one persistent CTA per SM, CTA pairs share the weight stream by TMA multicast:
+//   warps  0..15  producers   trilinear gather of the 352 features into a ring of 64-channel layer-0 operand segments
+//   warps 16..19  epilogue    TMEM accumulator -> relu -> (hi, lo) fp16 operand of the next layer, IN PLACE (see below)
+//   warp  20      MMA issuer  one thread issues every tcgen05.mma
+//   warp  21      loader      one thread streams the pre-packed weights through a 3-slot shared-memory ring
+// (the warp scheduler favours high warp ids, so the latency-critical roles sit above the 16 throughput warps).
+//
+// TMEM (512 columns) is two 256-column regions R0 | R1 that swap roles every layer: layer l accumulates into one region
+// while its A operand (the previous layer's activations) is read from the other.  The epilogue converts an accumulator
+// in place -- the 16 fp32 columns of K-step k become 8 columns of fp16 hi pairs + 8 columns of fp16 lo pairs -- and
+// signals every 64 columns, so the issuer starts layer l+1 on the first converted quarter while the epilogue is still
+// converting the rest: conversion and MMA overlap instead of alternating.  Layer 4 (the 3-wide rgb head) of tile t is
+// issued after the first layer-0 segment of tile t+1, which fills the bubble of its short epilogue.
+//
+// Results do not depend on the (non-deterministic) order of the blocks in the list: a tile row is evaluated
+// independently of its neighbours.  The list and the raw (rgb logits, sigma) records cross HBM once each way.
 #include "nb_tc_common.cuh"
 
 namespace nb {
@@ -24,8 +31,6 @@ namespace tcl {
 
 using tcr::Quad;
 using tcr::Tracer;
-using tcr::named_bar_sync;
-using tcr::f16lo_of;
 
 constexpr int TP = 128;
 constexpr int NUM_SLOTS = 3;
@@ -41,9 +46,8 @@ constexpr int SEG_CHUNK_STRIDE = CHUNK_BYTES + 32;
 constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * SEG_CHUNK_STRIDE;  // 97.5 KB: 3 x (hi+lo) or 6 x hi
 constexpr int MAX_SEG_BUFS = 6;
 constexpr int PE_CHUNKS = 12;
-constexpr int EPI_WARPS = 4, MMA_WARP = 4, LOAD_WARP = 5, PROD_WARP0 = 6, PROD_WARPS = 16;
-constexpr int NT = (PROD_WARP0 + PROD_WARPS) * 32;               // 704
-constexpr int PROD_THREADS = PROD_WARPS * 32;                     // 512
+constexpr int PROD_WARPS = 16, EPI_WARP0 = 16, EPI_WARPS = 4, MMA_WARP = 20, LOAD_WARP = 21;
+constexpr int NT = (LOAD_WARP + 1) * 32;                          // 704
 constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);
 constexpr int MAXS = 1024;                                         // samples per classification block
 #ifndef NB_LIST_CLUSTER
@@ -51,30 +55,28 @@ constexpr int MAXS = 1024;                                         // samples pe
 #endif
 constexpr int CLUSTER = NB_LIST_CLUSTER;       // CTAs that share one weight stream through TMA multicast (all tiles cost the same)
 constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry .w = frame sample id | level bits << 28
+constexpr int L4_BYTES = kStepsL4 * (int)kStepHalves4 * 2;         // the rgb head's 9 N=16 steps stay resident (4.5 KB)
 
 // shared-memory map (bytes)
 constexpr int OFF_SEG = 0;
 constexpr int OFF_ONES = OFF_SEG + SEG_RING_BYTES;
 constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;
 constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;
-constexpr int OFF_XF = OFF_RING + NUM_SLOTS * SLOT_BYTES;          // FrameXf
-constexpr int OFF_INFO = OFF_XF + 128;                             // TileInfo[2]
-constexpr int OFF_BAR = OFF_INFO + 64;
+constexpr int OFF_L4 = OFF_RING + NUM_SLOTS * SLOT_BYTES;
+constexpr int OFF_XF = OFF_L4 + L4_BYTES;                          // FrameXf
+constexpr int OFF_BAR = OFF_XF + 128;
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + MAX_SEG_BUFS,
-       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_RGB_FULL, BAR_H_READY, BAR_MSG_FULL, BAR_MSG_FREE, NUM_BARS };
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_RGB_FULL, BAR_L4W_FULL, BAR_H_READY /* x4: one per 64 columns */,
+       NUM_BARS = BAR_H_READY + 4 };
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(OFF_L4 % 128 == 0 && OFF_RING % 128 == 0 && OFF_PE % 128 == 0, "operand alignment");
 
-constexpr uint32_t TM_ACC = 0, TM_HI = 256, TM_LO = 384;
-constexpr uint32_t TM_RGB = TM_LO;      // layer 4 accumulates into the (then idle) lo plane, so ACC is free for the next tile's layer 0
-
-struct TileInfo {
-    int nrows;       // list entries in this tile
-    int tile;        // tile index: rows [tile * 128, tile * 128 + nrows) of the list
-    int flags;       // bit2 done (no more work)
-    int pad;
-};
+// TMEM: two 256-column regions; K-step k of an activation operand occupies columns [16k, 16k+8) (hi) and [16k+8, 16k+16) (lo)
+constexpr uint32_t TM_R0 = 0, TM_R1 = 256;
+constexpr uint32_t TM_SIGMA = TM_R1 + 128;     // layer-3 accumulator columns 128..143: alpha_fc hi / lo rows
+constexpr uint32_t TM_RGB = TM_R1 + 192;       // layer-4 accumulator (16 columns), beyond layer 3's 144
 
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -109,7 +111,8 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
     load_frame_xf(P, &xf, tid);
     __syncthreads();
     const float sigma_empty = __ldg(P.wf32 + oSigmaEmpty);
-    const bool can_skip = sigma_empty < -1e-3f;      // robustly negative => empty samples have weight exactly 0
+    // robustly negative sigma on all-zero features => such a sample has compositing weight exactly 0 and is not evaluated
+    const bool can_skip = P.skip_empty && sigma_empty < -1e-3f;
     const uint32_t* occ_base = reinterpret_cast<const uint32_t*>(P.volume);
 
     float4 gm[CLS_PER_THREAD];
@@ -177,7 +180,6 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-    volatile TileInfo* info = reinterpret_cast<volatile TileInfo*>(smem + OFF_INFO);
     FrameXf* xf = reinterpret_cast<FrameXf*>(smem + OFF_XF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = P.n_samples;
@@ -190,19 +192,17 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
         tc::mbar_init(&bars[BAR_RGB_FULL], 1);
-        tc::mbar_init(&bars[BAR_H_READY], EPI_WARPS * 32);
-        tc::mbar_init(&bars[BAR_MSG_FULL], PROD_WARPS);
-        tc::mbar_init(&bars[BAR_MSG_FREE], EPI_WARPS * 32 + 2);       // epilogue threads + MMA thread + loader thread
+        tc::mbar_init(&bars[BAR_L4W_FULL], 1);
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[BAR_H_READY + i], EPI_WARPS * 32);
         tc::fence_mbar_init();
     }
-    if (warp >= PROD_WARP0) {
-        const int pt = tid - PROD_WARP0 * 32;
-        if (pt < TP) {
+    if (warp < PROD_WARPS) {
+        if (tid < TP) {
             unsigned char* o = smem + OFF_ONES;
-            *reinterpret_cast<uint4*>(o + (pt >> 3) * 128 + (pt & 7) * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(o + CHUNK_BYTES + (pt >> 3) * 128 + (pt & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(o + (tid >> 3) * 128 + (tid & 7) * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(o + CHUNK_BYTES + (tid >> 3) * 128 + (tid & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        load_frame_xf(P, xf, pt);
+        load_frame_xf(P, xf, tid);
         tc::fence_proxy_async();
     }
     tc::tc_fence_before();
@@ -215,35 +215,26 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     if (tid == 0 && P.stats) atomicMax(P.frame_clock + 0, ~global_ns());     // min(start) over the CTAs, as max(~start)
     const unsigned int n_rows_total = *P.list_count;                  // written by classify_compact_kernel (previous launch)
     const int n_tiles = (int)((n_rows_total + TP - 1) / TP);
+    // a cluster walks the tiles in lockstep (shared weight stream): CTA r of cluster c takes tile c * CLUSTER + r of every
+    // round; a tile past the end is an empty one (nrows = 0) that keeps the peer's stream going.  Every role derives the
+    // same static schedule from the list length.
+    const int tile0 = (int)(blockIdx.x / CLUSTER) * CLUSTER;
+    auto rows_of = [&](int tile) { return tile < n_tiles ? min(TP, (int)(n_rows_total - (unsigned int)tile * TP)) : 0; };
 
     // ================================================================== PRODUCERS
-    if (warp >= PROD_WARP0) {
-        const int pt = tid - PROD_WARP0 * 32;
-        const int pw = warp - PROD_WARP0;
+    if (warp < PROD_WARPS) {
         const unsigned char* volbase = reinterpret_cast<const unsigned char*>(P.volume);
-        const int grp = pw * 4 + (lane >> 3);
+        const int grp = warp * 4 + (lane >> 3);
         const int t = lane & 7;
-        uint32_t msg = 0, it = 0;                      // messages sent, tiles sent
+        uint32_t it = 0;
         Tracer tr;
-        tr.init((pw == 0 && lane == 0) ? P.trace : nullptr, 0);
-        auto publish = [&](int nrows, int tile, int flags) {
-            tc::mbar_wait(&bars[BAR_MSG_FREE], (msg & 1) ^ 1);        // everybody has read the previous message
-            if (pt == 0) {
-                volatile TileInfo* ti = &info[msg & 1];
-                ti->nrows = nrows; ti->tile = tile; ti->flags = flags;
-            }
-            named_bar_sync(1, PROD_THREADS);
-            if (lane == 0) tc::mbar_arrive(&bars[BAR_MSG_FULL]);
-            ++msg;
-        };
+        tr.init((warp == 0 && lane == 0) ? P.trace : nullptr, 0);
         const uint32_t seg_base = tc::smem_u32(smem + OFF_SEG);
         const uint32_t so0 = (uint32_t)((t >> 1) * SEG_CHUNK_STRIDE + (grp >> 3) * 128 + (grp & 7) * 16 + (t & 1) * 8);
-        // a cluster walks the tiles in lockstep (shared weight stream): CTA r of cluster c takes tile c * CLUSTER + r of every
-        // round; a tile past the end is an empty one (nrows = 0) that keeps the peer's stream going
         uint32_t real_tiles = 0;
-        for (int tbase = (blockIdx.x / CLUSTER) * CLUSTER; tbase < n_tiles; tbase += gridDim.x) {
+        for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
             const int tile = tbase + (int)crank;
-            const int nrows = tile < n_tiles ? min(TP, (int)(n_rows_total - (unsigned int)tile * TP)) : 0;
+            const int nrows = rows_of(tile);
             real_tiles += nrows > 0;
             // the list entries of this thread's rows: grid coordinates + per-level occupancy bits
             float4 g[PTS_PER_GROUP];
@@ -257,8 +248,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     g[pp].w = __int_as_float((int)(__float_as_uint(e.w) >> 28));
                 }
             }
-            publish(nrows, tile, 0);
-            tr.ev(1);                                   // tile published
+            tr.ev(1);                                   // tile begin
             uint32_t coff[PTS_PER_GROUP][8];
             float cw[PTS_PER_GROUP][8];
             bool occupied[PTS_PER_GROUP];
@@ -315,15 +305,21 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                             for (int c = 0; c < 8; ++c)
                                 if (cw[pp][c] != 0.f) Quad<VT>::fma(a, v[c], cw[pp][c]);
                         }
-                        uint2 hi;
-                        hi.x = tc::cvt_f16x2(a[0], a[1]); hi.y = tc::cvt_f16x2(a[2], a[3]);
                         const uint32_t so = dst + (uint32_t)(uu * 4 * SEG_CHUNK_STRIDE + pp * 8 * 128);   // K-major core-matrix layout
-                        tcr::sts_v2(so, hi);
                         if (NP == 3) {
-                            uint2 lo;
-                            lo.x = tc::cvt_f16x2(f16lo_of(a[0], hi.x, 0), f16lo_of(a[1], hi.x, 1));
-                            lo.y = tc::cvt_f16x2(f16lo_of(a[2], hi.y, 0), f16lo_of(a[3], hi.y, 1));
+                            // (hi, lo) split with a truncated hi: the residual is exact and costs one LOP3 + half an FADD2 a value
+                            uint2 hi, lo;
+                            hi.x = tc::cvt_rz_f16x2(a[0], a[1]); hi.y = tc::cvt_rz_f16x2(a[2], a[3]);
+                            float r0, r1, r2, r3;
+                            tc::trunc_residual2(a[0], a[1], r0, r1);
+                            tc::trunc_residual2(a[2], a[3], r2, r3);
+                            lo.x = tc::cvt_f16x2(r0, r1); lo.y = tc::cvt_f16x2(r2, r3);
+                            tcr::sts_v2(so, hi);
                             tcr::sts_v2(so + SEG_CHUNKS * SEG_CHUNK_STRIDE, lo);
+                        } else {
+                            uint2 hi;
+                            hi.x = tc::cvt_f16x2(a[0], a[1]); hi.y = tc::cvt_f16x2(a[2], a[3]);
+                            tcr::sts_v2(so, hi);
                         }
                     }
                 }
@@ -334,8 +330,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             }
             ++it;
         }
-        publish(0, 0, 4);                               // done
-        if (pt == 0 && P.stats) {
+        if (tid == 0 && P.stats) {
             atomicAdd(P.stats + 0, (unsigned long long)real_tiles);
             if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)n_rows_total);
         }
@@ -343,8 +338,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     // ================================================================== LOADER
     else if (warp == LOAD_WARP) {
         if (lane == 0) {
-            uint32_t cnt = 0, msg = 0;
+            uint32_t cnt = 0;
             const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
+            // the rgb head's weights stay resident: one plain bulk copy per CTA
+            tc::mbar_arrive_expect_tx(&bars[BAR_L4W_FULL], L4_BYTES);
+            tc::bulk_g2s(smem + OFF_L4, seq + sL4 * 2, L4_BYTES, &bars[BAR_L4W_FULL]);
             auto push = [&](const unsigned char* src, uint32_t bytes, const unsigned char* src2 = nullptr, uint32_t bytes2 = 0) {
                 const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
                 unsigned char* dst = smem + OFF_RING + slot * SLOT_BYTES;
@@ -359,12 +357,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 }
                 ++cnt;
             };
-            for (;;) {
-                tc::mbar_wait(&bars[BAR_MSG_FULL], msg & 1);
-                const int flags = info[msg & 1].flags;
-                tc::mbar_arrive(&bars[BAR_MSG_FREE]);
-                ++msg;
-                if (flags & 4) break;
+            for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
                 for (int layer = 0; layer < 3; ++layer) {
                     const int nks = layer == 0 ? kKsL0 : kKsL12;
                     const unsigned char* base = seq + 2 * (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
@@ -375,22 +368,20 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     }
                     push(base + 2 * bias256_offset(nks), STEP_BYTES);
                 }
-                {
-                    const uint32_t sb = kStepHalves3 * 2;
-                    const unsigned char* l3 = seq + sL3 * 2;
-                    for (int g0 = 0; g0 < 20; g0 += 4) push(l3 + (size_t)g0 * sb, 4 * sb);
-                    push(l3 + (size_t)20 * sb, sb, reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb, sb);
-                }
-                push(seq + sL4 * 2, kStepsL4 * kStepHalves4 * 2);
+                const uint32_t sb = kStepHalves3 * 2;
+                const unsigned char* l3 = seq + sL3 * 2;
+                for (int g0 = 0; g0 < 20; g0 += 4) push(l3 + (size_t)g0 * sb, 4 * sb);
+                push(l3 + (size_t)20 * sb, sb, reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb, sb);
             }
         }
     }
     // ================================================================== MMA ISSUER
     else if (warp == MMA_WARP) {
         if (lane == 0) {
-            uint32_t cnt = 0, hcnt = 0, msg = 0, it = 0;
+            uint32_t cnt = 0, hphase = 0, it = 0;
             const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
             const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
+            const uint32_t l4_addr = tc::smem_u32(smem + OFF_L4);
             constexpr uint32_t ID256 = tc::make_idesc_f16(128, 256), ID3 = tc::make_idesc_f16(128, kN3),
                                ID4 = tc::make_idesc_f16(128, kN4);
             auto wait_slot = [&](uint32_t& slot) {
@@ -411,19 +402,59 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             auto b_desc_rows = [&](uint32_t slot, int i, int N, int row0) {     // rows row0.. of step i (8-row groups are 128 B apart)
                 return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32 + row0 * 16, N * 16, 128);
             };
-            auto wait_h = [&]() { tc::mbar_wait(&bars[BAR_H_READY], hcnt & 1); ++hcnt; tc::tc_fence_after(); };
+            // the epilogue has converted columns [64 g, 64 g + 64) of the current activation region (K-steps 4g..4g+3)
+            auto wait_h = [&](int g) {
+                tc::mbar_wait(&bars[BAR_H_READY + g], (hphase >> g) & 1);
+                hphase ^= 1u << g;
+                tc::tc_fence_after();
+            };
             Tracer tr;
             tr.init(P.trace, 1);
-            for (;;) {
-                tc::mbar_wait(&bars[BAR_MSG_FULL], msg & 1);
-                const int flags = info[msg & 1].flags;
-                tc::mbar_arrive(&bars[BAR_MSG_FREE]);
-                ++msg;
-                if (flags & 4) break;
+            // layer 4 of the tile whose layer 3 was issued last: A = relu(colour hidden) in R1 (hi only), B resident
+            auto issue_l4 = [&]() {
+                wait_h(0);
+                wait_h(1);
+                tr.ev(34);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    tc::mma_ts(tmem + TM_RGB, tmem + TM_R1 + 16 * ks, tc::make_smem_desc(l4_addr + ks * kN4 * 32, kN4 * 16, 128), ID4, ks > 0);
+                tc::mma_ss(tmem + TM_RGB, a_desc(ones_addr, 0), tc::make_smem_desc(l4_addr + 8 * kN4 * 32, kN4 * 16, 128), ID4, true);
+                tc::mma_commit(&bars[BAR_RGB_FULL]);
+            };
+            // a 256 -> 256 layer: A = activations in region `rin` (TMEM), accumulator = region `rout`
+            auto layer256 = [&](uint32_t rin, uint32_t rout, int code) {
                 uint32_t slot;
-                // no wait here: the previous tile's layer 4 wrote TM_RGB, and its layer-3 accumulator was read before layer 4
-                // was issued (h_ready #4), so ACC is already free while the epilogue still reads the previous rgb columns
+                for (int g = 0; g < 4; ++g) {
+                    wait_h(g);
+                    if (g == 0) tr.ev(30 + code);
+                    wait_slot(slot);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t a = tmem + rin + 16 * (4 * g + i);
+                        tc::mma_ts(tmem + rout, a, b_desc(slot, i, 256), ID256, (g | i) != 0);
+                        if (NP == 3) tc::mma_ts(tmem + rout, a + 8, b_desc(slot, i, 256), ID256, true);
+                    }
+                    release_slot(slot);
+                    if (NP == 3) {
+                        wait_slot(slot);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            tc::mma_ts(tmem + rout, tmem + rin + 16 * (4 * g + i), b_desc(slot, i, 256), ID256, true);
+                        release_slot(slot);
+                    }
+                }
+                wait_slot(slot);
+                tc::mma_ss(tmem + rout, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
+                release_slot(slot);
+                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tr.ev(20 + code);
+            };
+            tc::mbar_wait(&bars[BAR_L4W_FULL], 0);
+            for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
+                uint32_t slot;
                 tr.ev(1);
+                // ---- layer 0: A = gathered feature segments (shared memory), accumulator R0.  R0 held the previous tile's h2,
+                // whose last reader (its layer 3) was issued before: the tensor pipe executes in issue order.
                 for (int seg = 0; seg < NUM_SEGS; ++seg) {
                     const uint32_t gseg = it * NUM_SEGS + seg;
                     const uint32_t buf = gseg % NUM_SEG_BUFS;
@@ -434,122 +465,114 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
                     wait_slot(slot);
                     for (int ks = 0; ks < nks; ++ks) {
-                        tc::mma_ss(tmem + TM_ACC, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, (seg | ks) != 0);
-                        if (NP == 3) tc::mma_ss(tmem + TM_ACC, a_seg(lo_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                        tc::mma_ss(tmem + TM_R0, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, (seg | ks) != 0);
+                        if (NP == 3) tc::mma_ss(tmem + TM_R0, a_seg(lo_addr, ks), b_desc(slot, ks, 256), ID256, true);
                     }
                     release_slot(slot);
                     if (NP == 3) {
                         wait_slot(slot);
                         for (int ks = 0; ks < nks; ++ks)
-                            tc::mma_ss(tmem + TM_ACC, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                            tc::mma_ss(tmem + TM_R0, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, true);
                         release_slot(slot);
                     }
                     tc::mma_commit(&bars[BAR_SEG_EMPTY + buf]);
+                    // the previous tile's rgb head, once its layer-3 epilogue is through (it ran under the MMAs above)
+                    if (seg == 0 && it > 0) issue_l4();
                 }
                 wait_slot(slot);
-                tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
+                tc::mma_ss(tmem + TM_R0, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
                 tr.ev(20);
-                for (int layer = 1; layer <= 2; ++layer) {
-                    wait_h();
-                    tr.ev(30 + layer);
-                    for (int g0 = 0; g0 < 16; g0 += 4) {
-                        wait_slot(slot);
-                        for (int i = 0; i < 4; ++i) {
-                            tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, 256), ID256, (g0 | i) != 0);
-                            if (NP == 3) tc::mma_ts(tmem + TM_ACC, tmem + TM_LO + (g0 + i) * 8, b_desc(slot, i, 256), ID256, true);
-                        }
-                        release_slot(slot);
-                        if (NP == 3) {
-                            wait_slot(slot);
-                            for (int i = 0; i < 4; ++i)
-                                tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, 256), ID256, true);
-                            release_slot(slot);
-                        }
-                    }
+                layer256(TM_R0, TM_R1, 1);       // layer 1: h0 (R0) -> R1
+                layer256(TM_R1, TM_R0, 2);       // layer 2: h1 (R1) -> R0
+                // ---- layer 3: A = h2 (R0); accumulator R1[0..143]: 128 colour columns + alpha_fc hi / lo rows
+                for (int g = 0; g < 4; ++g) {
+                    wait_h(g);
+                    if (g == 0) tr.ev(33);
                     wait_slot(slot);
-                    tc::mma_ss(tmem + TM_ACC, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
-                    release_slot(slot);
-                    tc::mma_commit(&bars[BAR_ACC_FULL]);
-                    tr.ev(20 + layer);
-                }
-                wait_h();
-                tr.ev(33);
-                for (int g0 = 0; g0 < 16; g0 += 4) {
-                    wait_slot(slot);
+#pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        tc::mma_ts(tmem + TM_ACC, tmem + TM_HI + (g0 + i) * 8, b_desc(slot, i, kN3), ID3, (g0 | i) != 0);
+                        const uint32_t a = tmem + TM_R0 + 16 * (4 * g + i);
+                        tc::mma_ts(tmem + TM_R1, a, b_desc(slot, i, kN3), ID3, (g | i) != 0);
                         // the lo half of the activations only matters on the density path: rows 128..143 of the step (alpha_fc
                         // hi / lo + padding) -> accumulator columns 128..143; the 128 colour columns take the hi half alone
-                        if (NP == 3) tc::mma_ts(tmem + TM_ACC + 128, tmem + TM_LO + (g0 + i) * 8, b_desc_rows(slot, i, kN3, 128), ID4, true);
+                        if (NP == 3) tc::mma_ts(tmem + TM_SIGMA, a + 8, b_desc_rows(slot, i, kN3, 128), ID4, true);
                     }
                     release_slot(slot);
                 }
                 wait_slot(slot);
-                for (int i = 0; i < 4; ++i) tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, i), b_desc(slot, i, kN3), ID3, true);
+                for (int i = 0; i < 4; ++i) tc::mma_ss(tmem + TM_R1, a_desc(pe_addr, i), b_desc(slot, i, kN3), ID3, true);
                 release_slot(slot);
                 wait_slot(slot);
-                for (int i = 0; i < 2; ++i) tc::mma_ss(tmem + TM_ACC, a_desc(pe_addr, 4 + i), b_desc(slot, i, kN3), ID3, true);
+                for (int i = 0; i < 2; ++i) tc::mma_ss(tmem + TM_R1, a_desc(pe_addr, 4 + i), b_desc(slot, i, kN3), ID3, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
                 tr.ev(23);
-                wait_h();
-                tr.ev(34);
-                wait_slot(slot);
-                for (int ks = 0; ks < 8; ++ks)
-                    tc::mma_ts(tmem + TM_RGB, tmem + TM_HI + ks * 8, b_desc(slot, ks, kN4), ID4, ks > 0);
-                tc::mma_ss(tmem + TM_RGB, a_desc(ones_addr, 0), b_desc(slot, 8, kN4), ID4, true);
-                release_slot(slot);
-                tc::mma_commit(&bars[BAR_RGB_FULL]);
                 ++it;
             }
+            if (it > 0) issue_l4();
         }
     }
     // ================================================================== EPILOGUE (thread = tile row)
     else {
-        const int row = tid;
-        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const int row = tid - EPI_WARP0 * 32;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         unsigned char* PE = smem + OFF_PE;
-        uint32_t acnt = 0, rcnt = 0, msg = 0;
+        uint32_t acnt = 0, rcnt = 0;
+        Tracer tr;
+        tr.init(row == 0 ? P.trace : nullptr, 2);
         auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
-        auto relu_to_h = [&](int ncols, bool with_lo) {
-            const int ng = ncols / 8;
-            uint32_t va[8], vb[8];
-            auto convert_store = [&](const uint32_t (&v)[8], int c) {
-                uint32_t h[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-                tc::tmem_st4(lane_base + TM_HI + c * 4, h);
+        // accumulator region `reg` -> relu -> fp16 operand of the next layer, in place: the 16 fp32 columns of K-step k become
+        // 8 columns of hi pairs [16k, 16k+8) and (3-pass mode, with_lo) 8 columns of lo pairs [16k+8, 16k+16).  H_READY[g]
+        // is signalled after every 4 K-steps, so the issuer can start the next layer on the first converted quarter.
+        auto convert_region = [&](uint32_t reg, int nblocks, bool with_lo) {
+            uint32_t va[16], vb[16];
+            const uint32_t base = lane_base + reg;
+            auto convert_store = [&](const uint32_t (&v)[16], int k) {
+                uint32_t h[8];
                 if (NP == 3 && with_lo) {
-                    uint32_t l[4];
+                    uint32_t l[8];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        l[i] = tc::cvt_f16x2(f16lo_of(fmaxf(__uint_as_float(v[2 * i]), 0.f), h[i], 0),
-                                             f16lo_of(fmaxf(__uint_as_float(v[2 * i + 1]), 0.f), h[i], 1));
-                    tc::tmem_st4(lane_base + TM_LO + c * 4, l);
+                    for (int i = 0; i < 8; ++i) {
+                        const float x0 = __uint_as_float(v[2 * i]), x1 = __uint_as_float(v[2 * i + 1]);
+                        h[i] = tc::cvt_rz_relu_f16x2(x0, x1);
+                        float r0, r1;
+                        tc::trunc_residual2(x0, x1, r0, r1);
+                        l[i] = tc::cvt_relu_f16x2(r0, r1);      // negative x: hi = 0 and the (negative) residual clamps to 0
+                    }
+                    tc::tmem_st8(base + 16 * k, h);
+                    tc::tmem_st8(base + 16 * k + 8, l);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                    tc::tmem_st8(base + 16 * k, h);
                 }
             };
-            tc::tmem_ld8(lane_base + TM_ACC, va);
-            tc::tmem_ld_wait();
-            for (int c = 0; c < ng; c += 2) {
-                tc::tmem_ld8(lane_base + TM_ACC + (c + 1) * 8, vb);
-                convert_store(va, c);
-                tc::tmem_ld_wait();
-                if (c + 2 < ng) tc::tmem_ld8(lane_base + TM_ACC + (c + 2) * 8, va);
-                convert_store(vb, c + 1);
-                tc::tmem_ld_wait();
+            auto chunk_done = [&](int k) {
+                if ((k & 3) == 3) {
+                    tc::tmem_st_wait();
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&bars[BAR_H_READY + (k >> 2)]);
+                }
+            };
+            tc::tmem_ld16(base, va);
+            tc::tmem_ld_wait(va);
+            for (int k = 0; k < nblocks; k += 2) {
+                tc::tmem_ld16(base + 16 * (k + 1), vb);
+                convert_store(va, k);
+                chunk_done(k);
+                tc::tmem_ld_wait(vb);
+                if (k + 2 < nblocks) tc::tmem_ld16(base + 16 * (k + 2), va);
+                convert_store(vb, k + 1);
+                chunk_done(k + 1);
+                if (k + 2 < nblocks) tc::tmem_ld_wait(va);
             }
-            tc::tmem_st_wait();
         };
-        auto h_done = [&]() { tc::tc_fence_before(); tc::mbar_arrive(&bars[BAR_H_READY]); };
 
-        for (;;) {
-            tc::mbar_wait(&bars[BAR_MSG_FULL], msg & 1);
-            const int nrows = info[msg & 1].nrows, flags = info[msg & 1].flags, tile = info[msg & 1].tile;
-            tc::mbar_arrive(&bars[BAR_MSG_FREE]);
-            ++msg;
-            if (flags & 4) break;
+        for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
+            const int tile = tbase + (int)crank;
+            const int nrows = rows_of(tile);
             float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
             int smp = -1;
             if (row < nrows) {
@@ -557,7 +580,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 smp = (int)(__float_as_uint(gm.w) & ID_MASK);
             }
             const size_t ri = (size_t)P.frame * P.n_rays + (smp >= 0 ? smp / S : 0);
+            tr.ev(1);
             {
+                // the per-point tile of layer 3: [PE(xyz) 63 | 0 | PE(view) 27 | 0 | 1 | 1 | 0 | 0].  The previous tile's layer 3
+                // has read it: this thread waited for that tile's RGB_FULL, which is committed after every earlier MMA.
                 __half* peh = reinterpret_cast<__half*>(PE);
                 auto put = [&](int k, float v) {
                     peh[((k >> 3) * 16 + (row >> 3)) * 64 + (row & 7) * 8 + (k & 7)] = __float2half_rn(v);
@@ -568,33 +594,39 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 const float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
                 positional_embed_anchored<4, 4>(__fdiv_rn(dx, nrm), __fdiv_rn(dy, nrm), __fdiv_rn(dz, nrm), [&](int j, float v) { put(64 + j, v); });
                 put(91, 0.f); put(92, 1.f); put(93, 1.f); put(94, 0.f); put(95, 0.f);
-                tc::fence_proxy_async();
+                tc::fence_proxy_async();     // ordered before this thread's first H_READY arrival, which the issuer waits for
             }
-            for (int layer = 0; layer < 3; ++layer) {
-                wait_acc();
-                relu_to_h(256, true);
-                h_done();
-            }
-            wait_acc();
+            tr.ev(2);
+            wait_acc(); tr.ev(10);
+            convert_region(TM_R0, 16, true);     // h0
+            tr.ev(20);
+            wait_acc(); tr.ev(11);
+            convert_region(TM_R1, 16, true);     // h1
+            tr.ev(21);
+            wait_acc(); tr.ev(12);
+            convert_region(TM_R0, 16, true);     // h2
+            tr.ev(22);
+            wait_acc(); tr.ev(13);
             float sigma;
             {
-                uint32_t v[16];
-                tc::tmem_ld16(lane_base + TM_ACC + 128, v);
-                tc::tmem_ld_wait();
+                uint32_t v[8];
+                tc::tmem_ld8(lane_base + TM_SIGMA, v);
+                tc::tmem_ld_wait(v);
                 sigma = __uint_as_float(v[0]) + __uint_as_float(v[1]);
             }
-            relu_to_h(128, false);
-            h_done();
+            convert_region(TM_R1, 8, false);     // relu(colour hidden), hi only: H_READY[0], H_READY[1]
+            tr.ev(23);
             tc::mbar_wait(&bars[BAR_RGB_FULL], rcnt & 1); ++rcnt; tc::tc_fence_after();
+            tr.ev(14);
             {
-                uint32_t v[16];
-                tc::tmem_ld16(lane_base + TM_RGB, v);
-                tc::tmem_ld_wait();
+                uint32_t v[8];
+                tc::tmem_ld8(lane_base + TM_RGB, v);
+                tc::tmem_ld_wait(v);
                 if (smp >= 0)
                     P.raw_ws[smp] = make_float4(__uint_as_float(v[0]) + __uint_as_float(v[3]), __uint_as_float(v[1]) + __uint_as_float(v[4]),
                                                 __uint_as_float(v[2]) + __uint_as_float(v[5]), sigma);
             }
-            tc::tc_fence_before();      // (the next write of TM_RGB's columns is this thread's own layer-0 epilogue of the next tile)
+            tc::tc_fence_before();      // (TM_RGB is next written by the next tile's layer 1, issued after this thread's next H_READY)
         }
     }
 
@@ -662,6 +694,8 @@ constexpr size_t CTL_BYTES = 32;   // per frame: u32 list count, pad, u64 ~start
 
 }  // namespace tcl
 
+bool tc_available() { return true; }
+
 size_t render_tc_list_workspace_bytes(int batch, int n_rays, int n_samples) {
     const size_t per_frame = (size_t)n_rays * n_samples * sizeof(float4);
     return tcl::align256((size_t)batch * tcl::CTL_BYTES) + 2 * tcl::align256(per_frame);
@@ -676,11 +710,12 @@ int launch_render_tc_list(const RenderParams& p_in, int volume_dtype, int passes
     RenderParams p = p_in;
     const int S = p.n_samples;
     if (!render_tc_list_supported(p)) {
-        set_error("the list render pipeline supports n_samples <= %d and n_rays * n_samples < 2^28 per frame", tcl::MAXS);
+        set_error("the tensor-core render path supports n_samples <= %d and n_rays * n_samples < 2^28 per frame", tcl::MAXS);
         return NB_ERR_UNSUPPORTED;
     }
     if (!workspace || workspace_bytes < render_tc_list_workspace_bytes(p.batch, p.n_rays, S)) {
-        set_error("nb_render_fwd: workspace too small (%zu bytes, need %zu; see nb_render_fwd_workspace_bytes)", workspace_bytes,
+        set_error("nb_render_fwd: the tensor-core precisions need nb_render_args.workspace (%zu bytes given, %zu needed; see "
+                  "nb_render_fwd_workspace_bytes)", workspace ? workspace_bytes : (size_t)0,
                   render_tc_list_workspace_bytes(p.batch, p.n_rays, S));
         return NB_ERR_BAD_ARG;
     }

@@ -41,8 +41,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Every wait in the kernels completes within microseconds; a wait that is still pending after thousands of ~1 ms
+// suspended probes is a protocol bug.  It then traps (the launch fails with an error) instead of hanging the device.
+#ifndef NB_WATCHDOG_PROBES
+#define NB_WATCHDOG_PROBES 20000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t probes = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (++probes > NB_WATCHDOG_PROBES) __trap();
     }
 }
 
@@ -174,6 +181,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// same wait, with the loaded registers as in/out operands: no consumer of them (the register-only cvt asm included) can be
+// scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
@@ -204,6 +226,27 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+}
+// round-toward-zero variants: the hi half of a (hi, lo) fp16 pair.  Truncation makes fp32(hi) = x & 0xFFFFE000 (for
+// x in fp16's normal range), so the residual x - hi is one LOP3 + half a packed FADD2 instead of a convert + subtract.
+__device__ __forceinline__ uint32_t cvt_rz_relu_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rz.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t cvt_rz_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rz.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// (x0 - trunc10(x0), x1 - trunc10(x1)): the exact fp32 residuals of the round-toward-zero fp16 split, as one FADD2
+__device__ __forceinline__ void trunc_residual2(float x0, float x1, float& r0, float& r1) {
+    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+    uint64_t a, b, r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(x0), "f"(x1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(h0), "f"(h1));
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(r));
 }
 
 }  // namespace tc

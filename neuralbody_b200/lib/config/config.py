@@ -107,7 +107,6 @@ def _defaults():
                                         # (meets the 1e-3 parity gate) | "tc_fp16" tcgen05 1-pass (fastest, ~4e-3 on depth)
     c.render_volume_dtype = "auto"      # "auto": fp16 volume for tc_fp16, fp32 otherwise
     c.render_skip_empty = True          # tensor-core modes: exact empty-sample skipping (bit-identical outputs)
-    c.render_compact_frame = True       # with skip_empty: compact the occupied samples over the whole frame (3 launches) instead of per 1024-sample block (1 fused launch)
     c.render_return_weights = True      # 'weights' (B,n,S) is unused downstream; may be skipped
     c.render_importance = 0             # f-4: > 0 adds a fine pass with this many importance samples (upstream's N_importance is a dead key for Neural Body, so the default stays single-pass)
     c.chunk = 0                         # 0 = all rays of the call in one launch

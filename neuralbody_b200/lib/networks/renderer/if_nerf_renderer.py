@@ -61,6 +61,8 @@ class Renderer:
         self._vol_dtype = None
         self._w_key = None
         self._w_blob = None
+        self._vol_keep = None
+        self._w_keep = None
         self._tvals = {}
         self.launches = 0          # render kernels enqueued so far (bench accounting)
 
@@ -129,6 +131,8 @@ class Renderer:
     # ------------------------------------------------------------------ once-per-frame packs
     def pack_volume(self, feature_volume, dtype):
         """NCDHW fp32 volumes -> channels-last blob (nb_pack_volume); cached until the tensors change."""
+        # the key holds STRONG references to the keyed tensors (self._vol_keep): while an entry is cached, the caching
+        # allocator cannot hand the same address to another frame's volumes, so (data_ptr, shape, _version) identifies them
         key = (dtype,) + tuple((v.data_ptr(), tuple(v.shape), v._version) for v in feature_volume)
         if key == self._vol_key:
             return self._vol_blob, self._vol_dims
@@ -156,13 +160,16 @@ class Renderer:
         capi.check(self.lib.nb_pack_volume(levels, B, dtype, blob.data_ptr(), nbytes, C.c_void_p(stream)),
                    "nb_pack_volume")
         self._vol_key, self._vol_blob, self._vol_dims, self._vol_dtype = key, blob, dims, dtype
+        self._vol_keep = list(feature_volume)
         return blob, dims
 
     def pack_weights(self, latent_index, device):
-        """Fold + re-lay-out the decoder (nb_pack_weights); cached on parameter versions."""
+        """Fold + re-lay-out the decoder (nb_pack_weights); cached on parameter versions.  nb_pack_weights folds the VALUE
+        of latent_index into the blob, so the cache keeps a strong reference to the keyed index tensor (self._w_keep): a
+        new frame's freshly allocated index can then never alias the cached one's address."""
         tensors = self.net.decoder_tensors()
         key = tuple((t.data_ptr(), t._version) for t in tensors) + (latent_index.data_ptr(), latent_index._version,
-                                                                    tuple(latent_index.shape))
+                                                                    tuple(latent_index.shape), str(latent_index.device))
         if key == self._w_key:
             return self._w_blob
         B = int(latent_index.shape[0])
@@ -172,6 +179,7 @@ class Renderer:
         stream = torch.cuda.current_stream(device).cuda_stream
         capi.check(self.lib.nb_pack_weights(C.byref(w), blob.data_ptr(), nbytes, C.c_void_p(stream)), "nb_pack_weights")
         self._w_key, self._w_blob = key, blob
+        self._w_keep = (list(tensors), latent_index)
         return blob
 
     def _t_vals(self, S, device):
@@ -194,6 +202,9 @@ class Renderer:
         When autograd is recording and any volume / decoder tensor requires grad, the call goes through
         the exact kernel and `_FusedRender` so that `loss.backward()` works as it does upstream."""
         cfg = get_active_cfg()
+        if int(self._opt("xyz_res", 10)) != 10 or int(self._opt("view_res", 4)) != 4:
+            # embedder.py:53-54: the kernels (and view_fc's 346 input columns) are built for PE widths 63 / 27
+            raise NotImplementedError("cfg.xyz_res / cfg.view_res other than 10 / 4 are not supported by the fused kernels")
         if float(cfg.raw_noise_std) > 0.:
             # upstream's branch draws CPU randn and would crash on GPU tensors (nerf_net_utils.py:33)
             raise NotImplementedError("raw_noise_std > 0 is not supported (it is 0 in every reference config)")
@@ -207,10 +218,9 @@ class Renderer:
                                                   any(v.requires_grad for v in feature_volume))
         precision = capi.NB_PRECISION_FP32 if needs_grad else self._precision()
         skip_empty = bool(self._opt("render_skip_empty", True))
-        compact = (skip_empty or masks is not None) and bool(self._opt("render_compact_frame", True)) and n * S < (1 << 28)
-        if precision != capi.NB_PRECISION_FP32 and (S > 1024 or (S > 128 and not compact)):
-            # the single-launch tensor-core kernels tile whole rays into 128-row MMA tiles (N_samples <= 128, every reference
-            # config); the frame-compacting pipeline takes rays of up to 1024 samples; anything else runs on the exact kernel
+        if precision != capi.NB_PRECISION_FP32 and (S > 1024 or n * S >= (1 << 28)):
+            # the tensor-core pipeline works on a frame-wide sample list: rays of up to 1024 samples, < 2^28 samples per frame
+            # (every reference config: 64 / 128 samples, <= 1024^2 rays); anything else runs on the exact kernel
             precision = capi.NB_PRECISION_FP32
         if z_vals is not None:
             t_rand = None
@@ -223,7 +233,7 @@ class Renderer:
             "bounds": _f32c(sp_input['bounds'], dev), "latent_index": sp_input['latent_index'],
             "out_sh": [int(v) for v in sp_input['out_sh']], "voxel_size": [float(v) for v in cfg.voxel_size],
             "t_rand": None if t_rand is None else _f32c(t_rand, dev), "white_bkgd": bool(cfg.white_bkgd),
-            "z_vals": None if z_vals is None else _f32c(z_vals.detach(), dev), "compact": compact,
+            "z_vals": None if z_vals is None else _f32c(z_vals.detach(), dev),
             "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "out": out, "trace": trace,
             "want_weights": (bool(self._opt("render_return_weights", True)) if want_weights is None else bool(want_weights))
                             or needs_grad,
@@ -324,13 +334,13 @@ class Renderer:
                 a.mask_nv, a.mask_H, a.mask_W = int(msks.shape[0]), int(msks.shape[1]), int(msks.shape[2])
             a.stats = call["stats"].data_ptr() if call["stats"] is not None else None
             ws = None
-            if precision != capi.NB_PRECISION_FP32 and call["compact"]:   # frame-wide sample compaction: classify -> decoder over full tiles -> composite (3 launches / frame)
+            if precision != capi.NB_PRECISION_FP32:   # classify -> decoder over the frame's sample list -> composite (3 launches / frame)
                 ws = self._workspace(self.lib.nb_render_fwd_workspace_bytes(B, n, S), dev)
                 a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             a.trace = call["trace"].data_ptr() if call["trace"] is not None else None   # diagnostics (tools/trace_timeline.py)
             stream = torch.cuda.current_stream(dev).cuda_stream
             capi.check(self.lib.nb_render_fwd(C.byref(a), C.c_void_p(stream)), "nb_render_fwd")
-            self.launches += 3 * B if ws is not None else self.lib.nb_render_fwd_launches(precision)
+            self.launches += B * self.lib.nb_render_fwd_launches(precision)
             if save:   # everything nb_render_bwd needs stays alive with the autograd node
                 call["args"], call["save"], call["raw"] = a, sv, raw
                 call["keep"] = (vol_blob, w_blob, t_vals, out)

@@ -22,9 +22,8 @@ def make_net_and_renderer(scene, device="cuda:0"):
 
 def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False, t_rand=None,
                    precision="fp32", device="cuda:0", want_raw=False, chunk=0, renderer=None, net=None, skip_empty=True,
-                   masks=None, compact=True):
-    """Render `scene` through the public API on the GPU; returns dict of CPU tensors.
-    compact: with skip_empty, frame-wide sample compaction (3 launches) vs the single fused kernel."""
+                   masks=None):
+    """Render `scene` through the public API on the GPU; returns dict of CPU tensors."""
     cfg.N_samples = int(n_samples)
     cfg.perturb = float(perturb)
     cfg.white_bkgd = bool(white_bkgd)
@@ -33,7 +32,6 @@ def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=
     cfg.render_volume_dtype = "auto"
     cfg.chunk = int(chunk)
     cfg.render_skip_empty = bool(skip_empty)
-    cfg.render_compact_frame = bool(compact)
     if renderer is None:
         net, renderer = make_net_and_renderer(scene, device)
     net.train(training)

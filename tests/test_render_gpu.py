@@ -65,36 +65,40 @@ def test_raw_decoder_output_vs_oracle(precision):
 @pytest.mark.parametrize("precision", ["tc_fp16x3", "tc_fp16"])
 @pytest.mark.parametrize("name", ["eval_s64", "train_jitter_white", "batch2_s32", "eval_s48_seed7", "full_313"])
 def test_empty_sample_skipping_is_bit_exact(name, precision):
-    """Skipping samples whose trilinear cells are all unoccupied changes no output bit (sigma_empty < 0) -- neither in the
-    single fused kernel (compaction per 1024-sample block) nor in the frame-compacting 3-launch pipeline."""
+    """Skipping samples whose trilinear cells are all unoccupied changes no output bit (sigma_empty < 0): the same pipeline
+    with skip_empty = 0 lists EVERY sample and produces identical maps."""
     scene, rkw, _ = golden_case(name)
     net, ren = G.make_net_and_renderer(scene)
     ren.stats = torch.zeros(4, dtype=torch.int64, device="cuda")
-    dense = G.render_product(scene, precision=precision, skip_empty=False, renderer=ren, net=net, **rkw)
-    assert int(ren.stats[0]) == 0                      # the dense kernel does not count
     B, n = scene["ray_o"].shape[:2]
     S = rkw["n_samples"]
-    tiles = {}
-    for compact in (False, True):
-        ren.stats.zero_()
-        sparse = G.render_product(scene, precision=precision, skip_empty=True, renderer=ren, net=net, compact=compact, **rkw)
-        tiles[compact], occ = int(ren.stats[0]), int(ren.stats[1])
-        assert 0 < occ < B * n * S and tiles[compact] * 128 >= occ  # some, but not all, samples were evaluated
-        print(name, precision, "compact" if compact else "fused", "evaluated %.1f%% of the samples in %d tiles" % (
-            100.0 * occ / (B * n * S), tiles[compact]))
-        for k in ("rgb_map", "depth_map", "acc_map", "weights", "disp_map"):
-            assert torch.equal(torch.nan_to_num(dense[k], nan=-1.0), torch.nan_to_num(sparse[k], nan=-1.0)), (k, compact)
-    assert tiles[True] <= tiles[False] and tiles[True] <= (occ + 127) // 128 + B   # full tiles but the last of each frame
+    dense = G.render_product(scene, precision=precision, skip_empty=False, renderer=ren, net=net, **rkw)
+    assert int(ren.stats[1]) == B * n * S               # every sample went through the decoder
+    ren.stats.zero_()
+    sparse = G.render_product(scene, precision=precision, skip_empty=True, renderer=ren, net=net, **rkw)
+    tiles, occ = int(ren.stats[0]), int(ren.stats[1])
+    assert 0 < occ < B * n * S and tiles * 128 >= occ    # some, but not all, samples were evaluated
+    assert tiles <= (occ + 127) // 128 + B               # full tiles but the last of each frame
+    print(name, precision, "evaluated %.1f%% of the samples in %d tiles" % (100.0 * occ / (B * n * S), tiles))
+    for k in ("rgb_map", "depth_map", "acc_map", "weights", "disp_map"):
+        assert torch.equal(torch.nan_to_num(dense[k], nan=-1.0), torch.nan_to_num(sparse[k], nan=-1.0)), k
 
 
-def test_frame_compaction_writes_the_same_raw_records():
-    """want_raw: the 3-launch pipeline writes its raw records straight into the caller's buffer; they equal the fused kernel's."""
+def test_raw_records_of_skipped_samples():
+    """want_raw: evaluated samples carry the same (rgb logits, sigma) with and without skipping; skipped ones carry the
+    constant (0, 0, 0, min(sigma_empty, 0)) record (documented in the header next to `raw`)."""
     scene, rkw, _ = golden_case("train_jitter_white")
     net, ren = G.make_net_and_renderer(scene)
-    a = G.render_product(scene, precision="tc_fp16x3", want_raw=True, renderer=ren, net=net, compact=False, **rkw)
-    b = G.render_product(scene, precision="tc_fp16x3", want_raw=True, renderer=ren, net=net, compact=True, **rkw)
-    for k in ("raw", "rgb_map", "depth_map", "acc_map"):
+    a = G.render_product(scene, precision="tc_fp16x3", want_raw=True, renderer=ren, net=net, skip_empty=False, **rkw)
+    b = G.render_product(scene, precision="tc_fp16x3", want_raw=True, renderer=ren, net=net, skip_empty=True, **rkw)
+    for k in ("rgb_map", "depth_map", "acc_map"):
         assert torch.equal(a[k], b[k]), k
+    same = (a["raw"] == b["raw"]).all(dim=-1)
+    skipped = ~same
+    assert 0 < int(skipped.sum()) < skipped.numel()
+    rs = b["raw"][skipped]
+    assert float(rs[:, :3].abs().max()) == 0.0 and float(rs[:, 3].max()) <= 0.0 and float((rs[:, 3] - rs[0, 3]).abs().max()) == 0.0
+    assert float(a["raw"][skipped][:, 3].max()) < 0.0   # the dense run's sigma of those samples is sigma_empty < 0: weight 0
 
 
 def test_density_only_decoder_matches_oracle():
@@ -115,9 +119,8 @@ def test_density_only_decoder_matches_oracle():
 
 
 def test_long_rays():
-    """N_samples > 128 (e.g. 64 coarse + 128 importance merged): the frame-compacting pipeline keeps such rays
-    on the tensor cores (its decoder works on a sample list and does not care about S); the single fused launch tiles
-    whole rays into 128-row tiles and hands them to the exact kernel instead."""
+    """N_samples > 128 (e.g. 64 coarse + 128 importance merged) stays on the tensor cores: the decoder works on a
+    sample list and does not care about S."""
     scene, rkw, _ = golden_case("eval_s64")
     sub = dict(scene)
     for k in ("ray_o", "ray_d", "near", "far"):
@@ -129,11 +132,6 @@ def test_long_rays():
     assert int(ren.stats[3]) == 1 and int(ren.stats[0]) > 0          # one decoder launch of the list pipeline ran
     for k in ("rgb_map", "depth_map", "acc_map"):
         assert float((out[k] - ref[k]).abs().max()) < 1e-3, k
-    ren.stats.zero_()
-    out = G.render_product(sub, precision="tc_fp16x3", n_samples=192, compact=False, renderer=ren, net=net)
-    assert int(ren.stats[0]) == 0                                      # exact kernel: no tensor-core tiles
-    for k in ("rgb_map", "depth_map", "acc_map"):
-        assert float((out[k] - ref[k]).abs().max()) < 1e-4, k
 
 
 def test_chunked_equals_single_launch():
@@ -215,7 +213,7 @@ def test_hierarchical_render_matches_reference_pieces(name, precision):
     net, ren = G.make_net_and_renderer(scene)
     cfg.N_samples, cfg.perturb, cfg.white_bkgd = rkw["n_samples"], float(rkw.get("perturb", 0.)), bool(rkw.get("white_bkgd", False))
     cfg.raw_noise_std, cfg.render_precision, cfg.render_volume_dtype, cfg.chunk = 0, precision, "auto", 0
-    cfg.render_skip_empty, cfg.render_compact_frame, cfg.render_importance = True, True, rkw["n_importance"]
+    cfg.render_skip_empty, cfg.render_importance = True, rkw["n_importance"]
     net.train(bool(rkw.get("training", False)))
     try:
         batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}

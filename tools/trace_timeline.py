@@ -8,14 +8,14 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
-PROD = {1: "geom done / tile published", 2: "block begin", 3: "block classified"}
+PROD = {1: "tile begin (list rows loaded)"}
 PROD.update({10 + s: "seg%d buf free" % s for s in range(6)})
 PROD.update({20 + s: "seg%d gathered" % s for s in range(6)})
 MMA = {1: "tile begin", 20: "L0 issued", 21: "L1 issued", 22: "L2 issued", 23: "L3 issued", 31: "h ready L1", 32: "h ready L2",
        33: "h ready L3", 34: "h ready L4"}
 MMA.update({10 + s: "seg%d available" % s for s in range(6)})
-EPI = {1: "geom avail", 2: "PE written", 10: "acc L0", 11: "acc L1", 12: "acc L2", 13: "acc L3", 14: "acc L4", 20: "epi L0 done",
-       21: "epi L1 done", 22: "epi L2 done", 23: "epi L3 done", 30: "composite done"}
+EPI = {1: "tile begin", 2: "PE written", 10: "acc L0", 11: "acc L1", 12: "acc L2", 13: "acc L3", 14: "acc L4 (rgb)", 20: "epi L0 done",
+       21: "epi L1 done", 22: "epi L2 done", 23: "epi L3 done"}
 
 
 def main():
@@ -28,8 +28,7 @@ def main():
     scene = synth.make_scene(H=512, W=512, scale=1.0, all_hit=True)
     net, ren = G.make_net_and_renderer(scene)
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.render_precision, cfg.render_volume_dtype = 64, 0.0, False, prec, "auto"
-    cfg.render_skip_empty = len(sys.argv) > 4 and sys.argv[4] in ("sparse", "list")
-    cfg.render_compact_frame = len(sys.argv) > 4 and sys.argv[4] == "list"
+    cfg.render_skip_empty = not (len(sys.argv) > 4 and sys.argv[4] == "dense")
     net.eval()
     batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}
     sp = ren.prepare_sp_input(batch)
