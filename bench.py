@@ -118,7 +118,7 @@ def pick_cpu_threads(fn):
 
 
 def build_scene():
-    from neuralbody_b200 import synth
+    from oracle import synth
     scene = synth.make_scene(H=H, W=W, scale=1.0, all_hit=True)
     assert scene["ray_o"].shape[1] == H * W
     return scene

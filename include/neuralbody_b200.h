@@ -131,6 +131,11 @@ typedef struct nb_render_args {
     const float* mask_RT;            /* device (nv,3,4) world->camera */
     const float* mask_Ks;            /* device (nv,3,3) */
     int   mask_nv, mask_H, mask_W;
+    /* single-view variant (if_clight_renderer_msk.py:12-49, People-Snapshot demos): before projecting, a sample is taken from the
+       world to the SMPL frame with this frame's (R, Th) and from there into the world of the snapshot frame the mask was
+       shot in: q = ((p - Th) R) R0^T + Th0.  Both NULL => no such transform (the multi-view renderer) */
+    const float* mask_R0;            /* device (3,3) batch['R0_snap'] or NULL */
+    const float* mask_Th0;           /* device (3)   batch['Th0_snap'] or NULL */
     int   skip_empty;      /* tensor-core precisions: 1 = exact empty-sample skipping (samples whose trilinear cells are all
                               unoccupied have weight exactly 0 when sigma(empty) < 0; their MLP evaluation is skipped and `raw`,
                               if requested, holds (0, 0, 0, min(sigma_empty, 0)) for them instead of the decoder's rgb logits);

@@ -49,7 +49,8 @@ class nb_render_args(C.Structure):
         ("rgb_map", C.c_void_p), ("disp_map", C.c_void_p), ("acc_map", C.c_void_p), ("weights", C.c_void_p),
         ("depth_map", C.c_void_p), ("raw", C.c_void_p),
         ("mask_msks", C.c_void_p), ("mask_RT", C.c_void_p), ("mask_Ks", C.c_void_p),
-        ("mask_nv", C.c_int), ("mask_H", C.c_int), ("mask_W", C.c_int), ("skip_empty", C.c_int), ("stats", C.c_void_p), ("save", C.c_void_p),
+        ("mask_nv", C.c_int), ("mask_H", C.c_int), ("mask_W", C.c_int), ("mask_R0", C.c_void_p), ("mask_Th0", C.c_void_p),
+        ("skip_empty", C.c_int), ("stats", C.c_void_p), ("save", C.c_void_p),
         ("trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("z_vals", C.c_void_p),
     ]
 

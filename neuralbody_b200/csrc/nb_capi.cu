@@ -461,6 +461,8 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
     p.rgb_map = a->rgb_map; p.disp_map = a->disp_map; p.acc_map = a->acc_map; p.weights = a->weights; p.depth_map = a->depth_map; p.raw = a->raw; p.trace = a->trace; p.save = a->save; p.stats = a->stats;
     p.mask_msks = a->mask_msks; p.mask_RT = a->mask_RT; p.mask_Ks = a->mask_Ks;
     p.mask_nv = a->mask_msks ? a->mask_nv : 0; p.mask_H = a->mask_H; p.mask_W = a->mask_W;
+    p.mask_R0 = a->mask_msks ? a->mask_R0 : nullptr; p.mask_Th0 = a->mask_msks ? a->mask_Th0 : nullptr;
+    if ((p.mask_R0 != nullptr) != (p.mask_Th0 != nullptr)) { set_error("nb_render_fwd: mask_R0 and mask_Th0 go together"); return NB_ERR_BAD_ARG; }
     if (a->mask_msks && (a->batch != 1 || !a->mask_RT || !a->mask_Ks || a->mask_nv <= 0 || a->mask_H <= 0 || a->mask_W <= 0)) {
         set_error("nb_render_fwd: mask views need batch == 1 (as upstream), RT, Ks and positive nv/H/W");
         return NB_ERR_BAD_ARG;

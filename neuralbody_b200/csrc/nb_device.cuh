@@ -110,7 +110,19 @@ __device__ __forceinline__ int mask_pixel(float r, int size) {
     const long long q = (long long)rintf(r);
     return (int)(q < 0 ? 0 : (q > size - 1 ? size - 1 : q));
 }
-__device__ __forceinline__ bool inside_masks(const RenderParams& P, float wx, float wy, float wz) {
+// The single-view variant (if_clight_renderer_msk.py:17-30) first moves the sample into the world of the snapshot frame:
+// can = (p - Th) @ R;  q = can @ R0^T + Th0.
+__device__ __forceinline__ bool inside_masks(const RenderParams& P, const FrameXf& f, float wx, float wy, float wz) {
+    if (P.mask_R0) {
+        const float px = __fsub_rn(wx, f.Th[0]), py = __fsub_rn(wy, f.Th[1]), pz = __fsub_rn(wz, f.Th[2]);
+        const float cx = fmaf(pz, f.R[6], fmaf(py, f.R[3], __fmul_rn(px, f.R[0])));
+        const float cy = fmaf(pz, f.R[7], fmaf(py, f.R[4], __fmul_rn(px, f.R[1])));
+        const float cz = fmaf(pz, f.R[8], fmaf(py, f.R[5], __fmul_rn(px, f.R[2])));
+        const float* R0 = P.mask_R0;
+        wx = __fadd_rn(fmaf(cz, __ldg(R0 + 2), fmaf(cy, __ldg(R0 + 1), __fmul_rn(cx, __ldg(R0 + 0)))), __ldg(P.mask_Th0 + 0));
+        wy = __fadd_rn(fmaf(cz, __ldg(R0 + 5), fmaf(cy, __ldg(R0 + 4), __fmul_rn(cx, __ldg(R0 + 3)))), __ldg(P.mask_Th0 + 1));
+        wz = __fadd_rn(fmaf(cz, __ldg(R0 + 8), fmaf(cy, __ldg(R0 + 7), __fmul_rn(cx, __ldg(R0 + 6)))), __ldg(P.mask_Th0 + 2));
+    }
     for (int v = 0; v < P.mask_nv; ++v) {
         const float* RT = P.mask_RT + v * 12;
         const float* K = P.mask_Ks + v * 9;

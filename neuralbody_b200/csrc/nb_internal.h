@@ -35,6 +35,7 @@ struct RenderParams {
     unsigned long long* trace;
     const unsigned char* mask_msks; const float* mask_RT; const float* mask_Ks;   // f-1 mask views (null = none)
     int mask_nv, mask_H, mask_W;
+    const float *mask_R0, *mask_Th0;   // single-view _msk variant: SMPL -> snapshot-world transform, or null
     unsigned long long* stats; // u64[4] or null: [0] += tiles executed, [1] += listed samples,
                                // [2] += decoder-kernel ns, [3] += decoder launches
     float* save;               // (B,n,S,kSaveDim) activation record for nb_render_bwd (exact kernel only) or null

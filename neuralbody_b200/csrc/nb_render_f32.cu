@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
                     const float wz = __fadd_rn(r.o[2], __fmul_rn(r.d[2], z));
                     float gx, gy, gz;
                     world_to_grid(xf, wx, wy, wz, gx, gy, gz);
-                    if (P.mask_nv > 0) pins[tid] = inside_masks(P, wx, wy, wz) ? 1 : 0;
+                    if (P.mask_nv > 0) pins[tid] = inside_masks(P, xf, wx, wy, wz) ? 1 : 0;
                     gcoord[tid * 3 + 0] = gx; gcoord[tid * 3 + 1] = gy; gcoord[tid * 3 + 2] = gz;
                     positional_embed<10>(wx, wy, wz, [&](int j, float v) { yrow[j] = v; });   // PE of WORLD xyz (latent_xyzc.py:115)
                     yrow[kXyzPE] = 0.f;

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
             float gx, gy, gz;
             world_to_grid(xf, gm[k].x, gm[k].y, gm[k].z, gx, gy, gz);
             uint32_t lm = 0;                           // bit l = the sample's level-l cell holds a non-zero voxel
-            const bool inside = P.mask_nv == 0 || inside_masks(P, gm[k].x, gm[k].y, gm[k].z);   // f-1 mask views
+            const bool inside = P.mask_nv == 0 || inside_masks(P, xf, gm[k].x, gm[k].y, gm[k].z);   // f-1 mask views
             if (inside) {
 #pragma unroll
                 for (int lvl = 0; lvl < 4; ++lvl) {

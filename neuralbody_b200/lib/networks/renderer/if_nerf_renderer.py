@@ -244,7 +244,10 @@ class Renderer:
             if needs_grad:
                 raise NotImplementedError("mask views are an inference feature upstream (vis_novel_view / vis_novel_pose)")
             msks = masks["msks"][0].to(device=dev, dtype=torch.uint8).contiguous()
-            call["masks"] = (msks, _f32c(masks["RT"][0][:, :3, :4], dev), _f32c(masks["Ks"][0], dev))
+            snap = None
+            if masks.get("R0_snap") is not None:   # single-view variant (if_clight_renderer_msk.py): SMPL -> snapshot world
+                snap = (_f32c(masks["R0_snap"][0], dev), _f32c(masks["Th0_snap"][0], dev).reshape(3))
+            call["masks"] = (msks, _f32c(masks["RT"][0][:, :3, :4], dev), _f32c(masks["Ks"][0], dev), snap)
         if call["t_rand"] is not None:
             assert tuple(call["t_rand"].shape) == (B, n, S)
         if needs_grad:
@@ -329,8 +332,10 @@ class Renderer:
             a.save = sv.data_ptr() if sv is not None else None
             a.skip_empty = 1 if call["skip_empty"] else 0
             if call["masks"] is not None:
-                msks, RT, Ks = call["masks"]
+                msks, RT, Ks, snap = call["masks"]
                 a.mask_msks, a.mask_RT, a.mask_Ks = msks.data_ptr(), RT.data_ptr(), Ks.data_ptr()
+                if snap is not None:
+                    a.mask_R0, a.mask_Th0 = snap[0].data_ptr(), snap[1].data_ptr()
                 a.mask_nv, a.mask_H, a.mask_W = int(msks.shape[0]), int(msks.shape[1]), int(msks.shape[2])
             a.stats = call["stats"].data_ptr() if call["stats"] is not None else None
             ws = None

@@ -23,12 +23,15 @@ CASES = {
     "full_313": (dict(H=512, W=512, scale=1.0, all_hit=True), dict(n_samples=64), 521),
     # f-1 masked renderer (if_clight_renderer_mmsk): 4 mask views, samples outside any silhouette get raw = 0
     "mmsk_s64": (dict(H=48, W=48, scale=0.3, all_hit=True), dict(n_samples=64), 9),
+    # f-1, single-view variant (if_clight_renderer_msk, the renderer snapshot_f3c.yaml selects for its demos): extra
+    # SMPL -> snapshot-world transform, one mask; Th in the monocular (B,3) form its `Th[:, None, None]` needs
+    "msk_s64": (dict(H=48, W=48, scale=0.3, all_hit=True, th_shape=(3,)), dict(n_samples=64), 9),
 }
 
 
 def build_case(name):
     """-> (scene, render_kwargs incl. t_rand) with rays subsampled by the case's stride."""
-    from neuralbody_b200 import synth
+    from oracle import synth
     skw, rkw, stride = CASES[name]
     scene = synth.make_scene(**skw)
     n = scene["ray_o"].shape[1]
@@ -41,6 +44,8 @@ def build_case(name):
         rkw["t_rand"] = torch.rand((scene["ray_o"].shape[0], scene["ray_o"].shape[1], rkw["n_samples"]), generator=g)
     if name.startswith("mmsk"):
         rkw["masks"] = synth.make_mask_views(scene, nv=4, H=96, W=96, radius=2)
+    if name.startswith("msk"):
+        rkw["masks"] = synth.make_snapshot_view(scene, H=96, W=96, radius=2)
     return scene, rkw
 
 
@@ -55,7 +60,7 @@ HIER_CASES = {
 
 
 def build_hier_case(name):
-    from neuralbody_b200 import synth
+    from oracle import synth
     skw, rkw, stride = HIER_CASES[name]
     scene = synth.make_scene(**skw)
     idx = torch.arange(0, scene["ray_o"].shape[1], stride)

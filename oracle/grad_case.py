@@ -10,7 +10,7 @@ N_SAMPLES = 32
 
 
 def build():
-    from neuralbody_b200 import synth
+    from oracle import synth
     scene = synth.make_scene(H=24, W=24, scale=0.25, all_hit=True, latent_index=3)
     idx = torch.arange(0, scene["ray_o"].shape[1], 5)
     for k in ("ray_o", "ray_d", "near", "far"):

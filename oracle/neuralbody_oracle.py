@@ -10,7 +10,7 @@ library.
 Parity pinning: the reference ships no tests or golden vectors.
 This restatement is pinned instead against outputs of the UNMODIFIED reference
 executed in the build container (oracle/ref_harness.py) on the seeded synthetic
-scenes of neuralbody_b200/synth.py; the vectors are committed under tests/golden/
+scenes of oracle/synth.py; the vectors are committed under tests/golden/
 together with the generating script oracle/make_golden.py, and
 tests/test_oracle.py re-checks the restatement against them on every run.
 
@@ -192,7 +192,10 @@ def get_pixel_value_mmsk(w, ray_o, ray_d, near, far, feature_volume, sp_input, v
                          white_bkgd=False):
     """if_clight_renderer_mmsk.py:47-94: decoder only on inside samples, raw = 0 elsewhere."""
     wpts, z_vals = get_sampling_points(ray_o, ray_d, near, far, n_samples)
-    inside = prepare_inside_pts(wpts, masks, masks["mask_H"], masks["mask_W"])
+    if "R0_snap" in masks:   # if_clight_renderer_msk.Renderer overrides prepare_inside_pts, nothing else
+        inside = prepare_inside_pts_msk(wpts, masks, masks["mask_H"], masks["mask_W"])
+    else:
+        inside = prepare_inside_pts(wpts, masks, masks["mask_H"], masks["mask_W"])
     viewdir = ray_d / torch.norm(ray_d, dim=2, keepdim=True)
     n_batch, n_pixel, n_sample = wpts.shape[:3]
     wp = wpts.view(n_batch, n_pixel * n_sample, -1)
@@ -208,10 +211,37 @@ def get_pixel_value_mmsk(w, ray_o, ray_d, near, far, feature_volume, sp_input, v
             'depth_map': depth_map.view(n_batch, n_pixel)}
 
 
+def prepare_inside_pts_msk(wpts, batch, H, W):
+    """lib/networks/renderer/if_clight_renderer_msk.py:12-49 (single-view variant of the People-Snapshot demos): world ->
+    SMPL frame with the rendered frame's (R, Th) -> world of the snapshot frame (R0_snap, Th0_snap) -> that frame's camera
+    (RT (1,3,4), K (1,3,3)) -> foreground test in msk (1,H,W).  wpts (1,n,S,3) -> inside (1, n*S) bool."""
+    Th = batch['Th']
+    can_pts = wpts - Th[:, None, None]
+    can_pts = torch.matmul(can_pts, batch['R'])
+    R0 = batch['R0_snap']
+    Th0 = batch['Th0_snap']
+    sh = can_pts.shape
+    can_pts = can_pts.view(sh[0], -1, sh[3])
+    pts = torch.matmul(can_pts, R0.transpose(2, 1)) + Th0[:, None]
+    R = batch['RT'][..., :3]
+    T = batch['RT'][..., 3]
+    pts = torch.matmul(pts, R.transpose(2, 1)) + T[:, None]
+    pts = torch.matmul(pts, batch['K'].transpose(2, 1))
+    pts2d = pts[..., :2] / pts[..., 2:]
+    pts2d = pts2d.round().long()
+    pts2d[..., 0] = torch.clamp(pts2d[..., 0], 0, W - 1)
+    pts2d[..., 1] = torch.clamp(pts2d[..., 1], 0, H - 1)
+    pts2d = pts2d[0]
+    msk = batch['msk'][0]
+    return msk[pts2d[:, 1], pts2d[:, 0]][None].bool()
+
+
 def render_mmsk(scene, masks, n_samples=64, white_bkgd=False, chunk=2048):
     """Renderer.render (if_clight_renderer.py:94-122) driving the masked get_pixel_value."""
     sp_input = prepare_sp_input(scene)
     n_pixel = scene['ray_o'].shape[1]
+    if "R0_snap" in masks:
+        masks = dict(masks, R=scene['R'], Th=scene['Th'])
     ret_list = []
     for i in range(0, n_pixel, chunk):
         ret_list.append(get_pixel_value_mmsk(

@@ -92,7 +92,7 @@ def load_reference(cfg_file="configs/snapshot_exp/snapshot_f3c.yaml"):
 
 def reference_render(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=False,
                      t_rand=None, chunk=2048, num_train_frame=None, grad=False, masks=None):
-    """Run the reference renderer on a synthetic scene dict (neuralbody_b200.synth).
+    """Run the reference renderer on a synthetic scene dict (oracle.synth).
 
     Follows Renderer.render (if_clight_renderer.py:94-122) literally, except that
     net.encode_sparse_voxels (spconv) is replaced by the supplied dense volumes.
@@ -122,6 +122,11 @@ def reference_render(scene, n_samples=64, perturb=0.0, training=False, white_bkg
                                    "ray_o", "ray_d", "near", "far")}
     if masks is None:
         renderer = if_clight_renderer.Renderer(net)
+    elif "R0_snap" in masks:   # f-1, single view: lib/networks/renderer/if_clight_renderer_msk.py
+        from lib.networks.renderer import if_clight_renderer_msk
+        cfg.H, cfg.W, cfg.ratio = int(masks["mask_H"]), int(masks["mask_W"]), 1.0
+        renderer = if_clight_renderer_msk.Renderer(net)
+        batch.update({k: masks[k] for k in ("R0_snap", "Th0_snap", "RT", "K", "msk")})
     else:   # f-1: lib/networks/renderer/if_clight_renderer_mmsk.py (H, W come from cfg.H * cfg.ratio)
         from lib.networks.renderer import if_clight_renderer_mmsk
         cfg.H, cfg.W, cfg.ratio = int(masks["mask_H"]), int(masks["mask_W"]), 1.0

@@ -1,4 +1,4 @@
-"""Deterministic synthetic scene `synth-313`.
+"""TEST / BENCH INPUT GENERATION (not product code): deterministic synthetic scene `synth-313`.
 
 The licensed ZJU-MoCap / People-Snapshot data and spconv are absent, so every
 test and bench line runs on a synthetic SMPL-posed body that follows the
@@ -161,6 +161,56 @@ def look_at_camera(center, distance, azimuth_deg=20.0, elevation_deg=5.0):
     R = np.stack([right, down, fwd], 0)  # rows = camera axes in world coords
     T = -R @ eye
     return R, T.reshape(3, 1)
+
+
+def training_cameras(center, n_cams=21, distance=3.0, elevation_deg=5.0, f=537.0, H=512, W=512):
+    """A ZJU-MoCap-like rig: `n_cams` pin-holes on a ring around `center`.  Returns (K list of (3,3), RT list of (4,4)
+    world->camera), the form lib/utils/render_utils.py:27-49 (`load_cam`) hands to `gen_path`."""
+    Ks, RTs = [], []
+    for i in range(n_cams):
+        R, T = look_at_camera(np.asarray(center, np.float64), distance, azimuth_deg=360.0 * i / n_cams, elevation_deg=elevation_deg)
+        RTs.append(np.concatenate([np.concatenate([R, T], 1), np.array([[0., 0., 0., 1.]])], 0))
+        Ks.append(np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1.0]]))
+    return Ks, RTs
+
+
+def _normalize(x):
+    return x / np.linalg.norm(x)
+
+
+def gen_path(RT, num_render_views=144, center=None):
+    """lib/utils/render_utils.py:61-106 (`gen_path`): the spiral of `cfg.num_render_views` novel views the reference's
+    demo dataset renders (multi_view_demo_dataset.py:29-31), from the training cameras' world->camera matrices."""
+    lower_row = np.array([[0., 0., 0., 1.]])
+    RT = np.array(RT)
+    RT[:] = np.linalg.inv(RT[:])
+    RT = np.concatenate([RT[:, :, 1:2], RT[:, :, 0:1], -RT[:, :, 2:3], RT[:, :, 3:4]], 2)
+    up = _normalize(RT[:, :3, 0].sum(0))
+    z = _normalize(RT[0, :3, 2])
+    vec1 = _normalize(np.cross(z, up))
+    vec2 = _normalize(np.cross(up, vec1))
+    z_off = 0
+    if center is None:
+        center = RT[:, :3, 3].mean(0)
+        z_off = 1.3
+    c2w = np.stack([up, vec1, vec2, center], 1)
+    tt = np.matmul(c2w[:3, :3].T, (RT[:, :3, 3] - c2w[:3, 3])[..., np.newaxis])[..., 0].T
+    rads = np.percentile(np.abs(tt), 80, -1)
+    rads = rads * 1.3
+    rads = np.array(list(rads) + [1.])
+    render_w2c = []
+    for theta in np.linspace(0., 2 * np.pi, num_render_views + 1)[:-1]:
+        cam_pos = np.array([0, np.sin(theta), np.cos(theta), 1] * rads)
+        cam_pos_world = np.dot(c2w[:3, :4], cam_pos)
+        z = _normalize(cam_pos_world - np.dot(c2w[:3, :4], np.array([z_off, 0, 0, 1.])))
+        vec2_ = _normalize(z)
+        vec1_ = _normalize(np.cross(vec2_, up))
+        vec0_ = _normalize(np.cross(vec1_, vec2_))
+        mat = np.stack([vec0_, vec1_, vec2_, cam_pos_world], 1)
+        mat = np.concatenate([mat[:, 1:2], mat[:, 0:1], -mat[:, 2:3], mat[:, 3:4]], 1)
+        mat = np.concatenate([mat, lower_row], 0)
+        render_w2c.append(np.linalg.inv(mat))
+    return render_w2c
 
 
 def make_rays(can_bounds, H, W, all_hit=True, azimuth_deg=20.0, distance=3.0, focal=None):
@@ -376,6 +426,39 @@ def make_mask_views(scene, nv=4, H=128, W=128, radius=3, distance=None):
     return {"RT": torch.from_numpy(np.stack(RT).astype(np.float32))[None],
             "Ks": torch.from_numpy(np.stack(Ks).astype(np.float32))[None],
             "msks": torch.from_numpy(np.stack(msks))[None], "mask_H": H, "mask_W": W}
+
+
+def make_snapshot_view(scene, H=96, W=96, radius=2, dRh=(0.05, 0.6, -0.1), dTh=(0.15, -0.05, 0.3)):
+    """Inputs of the single-view masked renderer (lib/networks/renderer/if_clight_renderer_msk.py:12-49; dataset side
+    lib/datasets/light_stage/monocular_demo_dataset.py:138-141): the pose (R0_snap, Th0_snap) of the snapshot frame the mask
+    was shot in -- here the rendered frame's pose turned by `dRh` and shifted by `dTh` -- that frame's camera (RT (3,4),
+    K (3,3)) and its foreground mask msk (H,W) uint8 = silhouette of the vertex cloud in the snapshot pose.
+    Returned with the leading batch dimension of 1 (B = 1 only upstream)."""
+    R = scene["R"][0].numpy().astype(np.float64)
+    Th = scene["Th"][0].numpy().astype(np.float64).reshape(3)
+    verts_can = (scene["verts_world"].numpy().astype(np.float64) - Th) @ R
+    R0 = (_rodrigues(dRh) @ R).astype(np.float32)
+    Th0 = (Th + np.asarray(dTh, np.float64)).astype(np.float32)
+    snap = verts_can @ R0.astype(np.float64).T + Th0.astype(np.float64)
+    center = 0.5 * (snap.min(0) + snap.max(0))
+    ext = float(np.max(snap.max(0) - snap.min(0)))
+    distance = 2.2 * ext
+    f = 0.9 * min(H, W) * distance / ext
+    Rc, Tc = look_at_camera(center, distance, azimuth_deg=-25.0, elevation_deg=6.0)
+    K = np.array([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1.0]])
+    uv = (snap @ Rc.T + Tc.ravel()) @ K.T
+    u = np.round(uv[:, 0] / uv[:, 2]).astype(int)
+    v = np.round(uv[:, 1] / uv[:, 2]).astype(int)
+    m = np.zeros((H, W), np.uint8)
+    yy, xx = np.mgrid[-radius:radius + 1, -radius:radius + 1]
+    disc = (yy ** 2 + xx ** 2) <= radius ** 2
+    for dy, dx in zip(yy[disc], xx[disc]):
+        uu, vv = u + dx, v + dy
+        ok = (uu >= 0) & (uu < W) & (vv >= 0) & (vv < H)
+        m[vv[ok], uu[ok]] = 1
+    return {"R0_snap": torch.from_numpy(R0)[None], "Th0_snap": torch.from_numpy(Th0)[None],
+            "RT": torch.from_numpy(np.concatenate([Rc, Tc], 1).astype(np.float32))[None],
+            "K": torch.from_numpy(K.astype(np.float32))[None], "msk": torch.from_numpy(m)[None], "mask_H": H, "mask_W": W}
 
 
 def scene_checksum(scene):

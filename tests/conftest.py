@@ -31,7 +31,7 @@ def golden_case(name):
     """(scene, render kwargs, golden dict); asserts the rebuilt inputs are the ones the
     reference saw when the vectors were made (sha256 over every input tensor)."""
     if name not in _case_cache:
-        from neuralbody_b200 import synth
+        from oracle import synth
         from oracle import golden_cases
         scene, rkw = golden_cases.build_case(name)
         gold = load_golden(name)
@@ -46,7 +46,7 @@ def hier_golden_case(name):
     """f-4 cases (oracle/golden_cases.HIER_CASES): (scene, render kwargs incl. t_rand / u, golden dict)."""
     key = "hier:" + name
     if key not in _case_cache:
-        from neuralbody_b200 import synth
+        from oracle import synth
         from oracle import golden_cases
         scene, rkw = golden_cases.build_hier_case(name)
         gold = load_golden(name)

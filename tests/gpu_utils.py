@@ -40,10 +40,12 @@ def render_product(scene, n_samples=64, perturb=0.0, training=False, white_bkgd=
         import os
         from neuralbody_b200.lib.networks.make_network import load_source
         here = os.path.dirname(os.path.abspath(__file__))
-        path = os.path.join(here, "..", "neuralbody_b200", "lib", "networks", "renderer", "if_nerf_renderer_mmsk.py")
-        mren = load_source("neuralbody_b200.lib.networks.renderer.if_nerf_renderer_mmsk", os.path.abspath(path)).Renderer(net)
+        single = "R0_snap" in masks          # if_clight_renderer_msk (one snapshot view) vs _mmsk (nv training views)
+        mod = "if_nerf_renderer_msk" if single else "if_nerf_renderer_mmsk"
+        path = os.path.join(here, "..", "neuralbody_b200", "lib", "networks", "renderer", mod + ".py")
+        mren = load_source("neuralbody_b200.lib.networks.renderer." + mod, os.path.abspath(path)).Renderer(net)
         cfg.H, cfg.W, cfg.ratio = int(masks["mask_H"]), int(masks["mask_W"]), 1.0
-        batch.update({k: masks[k].to(device) for k in ("RT", "Ks", "msks")})
+        batch.update({k: masks[k].to(device) for k in (("R0_snap", "Th0_snap", "RT", "K", "msk") if single else ("RT", "Ks", "msks"))})
         with torch.no_grad():
             out = mren.render(batch)
         torch.cuda.synchronize()

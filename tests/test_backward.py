@@ -11,7 +11,7 @@ from oracle import grad_case
 
 @pytest.fixture(scope="module")
 def case():
-    from neuralbody_b200 import synth
+    from oracle import synth
     scene, t_rand, G = grad_case.build()
     gold = load_golden("grad_train_s32")
     assert synth.scene_checksum(scene) == gold["input_sha256"]
@@ -91,7 +91,7 @@ def test_inference_path_unchanged_under_no_grad(case):
 # ---------------------------------------------------------------------------------------------- f-4: coarse + fine pass
 @pytest.fixture(scope="module")
 def hier_case():
-    from neuralbody_b200 import synth
+    from oracle import synth
     scene, t_rand, u, G = grad_case.hier_build()
     gold = load_golden("grad_hier_s32_i48")
     assert synth.scene_checksum(scene) == gold["input_sha256"]

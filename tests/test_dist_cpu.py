@@ -23,7 +23,8 @@ def _worker(rank, world, port, n_rays, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from neuralbody_b200 import synth, dist as nbdist
+        from oracle import synth
+        from neuralbody_b200 import dist as nbdist
         from oracle import neuralbody_oracle as O
         torch.set_num_threads(1)
         scene = synth.make_scene(H=16, W=16, scale=0.25, all_hit=True, n_rays=n_rays)

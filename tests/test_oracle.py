@@ -21,7 +21,7 @@ def test_oracle_matches_reference_golden(name):
         assert a.shape == b.shape
         # same torch ops in the same order => bit-identical, NaNs (acc == 0 rays) included
         np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
-        np.testing.assert_allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=0, atol=1e-6, err_msg=k)
+        np.testing.assert_array_equal(np.nan_to_num(a), np.nan_to_num(b), err_msg=k)
 
 
 @pytest.mark.parametrize("name", list(golden_cases.HIER_CASES))
@@ -33,7 +33,7 @@ def test_hierarchical_oracle_matches_reference_pieces(name):
         a, b = out[k].numpy(), gold[k]
         assert a.shape == b.shape, k
         np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
-        np.testing.assert_allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=0, atol=1e-6, err_msg=k)
+        np.testing.assert_array_equal(np.nan_to_num(a), np.nan_to_num(b), err_msg=k)
     S, Ni = rkw["n_samples"], rkw["n_importance"]
     assert gold["z_vals"].shape[-1] == S + Ni and (np.diff(gold["z_vals"], axis=-1) >= 0).all()
     assert np.abs(gold["rgb_map"] - gold["rgb0"]).max() > 1e-3      # the fine pass is not a no-op on these scenes
@@ -146,3 +146,39 @@ def test_raw2outputs_known_answers():
     rgb, disp, acc, wts, depth = O.raw2outputs(raw0, z, d, white_bkgd=True)
     assert float(acc) == 0.0 and math.isnan(float(disp))
     np.testing.assert_allclose(rgb.numpy(), [[1.0, 1.0, 1.0]])
+
+
+def test_data_side_restatements_match_reference():
+    """oracle/synth.py's prepare_input / get_rays / get_near_far / gen_path are pinned bit-for-bit to the outputs of the
+    reference's own functions (tests/golden/data_utils.npz, written by `python -m oracle.make_golden data`)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from oracle import synth
+    g = np.load(os.path.join(GOLDEN_DIR, "data_utils.npz"))
+    verts = synth.humanoid_vertices(313, synth.N_SMPL_VERTS, 1.0)
+    world = (verts.astype(np.float64) @ synth._rodrigues(g["Rh"]).T + g["Th_in"]).astype(np.float32)
+    np.testing.assert_array_equal(world, g["verts_world"])
+    coord, out_sh, can_bounds, bounds, R, Th = synth.prepare_input(world, g["Rh"], g["Th_in"], (0.005, 0.005, 0.005))
+    for k, v in (("coord", coord), ("out_sh", out_sh), ("can_bounds", can_bounds), ("bounds", bounds), ("Th", Th)):
+        np.testing.assert_array_equal(v, g[k], err_msg=k)
+    center = 0.5 * (can_bounds[0] + can_bounds[1]).astype(np.float64)
+    Ks, RTs = synth.training_cameras(center, n_cams=21, distance=3.0, H=64, W=64, f=70.0)
+    path = np.stack(synth.gen_path([m.copy() for m in RTs], num_render_views=144))
+    np.testing.assert_array_equal(path, g["gen_path"])
+    ro, rd = synth.get_rays(64, 64, Ks[3], RTs[3][:3, :3], RTs[3][:3, 3:4])
+    np.testing.assert_array_equal(np.ascontiguousarray(ro), g["rays_o"])
+    np.testing.assert_array_equal(rd, g["rays_d"])
+    near, far, mask = synth.get_near_far(can_bounds, ro.reshape(-1, 3).astype(np.float32), rd.reshape(-1, 3).astype(np.float32))
+    np.testing.assert_array_equal(mask, g["mask_at_box"])
+    np.testing.assert_array_equal(near.astype(np.float32), g["near"])
+    np.testing.assert_array_equal(far.astype(np.float32), g["far"])
+    assert 0 < int(mask.sum()) < mask.size
+    # lib/utils/render_utils.py:120-137 (image_rays) on a view of the spiral = get_rays + get_near_far + mask compaction
+    ro, rd = synth.get_rays(64, 64, Ks[0], path[17][:3, :3], path[17][:3, 3])
+    ro, rd = ro.reshape(-1, 3).astype(np.float32), rd.reshape(-1, 3).astype(np.float32)
+    near, far, mask = synth.get_near_far(can_bounds, ro, rd)
+    np.testing.assert_array_equal(mask, g["img_mask"])
+    np.testing.assert_array_equal(ro[mask], g["img_ray_o"])
+    np.testing.assert_array_equal(rd[mask], g["img_ray_d"])
+    np.testing.assert_array_equal(near.astype(np.float32), g["img_near"])
+    np.testing.assert_array_equal(far.astype(np.float32), g["img_far"])

@@ -76,8 +76,9 @@ def test_pack_weights_fold_matches_fp64_torch():
 
 
 def test_gen_rays_matches_reference_numpy():
-    """f-2: nb_gen_rays vs get_rays / get_near_far (restated literally in neuralbody_b200/synth.py)."""
-    from neuralbody_b200 import synth, rays
+    """f-2: nb_gen_rays vs get_rays / get_near_far (restated literally in oracle/synth.py)."""
+    from oracle import synth
+    from neuralbody_b200 import rays
     scene, _, _ = golden_case("eval_s64")
     cb = scene["can_bounds"][0].numpy()
     center = 0.5 * (cb[0] + cb[1]).astype(np.float64)

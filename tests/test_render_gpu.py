@@ -163,7 +163,7 @@ def test_full_size_properties():
     """512x512 x 64 samples on the full synth-313 body (config 2): properties that need no oracle
     run.  Empty rays give exact zeros and NaN disparity, weights sum to acc, acc in [0,1], and the
     result does not depend on how rays are grouped into launches (permutation invariance)."""
-    from neuralbody_b200 import synth
+    from oracle import synth
     scene = synth.make_scene(H=512, W=512, scale=1.0, all_hit=True)
     assert scene["ray_o"].shape[1] == 512 * 512
     net, ren = G.make_net_and_renderer(scene)
@@ -254,7 +254,7 @@ def test_hierarchical_render_matches_reference_pieces(name, precision):
 def test_sample_pdf_kernel_vs_oracle_random():
     """nb_sample_pdf alone on random weights / jitter / uniforms against oracle.importance_z_vals (no rendering involved)."""
     torch.manual_seed(5)
-    from neuralbody_b200 import synth
+    from oracle import synth
     scene = synth.make_scene(H=8, W=8, scale=0.25)
     net, ren = G.make_net_and_renderer(scene)
     B, n, S, Ni = 2, 300, 48, 77

@@ -72,7 +72,7 @@ def test_whole_network_matches_and_keeps_the_reference_parameter_tree():
 
 def test_network_hook_and_gradients():
     """Network.attach_dense_encoder(): encode_sparse_voxels works without spconv and gradients reach `c` and the conv weights."""
-    from neuralbody_b200 import synth
+    from oracle import synth
     from neuralbody_b200.lib.networks.latent_xyzc import Network
     from neuralbody_b200.lib.networks.renderer.if_nerf_renderer import Renderer
     scene = synth.make_scene(H=8, W=8, scale=0.12)

@@ -15,7 +15,7 @@ import torch  # noqa: E402
 def main():
     ni = int(sys.argv[1]) if len(sys.argv) > 1 else 128
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 30
-    from neuralbody_b200 import synth
+    from oracle import synth
     from neuralbody_b200.lib.config import cfg
     import gpu_utils as G
     scene = synth.make_scene(H=512, W=512, scale=1.0, all_hit=True)

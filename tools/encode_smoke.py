@@ -11,7 +11,7 @@ import torch  # noqa: E402
 
 
 def main():
-    from neuralbody_b200 import synth
+    from oracle import synth
     from neuralbody_b200.lib.config import cfg
     from neuralbody_b200.lib.networks.make_network import make_network
     from neuralbody_b200.lib.networks.renderer.make_renderer import make_renderer

@@ -22,7 +22,7 @@ def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "tc_fp16x3"
     first = int(sys.argv[2]) if len(sys.argv) > 2 else 6
     ntile = int(sys.argv[3]) if len(sys.argv) > 3 else 2
-    from neuralbody_b200 import synth
+    from oracle import synth
     from neuralbody_b200.lib.config import cfg
     import gpu_utils as G
     scene = synth.make_scene(H=512, W=512, scale=1.0, all_hit=True)
