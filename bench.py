@@ -189,7 +189,7 @@ def run_product(args, rank, world, local_rank):
     net = net.to(dev).eval()
     net.set_feature_volume([v.to(dev) for v in scene["volumes"]])
     ren = make_renderer(cfg, net)
-    ren.stats = torch.zeros(4, dtype=torch.int64, device=dev)   # tiles executed / occupied samples / decoder ns / decoder launches
+    ren.stats = torch.zeros(8, dtype=torch.int64, device=dev)   # tiles executed / occupied samples / decoder ns / decoder launches
 
     keys = ("coord", "out_sh", "bounds", "R", "Th", "latent_index", "ray_o", "ray_d", "near", "far")
     host = {k: scene[k].pin_memory() for k in keys}

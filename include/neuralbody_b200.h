@@ -140,7 +140,8 @@ typedef struct nb_render_args {
                               unoccupied have weight exactly 0 when sigma(empty) < 0; their MLP evaluation is skipped and `raw`,
                               if requested, holds (0, 0, 0, min(sigma_empty, 0)) for them instead of the decoder's rgb logits);
                               0 = every sample goes through the decoder (same maps bit for bit) */
-    unsigned long long* stats; /* device u64[4] or NULL: [0] += 128-sample tiles executed, [1] += occupied samples,
+    unsigned long long* stats; /* device u64[8] or NULL: [0] += 128-sample tiles executed, [1] += listed samples,
+                                  [4] += layer-0 K-steps executed by those tiles (8 / 16 / 20 / 22 per tile, see below),
                                   [2] += ns spent in the decoder kernel (%globaltimer, first CTA start to last CTA end) and
                                   [3] += decoder launches (tensor-core precisions) */
     float* save;           /* device (B,n,S,1312) activation record for nb_render_bwd, or NULL (NB_PRECISION_FP32 only);
@@ -149,7 +150,9 @@ typedef struct nb_render_args {
                                   (tensor-core kernel only; diagnostics, see tools/trace_timeline.py) */
     void*  workspace;      /* device scratch of nb_render_fwd_workspace_bytes() bytes; REQUIRED by the tensor-core precisions (NULL
                               is fine for NB_PRECISION_FP32).  The samples of a frame that need the decoder (all of them with
-                              skip_empty = 0) are compacted into one list and the decoder runs over full 128-sample tiles:
+                              skip_empty = 0) are compacted into four lists, one per finest occupied volume level, and the
+                              decoder runs over full 128-sample tiles; a tile whose samples see no occupied cell in the finer
+                              levels skips those levels' gather and layer-0 K-steps (exact: the features are zeros):
                               3 launches per frame (classify, decoder, composite) */
     size_t workspace_bytes;
     const float* z_vals;   /* device (B,n,S) or NULL.  When given, sample s of a ray sits at depth z_vals[b,r,s] (ascending) and
@@ -160,7 +163,8 @@ typedef struct nb_render_args {
 int nb_render_fwd(const nb_render_args* args, void* stream);
 
 /* Scratch bytes nb_render_fwd wants in nb_render_args.workspace for (batch, n_rays, n_samples): a 32-byte control block per
- * frame + one frame's sample list + one frame's raw records (16 B per sample each).  The buffer may be reused by
+ * frame + two list buffers (each holds two of the four class lists, growing towards each other) + one frame's raw records
+ * (16 B per sample each).  The buffer may be reused by
  * later calls on the same stream. */
 size_t nb_render_fwd_workspace_bytes(int batch, int n_rays, int n_samples);
 

@@ -251,7 +251,8 @@ __global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f3
             const int sl = i / 4096, n = (i / 16) % 256, kk = i % 16;
             if (sl < 2 * nks) {
                 const int ks = sl >> 1, lo = sl & 1;
-                const float x = W[(size_t)n * K + ks * 16 + kk];
+                const int k = ks * 16 + kk;
+                const float x = W[(size_t)n * K + (layer == 0 ? feat_tc_to_orig(k) : k)];
                 dst[step256_offset(ks, lo, nks) + step_offset(n, kk, 256)] = lo ? f16_lo(x) : f16_hi(x);
             } else {
                 dst[bias256_offset(nks) + step_offset(n, kk, 256)] =
@@ -468,7 +469,7 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
         return NB_ERR_BAD_ARG;
     }
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
-    p.frame = 0; p.list = nullptr; p.list_count = nullptr; p.frame_clock = nullptr; p.raw_ws = nullptr;
+    p.frame = 0; p.list_a = p.list_b = nullptr; p.list_cap = 0; p.list_count = nullptr; p.frame_clock = nullptr; p.raw_ws = nullptr;
 
     return NB_OK;
 }

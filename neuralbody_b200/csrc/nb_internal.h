@@ -36,7 +36,7 @@ struct RenderParams {
     const unsigned char* mask_msks; const float* mask_RT; const float* mask_Ks;   // f-1 mask views (null = none)
     int mask_nv, mask_H, mask_W;
     const float *mask_R0, *mask_Th0;   // single-view _msk variant: SMPL -> snapshot-world transform, or null
-    unsigned long long* stats; // u64[4] or null: [0] += tiles executed, [1] += listed samples,
+    unsigned long long* stats; // u64[8] or null: [4] += layer-0 K-steps executed (x 128 rows); [0] += tiles executed, [1] += listed samples,
                                // [2] += decoder-kernel ns, [3] += decoder launches
     float* save;               // (B,n,S,kSaveDim) activation record for nb_render_bwd (exact kernel only) or null
     int rays_per_group;        // rays handled together by one CTA work item
@@ -45,8 +45,12 @@ struct RenderParams {
     int groups_per_frame;
     // list pipeline (nb_render_tc_list.cu): one frame per launch
     int frame;                 // frame of this launch
-    float4* list;              // compact sample list: (world xyz, frame sample id | level bits << 28)
-    unsigned int* list_count;  // entries appended by classify_compact_kernel
+    // sample lists: entries (world xyz, frame sample id | level bits << 28), one list per sample CLASS (= finest occupied
+    // level, nb_layout.h class_segments).  Two buffers of list_cap entries hold two classes each, growing towards each other:
+    // class 3 from the start of A upwards, class 2 from the end of A downwards, class 1 / class 0 likewise in B.
+    float4 *list_a, *list_b;
+    size_t list_cap;
+    unsigned int* list_count;  // [4] entries per class, appended by classify_compact_kernel
     unsigned long long* frame_clock;   // [0] max(~start), [1] max(end) of the decoder launch (%globaltimer ns)
     float4* raw_ws;            // (n, S) raw records of this frame: (rgb logits, sigma)
 };

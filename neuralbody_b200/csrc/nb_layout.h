@@ -78,6 +78,17 @@ constexpr size_t sL3 = sL2 + (2 * kKsL12 + 1) * kStepHalves256;
 constexpr size_t sL4 = sL3 + kStepsL3 * kStepHalves3;      // (the common copy of L3's last step is unused)
 constexpr size_t kF16Halves = sL4 + kStepsL4 * kStepHalves4;
 
+// Layer-0 K order of the tensor-core kernel: COARSE LEVEL FIRST -- [level 3: 128 | level 2: 128 | level 1: 64 | level 0: 32]
+// (upstream's feature order, latent_xyzc.py:66-71, is level 0 first).  A tile whose rows have no occupied cell in the fine
+// levels then simply stops after the leading K segments: 2 / 4 / 5 / 6 segments of 64 channels for a finest occupied level of
+// 3 / 2 / 1 / 0.  Maps a K index of that order to the channel of fc_0's 352-wide input.
+__host__ __device__ inline int feat_tc_to_orig(int j) {
+    return j < 128 ? 224 + j : j < 256 ? 96 + (j - 128) : j < 320 ? 32 + (j - 256) : j - 320;
+}
+// layer-0 segments / K-steps a tile of sample class c (= finest occupied level) runs
+__host__ __device__ inline int class_segments(int c) { return c == 0 ? 6 : c == 1 ? 5 : c == 2 ? 4 : 2; }
+__host__ __device__ inline int class_ksteps(int c) { return c == 0 ? 22 : c == 1 ? 20 : c == 2 ? 16 : 8; }
+
 // N=256 layers: half-offset (from the layer base) of K-step ks, hi or lo plane, with nks K-steps in the layer
 __host__ __device__ inline size_t step256_offset(int ks, int lo, int nks) {
     const int g = ks >> 2;

@@ -1,9 +1,12 @@
 // The tensor-core render path: three launches over a frame's COMPACT SAMPLE LIST (nb_render_args.workspace).
 //
 //   1. classify_compact_kernel   every sample of the frame is classified with the four cell-occupancy bitmaps; occupied
-//                                samples are appended to the frame's list (one atomicAdd per 1024-sample block), the others
-//                                get their constant raw record (0, 0, 0, min(sigma_empty, 0)) at once.  With
-//                                skip_empty = 0 every sample is listed (dense evaluation through the same decoder).
+//                                samples are appended to the list of their CLASS = finest occupied level (one atomicAdd per
+//                                class and 1024-sample block), the others get their constant raw record
+//                                (0, 0, 0, min(sigma_empty, 0)) at once.  With skip_empty = 0 every sample is listed.
+//                                Layer 0 consumes the features coarse level first, so a class-c tile runs only the leading
+//                                2 / 4 / 5 / 6 of its six 64-channel K segments (gather AND MMAs): exact, the skipped
+//                                segments are all zeros.
 //   2. render_tc_list_kernel     the decoder MLP (latent_xyzc.py:91-126) over the list, 128 entries per tile, as a
 //                                warp-specialised tcgen05 pipeline (roles below).
 //   3. composite_kernel          raw2outputs (nerf_net_utils.py:6-51), one warp per ray.
@@ -39,11 +42,11 @@ constexpr int SLOT_BYTES = 4 * STEP_BYTES;
 constexpr int CHUNK_BYTES = 2048;
 constexpr int SEG_CHUNKS = 8;
 constexpr int NUM_SEGS = 6;
-// a layer-0 operand chunk (128 rows x 8 k) is 2048 B; the chunks of a segment are laid 2080 B apart (the K-direction
-// core-matrix stride LBO is a free descriptor field), which rotates successive chunks by 8 banks: the 4 rows x 8 channel
-// quads a producer warp stores per instruction then cover every bank exactly twice instead of 8 banks eight times
-constexpr int SEG_CHUNK_STRIDE = CHUNK_BYTES + 32;
-constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * SEG_CHUNK_STRIDE;  // 97.5 KB: 3 x (hi+lo) or 6 x hi
+// a layer-0 operand chunk (128 rows x 8 k) is 2048 B; the chunks of a segment are laid 2064 B apart (the K-direction
+// core-matrix stride LBO is a free descriptor field), which rotates successive chunks by 4 banks: the 4 rows (two apart) x 8
+// channel quads a producer warp stores per instruction then cover every bank exactly twice (256 B = two wavefronts)
+constexpr int SEG_CHUNK_STRIDE = CHUNK_BYTES + 16;
+constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * SEG_CHUNK_STRIDE;  // 96.75 KB: 3 x (hi+lo) or 6 x hi
 constexpr int MAX_SEG_BUFS = 6;
 constexpr int PE_CHUNKS = 12;
 constexpr int PROD_WARPS = 16, EPI_WARP0 = 16, EPI_WARPS = 4, MMA_WARP = 20, LOAD_WARP = 21;
@@ -55,6 +58,11 @@ constexpr int MAXS = 1024;                                         // samples pe
 #endif
 constexpr int CLUSTER = NB_LIST_CLUSTER;       // CTAs that share one weight stream through TMA multicast (all tiles cost the same)
 constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry .w = frame sample id | level bits << 28
+#ifndef NB_CORNER_BATCH
+#define NB_CORNER_BATCH 4
+#endif
+constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
+constexpr int L3_GROUP = 7;                                        // layer-3 K-steps per ring slot (7 x 4.5 KB)
 constexpr int L4_BYTES = kStepsL4 * (int)kStepHalves4 * 2;         // the rgb head's 9 N=16 steps stay resident (4.5 KB)
 
 // shared-memory map (bytes)
@@ -102,8 +110,9 @@ __device__ __forceinline__ void load_frame_xf(const RenderParams& P, FrameXf* xf
 constexpr int CLS_THREADS = 256, CLS_PER_THREAD = MAXS / CLS_THREADS;
 __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __grid_constant__ RenderParams P) {
     __shared__ FrameXf xf;
-    __shared__ int wcnt[MAXS / 32];
-    __shared__ unsigned int sbase;
+    __shared__ int wcnt[4][MAXS / 32];
+    __shared__ unsigned int sbase[4];
+    __shared__ int stotal[4];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = P.n_samples, b = P.frame;
     const int r0 = blockIdx.x * P.rays_per_group;
@@ -116,14 +125,14 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
     const uint32_t* occ_base = reinterpret_cast<const uint32_t*>(P.volume);
 
     float4 gm[CLS_PER_THREAD];
-    uint32_t bal[CLS_PER_THREAD];
-    bool live[CLS_PER_THREAD], occ[CLS_PER_THREAD];
+    int cls[CLS_PER_THREAD];                          // 0..3 = finest occupied level (list class), -1 = not listed
+    bool live[CLS_PER_THREAD];
 #pragma unroll
     for (int k = 0; k < CLS_PER_THREAD; ++k) {
         const int j = k * CLS_THREADS + tid;
         const int ry = j % P.rays_per_group, s = j / P.rays_per_group;
         live[k] = ry < nr && s < S;
-        occ[k] = false;
+        cls[k] = -1;
         gm[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live[k]) {
             const size_t ri = (size_t)b * P.n_rays + r0 + ry;
@@ -150,27 +159,40 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
                     }
                 }
             }
-            occ[k] = inside && (lm != 0u || !can_skip);
+            if (inside && (lm != 0u || !can_skip)) cls[k] = lm ? __ffs((int)lm) - 1 : 3;
             gm[k].w = __uint_as_float((uint32_t)((r0 + ry) * S + s) | (lm << 28));
         }
-        bal[k] = __ballot_sync(0xffffffffu, occ[k]);
-        if (lane == 0) wcnt[k * (CLS_THREADS / 32) + warp] = __popc(bal[k]);
+        const int slot = k * (CLS_THREADS / 32) + warp;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, cls[k] == c);
+            if (lane == 0) wcnt[c][slot] = __popc(bal);
+        }
     }
     __syncthreads();
-    int total = 0;
-#pragma unroll
-    for (int w = 0; w < MAXS / 32; ++w) total += wcnt[w];
-    if (tid == 0) sbase = total ? atomicAdd(P.list_count, (unsigned int)total) : 0u;
+    if (tid < 4) {                                    // one reservation per class: the block's entries of a class stay contiguous
+        int total = 0;
+        for (int w = 0; w < MAXS / 32; ++w) total += wcnt[tid][w];
+        stotal[tid] = total;
+        sbase[tid] = total ? atomicAdd(P.list_count + tid, (unsigned int)total) : 0u;
+    }
     __syncthreads();
     const float4 empty = make_float4(0.f, 0.f, 0.f, fminf(sigma_empty, 0.f));   // skipped sample: weight exactly 0
 #pragma unroll
     for (int k = 0; k < CLS_PER_THREAD; ++k) {
-        const int slot = k * (CLS_THREADS / 32) + warp;     // list order = sample-major order of the block
-        int base = 0;
-#pragma unroll
-        for (int w = 0; w < MAXS / 32; ++w) base += (w < slot) ? wcnt[w] : 0;
-        if (occ[k]) P.list[(size_t)sbase + base + __popc(bal[k] & ((1u << lane) - 1))] = gm[k];
-        else if (live[k]) P.raw_ws[__float_as_uint(gm[k].w) & ID_MASK] = empty;
+        const int slot = k * (CLS_THREADS / 32) + warp;     // list order = sample-major order of the block, per class
+        const int c = cls[k];
+        const uint32_t same = __match_any_sync(0xffffffffu, c);
+        if (c >= 0) {
+            int local = __popc(same & ((1u << lane) - 1));
+            for (int w = 0; w < slot; ++w) local += wcnt[c][w];
+            // classes 3 / 1 grow upwards from the start of their buffer, classes 2 / 0 downwards from its end
+            float4* buf = c >= 2 ? P.list_a : P.list_b;
+            const size_t at = (c & 1) ? (size_t)sbase[c] + local : P.list_cap - (size_t)sbase[c] - stotal[c] + local;
+            buf[at] = gm[k];
+        } else if (live[k]) {
+            P.raw_ws[__float_as_uint(gm[k].w) & ID_MASK] = empty;
+        }
     }
 }
 
@@ -213,49 +235,70 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     constexpr uint16_t CMASK = (1u << CLUSTER) - 1;
     const uint32_t tmem = *tmem_slot;
     if (tid == 0 && P.stats) atomicMax(P.frame_clock + 0, ~global_ns());     // min(start) over the CTAs, as max(~start)
-    const unsigned int n_rows_total = *P.list_count;                  // written by classify_compact_kernel (previous launch)
-    const int n_tiles = (int)((n_rows_total + TP - 1) / TP);
-    // a cluster walks the tiles in lockstep (shared weight stream): CTA r of cluster c takes tile c * CLUSTER + r of every
-    // round; a tile past the end is an empty one (nrows = 0) that keeps the peer's stream going.  Every role derives the
-    // same static schedule from the list length.
+    // The frame's work: per sample class c (heaviest first) ceil(count_c / 128) tiles, rounded up to whole clusters so that the
+    // CTAs of a cluster -- which walk the tiles in lockstep on one shared weight stream -- always work on the same class
+    // (padding tiles have 0 rows).  Every role derives the same static schedule from the four list lengths.
+    const unsigned int cc0 = P.list_count[0], cc1 = P.list_count[1], cc2 = P.list_count[2], cc3 = P.list_count[3];   // (previous launch)
+    auto padded_tiles = [](unsigned int n) { return (int)(((n + TP - 1) / TP + CLUSTER - 1) / CLUSTER * CLUSTER); };
+    const int ts1 = padded_tiles(cc0), ts2 = ts1 + padded_tiles(cc1), ts3 = ts2 + padded_tiles(cc2);
+    const int n_tiles = ts3 + padded_tiles(cc3);
     const int tile0 = (int)(blockIdx.x / CLUSTER) * CLUSTER;
-    auto rows_of = [&](int tile) { return tile < n_tiles ? min(TP, (int)(n_rows_total - (unsigned int)tile * TP)) : 0; };
+    struct TileRef { int cls, nrows; const float4* ent; };
+    auto tile_ref = [&](int tile) {
+        TileRef r;
+        r.cls = tile >= ts3 ? 3 : tile >= ts2 ? 2 : tile >= ts1 ? 1 : 0;
+        const int lt = tile - (r.cls == 3 ? ts3 : r.cls == 2 ? ts2 : r.cls == 1 ? ts1 : 0);
+        const unsigned int cnt = r.cls == 3 ? cc3 : r.cls == 2 ? cc2 : r.cls == 1 ? cc1 : cc0;
+        const long long rem = (long long)cnt - (long long)lt * TP;
+        r.nrows = rem <= 0 ? 0 : rem < TP ? (int)rem : TP;
+        const float4* buf = r.cls >= 2 ? P.list_a : P.list_b;
+        r.ent = buf + ((r.cls & 1) ? (size_t)0 : P.list_cap - (size_t)cnt) + (size_t)lt * TP;
+        return r;
+    };
 
     // ================================================================== PRODUCERS
     if (warp < PROD_WARPS) {
         const unsigned char* volbase = reinterpret_cast<const unsigned char*>(P.volume);
         const int grp = warp * 4 + (lane >> 3);
         const int t = lane & 7;
-        uint32_t it = 0;
+        uint32_t gseg = 0;                             // segments produced so far (ring position)
         Tracer tr;
         tr.init((warp == 0 && lane == 0) ? P.trace : nullptr, 0);
         const uint32_t seg_base = tc::smem_u32(smem + OFF_SEG);
-        const uint32_t so0 = (uint32_t)((t >> 1) * SEG_CHUNK_STRIDE + (grp >> 3) * 128 + (grp & 7) * 16 + (t & 1) * 8);
-        uint32_t real_tiles = 0;
+        // An 8-lane group owns the ADJACENT tile rows 2 grp and 2 grp + 1 (a warp: 8 consecutive rows); lane t owns channels
+        // 4t..4t+3 of every 32-channel unit, so one corner of one row is one contiguous 128-byte (fp32) run.  Consecutive list
+        // entries are the same depth sample of neighbouring rays, a few millimetres apart: at the coarser levels the two rows
+        // usually sit in the same trilinear cell, and the second row then reuses the corner vectors the first one loaded --
+        // the L1 wavefronts of the corner loads, not their latency, bound the gather.
+        const uint32_t so0 = (uint32_t)((t >> 1) * SEG_CHUNK_STRIDE + (grp >> 2) * 128 + (grp & 3) * 32 + (t & 1) * 8);
+        uint32_t real_tiles = 0, real_ksteps = 0;
         for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
-            const int tile = tbase + (int)crank;
-            const int nrows = rows_of(tile);
+            const TileRef tref = tile_ref(tbase + (int)crank);
+            const int nrows = tref.nrows, nseg = class_segments(tref.cls);
             real_tiles += nrows > 0;
+            real_ksteps += nrows > 0 ? class_ksteps(tref.cls) : 0;
             // the list entries of this thread's rows: grid coordinates + per-level occupancy bits
-            float4 g[PTS_PER_GROUP];
+            float gx[PTS_PER_GROUP], gy[PTS_PER_GROUP], gz[PTS_PER_GROUP];
+            uint32_t lvl_bits = 0;                     // bit (4 pp + l): row pp has an occupied cell at level l
 #pragma unroll
             for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
-                const int row = grp + 64 * pp;
-                g[pp] = make_float4(-4.f, -4.f, -4.f, 0.f);
+                const int row = 2 * grp + pp;
+                gx[pp] = gy[pp] = gz[pp] = -4.f;
                 if (row < nrows) {
-                    const float4 e = __ldg(P.list + (size_t)tile * TP + row);
-                    world_to_grid(*xf, e.x, e.y, e.z, g[pp].x, g[pp].y, g[pp].z);
-                    g[pp].w = __int_as_float((int)(__float_as_uint(e.w) >> 28));
+                    const float4 e = __ldg(tref.ent + row);
+                    world_to_grid(*xf, e.x, e.y, e.z, gx[pp], gy[pp], gz[pp]);
+                    lvl_bits |= (__float_as_uint(e.w) >> 28) << (4 * pp);
                 }
             }
             tr.ev(1);                                   // tile begin
-            uint32_t coff[PTS_PER_GROUP][8];
+            // per level and row: byte offset of the cell's low corner (clamped into the volume, see below) and the 8 corner weights
+            uint32_t cbase[PTS_PER_GROUP];
             float cw[PTS_PER_GROUP][8];
-            bool occupied[PTS_PER_GROUP];
-            const VT* vol = nullptr;
+            bool occ0 = false, occ1 = false, same_cell = false;
+            uint32_t dX = 0, dY = 0, dZ = 0;           // byte strides of the level's x / y / z neighbours
+            const unsigned char* lvl_ptr = nullptr;    // this lane's channels of voxel 0 of the level
             int cur_lvl = -1;
-            for (int seg = 0; seg < NUM_SEGS; ++seg) {
-                const uint32_t gseg = it * NUM_SEGS + seg;
+            for (int seg = 0; seg < nseg; ++seg, ++gseg) {
                 const uint32_t buf = gseg % NUM_SEG_BUFS;
                 tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1);
                 tr.ev(10 + seg);
@@ -263,49 +306,79 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 const uint32_t dst = seg_base + buf * SEG_BYTES + so0;
                 const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
                 for (int uu = 0; uu < nunits; ++uu) {
-                    const int unit = 2 * seg + uu;
+                    const int unit = 2 * seg + uu;              // coarse level first (nb_layout.h feat_tc_to_orig)
                     int lvl, c0;
-                    if (unit < 1) { lvl = 0; c0 = 0; }
-                    else if (unit < 3) { lvl = 1; c0 = (unit - 1) * 32; }
-                    else if (unit < 7) { lvl = 2; c0 = (unit - 3) * 32; }
-                    else { lvl = 3; c0 = (unit - 7) * 32; }
+                    if (unit < 4) { lvl = 3; c0 = unit * 32; }
+                    else if (unit < 8) { lvl = 2; c0 = (unit - 4) * 32; }
+                    else if (unit < 10) { lvl = 1; c0 = (unit - 8) * 32; }
+                    else { lvl = 0; c0 = 0; }
                     if (lvl != cur_lvl) {
                         cur_lvl = lvl;
                         const int C = P.lvl_C[lvl], D = P.lvl_D[lvl], H = P.lvl_H[lvl], W = P.lvl_W[lvl];
-                        vol = reinterpret_cast<const VT*>(volbase + P.lvl_off[lvl]) + (size_t)P.frame * P.lvl_bstride[lvl];
-                        // lane t of the row's 8-lane group sets up corner t; the group exchanges the 8 (weight, offset) pairs
-                        const int ddx = t & 1, ddy = (t >> 1) & 1, ddz = t >> 2;
+                        lvl_ptr = volbase + P.lvl_off[lvl] + ((size_t)P.frame * P.lvl_bstride[lvl] + 4 * t) * sizeof(VT);
+                        dX = (uint32_t)(C * sizeof(VT)); dY = dX * W; dZ = dY * H;
+                        int cell[PTS_PER_GROUP];
 #pragma unroll
                         for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
                             Corners cn;
-                            corner_setup(unnormalize(g[pp].x, W), unnormalize(g[pp].y, H), unnormalize(g[pp].z, D), W, H, D, cn);
-                            occupied[pp] = (__float_as_int(g[pp].w) >> lvl) & 1;
-                            const bool ok = occupied[pp] && corner_valid(cn, ddx, ddy, ddz, W, H, D);
-                            const float w_own = ok ? __fmul_rn(__fmul_rn(ddx ? cn.wx[1] : cn.wx[0], ddy ? cn.wy[1] : cn.wy[0]),
-                                                               ddz ? cn.wz[1] : cn.wz[0]) : 0.f;
-                            // byte offset of the corner vector inside this frame's level; corners that do not contribute
-                            // (out of range, unoccupied cell) point at voxel 0 and are never accumulated
-                            const uint32_t o_own = ok ? (uint32_t)((((cn.z0 + ddz) * H + (cn.y0 + ddy)) * W + (cn.x0 + ddx)) * C) * (uint32_t)sizeof(VT) : 0u;
+                            corner_setup(unnormalize(gx[pp], W), unnormalize(gy[pp], H), unnormalize(gz[pp], D), W, H, D, cn);
+                            cell[pp] = (cn.z0 * (H + 2) + cn.y0) * (W + 2) + cn.x0;
+                            // The 8 corners are addressed as (clamped low corner) + constant strides.  A cell that straddles the
+                            // volume boundary (index -1 or size-1 on an axis; zeros padding upstream) is shifted inside by one and
+                            // its in-range voxel's weight moves to the slot that now addresses it; the out-of-range slot gets 0.
+                            auto axis = [](int i0, int size, float (&w)[2]) {
+                                if (i0 < 0) { w[0] = w[1]; w[1] = 0.f; return 0; }                        // i0 == -1: only voxel 0
+                                if (i0 >= size) { w[0] = w[1] = 0.f; return size - 2; }                   // both neighbours outside
+                                if (i0 == size - 1) { w[1] = w[0]; w[0] = 0.f; return size - 2; }         // only voxel size-1
+                                return i0;
+                            };
+                            const int xc = axis(cn.x0, W, cn.wx), yc = axis(cn.y0, H, cn.wy), zc = axis(cn.z0, D, cn.wz);
+                            cbase[pp] = (uint32_t)((zc * H + yc) * W + xc) * dX;
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                cw[pp][c] = __shfl_sync(0xffffffffu, w_own, c, 8);
-                                coff[pp][c] = __shfl_sync(0xffffffffu, o_own, c, 8) + (uint32_t)(4 * t * sizeof(VT));
+                            for (int c = 0; c < 8; ++c)
+                                cw[pp][c] = __fmul_rn(__fmul_rn(cn.wx[c & 1], cn.wy[(c >> 1) & 1]), cn.wz[c >> 2]);
+                            if (cn.x0 == -2) cell[pp] = -1 - pp;          // out of the volume altogether (never marked occupied)
+                        }
+                        occ0 = (lvl_bits >> lvl) & 1;
+                        occ1 = (lvl_bits >> (4 + lvl)) & 1;
+                        // same cell => the same 8 corner voxels: row 1 reuses row 0's loads
+                        same_cell = occ0 && occ1 && cell[0] == cell[1];
+                    }
+                    // corner c of the cell = base + (c & 1) dX + ((c >> 1) & 1) dY + (c >> 2) dZ
+                    auto corner_off = [&](uint32_t base, int c) { return base + ((c & 1) ? dX : 0u) + ((c & 2) ? dY : 0u) + ((c & 4) ? dZ : 0u); };
+                    float acc[PTS_PER_GROUP][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                    const unsigned char* ub = lvl_ptr + (size_t)c0 * sizeof(VT);
+                    if (occ0) {
+#pragma unroll
+                        for (int h = 0; h < 8; h += CORNER_BATCH) {          // corners in batches (register budget)
+                            typename Quad<VT>::raw v[CORNER_BATCH];
+#pragma unroll
+                            for (int c = 0; c < CORNER_BATCH; ++c) v[c] = Quad<VT>::load_bytes(ub + corner_off(cbase[0], h + c));
+#pragma unroll
+                            for (int c = 0; c < CORNER_BATCH; ++c)
+                                if (cw[0][h + c] != 0.f) Quad<VT>::fma(acc[0], v[c], cw[0][h + c]);
+                            if (same_cell) {
+#pragma unroll
+                                for (int c = 0; c < CORNER_BATCH; ++c)
+                                    if (cw[1][h + c] != 0.f) Quad<VT>::fma(acc[1], v[c], cw[1][h + c]);
                             }
+                        }
+                    }
+                    if (occ1 && !same_cell) {
+#pragma unroll
+                        for (int h = 0; h < 8; h += CORNER_BATCH) {
+                            typename Quad<VT>::raw v[CORNER_BATCH];
+#pragma unroll
+                            for (int c = 0; c < CORNER_BATCH; ++c) v[c] = Quad<VT>::load_bytes(ub + corner_off(cbase[1], h + c));
+#pragma unroll
+                            for (int c = 0; c < CORNER_BATCH; ++c)
+                                if (cw[1][h + c] != 0.f) Quad<VT>::fma(acc[1], v[c], cw[1][h + c]);
                         }
                     }
 #pragma unroll
                     for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
-                        float a[4] = {0.f, 0.f, 0.f, 0.f};
-                        if (occupied[pp]) {
-                            const unsigned char* ub = reinterpret_cast<const unsigned char*>(vol + c0);   // warp-uniform
-                            typename Quad<VT>::raw v[8];
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) v[c] = Quad<VT>::load_bytes(ub + coff[pp][c]);
-#pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                if (cw[pp][c] != 0.f) Quad<VT>::fma(a, v[c], cw[pp][c]);
-                        }
-                        const uint32_t so = dst + (uint32_t)(uu * 4 * SEG_CHUNK_STRIDE + pp * 8 * 128);   // K-major core-matrix layout
+                        const float (&a)[4] = acc[pp];
+                        const uint32_t so = dst + (uint32_t)(uu * 4 * SEG_CHUNK_STRIDE + pp * 16);   // K-major core-matrix layout
                         if (NP == 3) {
                             // (hi, lo) split with a truncated hi: the residual is exact and costs one LOP3 + half an FADD2 a value
                             uint2 hi, lo;
@@ -328,11 +401,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 if (lane == 0) tc::mbar_arrive(&bars[BAR_SEG_FULL + buf]);
                 tr.ev(20 + seg);
             }
-            ++it;
         }
         if (tid == 0 && P.stats) {
             atomicAdd(P.stats + 0, (unsigned long long)real_tiles);
-            if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)n_rows_total);
+            atomicAdd(P.stats + 4, (unsigned long long)real_ksteps);
+            if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)cc0 + cc1 + cc2 + cc3);
         }
     }
     // ================================================================== LOADER
@@ -358,10 +431,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 ++cnt;
             };
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
+                const int l0_ksteps = class_ksteps(tile_ref(tbase).cls);      // both CTAs of the cluster: same class
                 for (int layer = 0; layer < 3; ++layer) {
                     const int nks = layer == 0 ? kKsL0 : kKsL12;
                     const unsigned char* base = seq + 2 * (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
-                    for (int g0 = 0; g0 < nks; g0 += 4) {
+                    for (int g0 = 0; g0 < (layer == 0 ? l0_ksteps : nks); g0 += 4) {
                         const int gs = (nks - g0) < 4 ? (nks - g0) : 4;
                         push(base + 2 * step256_offset(g0, 0, nks), gs * STEP_BYTES);
                         if (NP == 3) push(base + 2 * step256_offset(g0, 1, nks), gs * STEP_BYTES);
@@ -370,15 +444,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 }
                 const uint32_t sb = kStepHalves3 * 2;
                 const unsigned char* l3 = seq + sL3 * 2;
-                for (int g0 = 0; g0 < 20; g0 += 4) push(l3 + (size_t)g0 * sb, 4 * sb);
-                push(l3 + (size_t)20 * sb, sb, reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb, sb);
+                for (int g0 = 0; g0 < 21; g0 += L3_GROUP) push(l3 + (size_t)g0 * sb, L3_GROUP * sb);
+                push(reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb, sb);   // per-frame step 21
             }
         }
     }
     // ================================================================== MMA ISSUER
     else if (warp == MMA_WARP) {
         if (lane == 0) {
-            uint32_t cnt = 0, hphase = 0, it = 0;
+            uint32_t cnt = 0, hphase = 0, it = 0, gseg = 0;
             const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
             const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
             const uint32_t l4_addr = tc::smem_u32(smem + OFF_L4);
@@ -455,8 +529,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 tr.ev(1);
                 // ---- layer 0: A = gathered feature segments (shared memory), accumulator R0.  R0 held the previous tile's h2,
                 // whose last reader (its layer 3) was issued before: the tensor pipe executes in issue order.
-                for (int seg = 0; seg < NUM_SEGS; ++seg) {
-                    const uint32_t gseg = it * NUM_SEGS + seg;
+                const int nseg = class_segments(tile_ref(tbase).cls);
+                for (int seg = 0; seg < nseg; ++seg, ++gseg) {
                     const uint32_t buf = gseg % NUM_SEG_BUFS;
                     tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
                     tc::tc_fence_after();
@@ -486,26 +560,28 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 tr.ev(20);
                 layer256(TM_R0, TM_R1, 1);       // layer 1: h0 (R0) -> R1
                 layer256(TM_R1, TM_R0, 2);       // layer 2: h1 (R1) -> R0
-                // ---- layer 3: A = h2 (R0); accumulator R1[0..143]: 128 colour columns + alpha_fc hi / lo rows
-                for (int g = 0; g < 4; ++g) {
-                    wait_h(g);
-                    if (g == 0) tr.ev(33);
-                    wait_slot(slot);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t a = tmem + TM_R0 + 16 * (4 * g + i);
-                        tc::mma_ts(tmem + TM_R1, a, b_desc(slot, i, kN3), ID3, (g | i) != 0);
+                // ---- layer 3: A = h2 (R0); accumulator R1[0..143]: 128 colour columns + alpha_fc hi / lo rows.  K-steps 0..15
+                // over h2 (TMEM), 16..21 over the per-point tile (shared memory); 7 steps per weight slot
+                for (int k = 0; k < kStepsL3; ++k) {
+                    if (k % L3_GROUP == 0) {
+                        if (k) release_slot(slot);
+                        wait_slot(slot);
+                    }
+                    if (k < 16 && (k & 3) == 0) {
+                        wait_h(k >> 2);
+                        if (k == 0) tr.ev(33);
+                    }
+                    const int i = k % L3_GROUP;
+                    if (k < 16) {
+                        const uint32_t a = tmem + TM_R0 + 16 * k;
+                        tc::mma_ts(tmem + TM_R1, a, b_desc(slot, i, kN3), ID3, k != 0);
                         // the lo half of the activations only matters on the density path: rows 128..143 of the step (alpha_fc
                         // hi / lo + padding) -> accumulator columns 128..143; the 128 colour columns take the hi half alone
                         if (NP == 3) tc::mma_ts(tmem + TM_SIGMA, a + 8, b_desc_rows(slot, i, kN3, 128), ID4, true);
+                    } else {
+                        tc::mma_ss(tmem + TM_R1, a_desc(pe_addr, k - 16), b_desc(slot, i, kN3), ID3, true);
                     }
-                    release_slot(slot);
                 }
-                wait_slot(slot);
-                for (int i = 0; i < 4; ++i) tc::mma_ss(tmem + TM_R1, a_desc(pe_addr, i), b_desc(slot, i, kN3), ID3, true);
-                release_slot(slot);
-                wait_slot(slot);
-                for (int i = 0; i < 2; ++i) tc::mma_ss(tmem + TM_R1, a_desc(pe_addr, 4 + i), b_desc(slot, i, kN3), ID3, true);
                 release_slot(slot);
                 tc::mma_commit(&bars[BAR_ACC_FULL]);
                 tr.ev(23);
@@ -571,12 +647,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         };
 
         for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
-            const int tile = tbase + (int)crank;
-            const int nrows = rows_of(tile);
+            const TileRef tref = tile_ref(tbase + (int)crank);
             float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
             int smp = -1;
-            if (row < nrows) {
-                gm = __ldg(P.list + (size_t)tile * TP + row);
+            if (row < tref.nrows) {
+                gm = __ldg(tref.ent + row);
                 smp = (int)(__float_as_uint(gm.w) & ID_MASK);
             }
             const size_t ri = (size_t)P.frame * P.n_rays + (smp >= 0 ? smp / S : 0);
@@ -690,7 +765,7 @@ static cudaError_t launch_list(const RenderParams& p, int grid, cudaStream_t str
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-constexpr size_t CTL_BYTES = 32;   // per frame: u32 list count, pad, u64 ~start, u64 end
+constexpr size_t CTL_BYTES = 32;   // per frame: u32 list counts [4], u64 ~start, u64 end
 
 }  // namespace tcl
 
@@ -698,7 +773,7 @@ bool tc_available() { return true; }
 
 size_t render_tc_list_workspace_bytes(int batch, int n_rays, int n_samples) {
     const size_t per_frame = (size_t)n_rays * n_samples * sizeof(float4);
-    return tcl::align256((size_t)batch * tcl::CTL_BYTES) + 2 * tcl::align256(per_frame);
+    return tcl::align256((size_t)batch * tcl::CTL_BYTES) + 3 * tcl::align256(per_frame);   // control + 2 list buffers + raw records
 }
 
 bool render_tc_list_supported(const RenderParams& p) {
@@ -730,19 +805,21 @@ int launch_render_tc_list(const RenderParams& p_in, int volume_dtype, int passes
     const size_t per_frame = tcl::align256((size_t)p.n_rays * S * sizeof(float4));
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     float4* list = reinterpret_cast<float4*>(ws + tcl::align256((size_t)p.batch * tcl::CTL_BYTES));
-    float4* raw_ws = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(list) + per_frame);
+    float4* raw_ws = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(list) + 2 * per_frame);
     cudaError_t e = cudaMemsetAsync(ws, 0, (size_t)p.batch * tcl::CTL_BYTES, stream);
     if (e != cudaSuccess) { set_error("render_tc_list: memset failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
     // the tile count of a frame is only known on the device: size the grid for the worst case (every sample occupied)
-    const long long max_tiles = ((long long)p.n_rays * S + tcl::TP - 1) / tcl::TP;
+    const long long max_tiles = ((long long)p.n_rays * S + tcl::TP - 1) / tcl::TP + 4 * tcl::CLUSTER;
     int grid = (int)(max_tiles < sms ? max_tiles : sms);
     grid = (grid + tcl::CLUSTER - 1) / tcl::CLUSTER * tcl::CLUSTER;     // whole clusters; tiles past the end are no-ops
     if (grid > sms) grid = sms / tcl::CLUSTER * tcl::CLUSTER;
     for (int b = 0; b < p.batch; ++b) {
         p.frame = b;
-        p.list = list;
+        p.list_a = list;
+        p.list_b = reinterpret_cast<float4*>(reinterpret_cast<unsigned char*>(list) + per_frame);
+        p.list_cap = (size_t)p.n_rays * S;
         p.list_count = reinterpret_cast<unsigned int*>(ws + (size_t)b * tcl::CTL_BYTES);
-        p.frame_clock = reinterpret_cast<unsigned long long*>(ws + (size_t)b * tcl::CTL_BYTES + 8);
+        p.frame_clock = reinterpret_cast<unsigned long long*>(ws + (size_t)b * tcl::CTL_BYTES + 16);
         p.raw_ws = p_in.raw ? reinterpret_cast<float4*>(p_in.raw) + (size_t)b * p.n_rays * S : raw_ws;
         tcl::classify_compact_kernel<<<p.groups_per_frame, tcl::CLS_THREADS, 0, stream>>>(p);
         e = cudaGetLastError();

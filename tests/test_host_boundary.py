@@ -66,10 +66,11 @@ def test_size_queries_without_gpu(built_lib):
     # argument validation happens before any CUDA call
     assert lib.nb_render_fwd(None, None) < 0
     assert b"null" in lib.nb_last_error()
-    # scratch of the frame-compacting pipeline: a 32-byte control block per frame + 2 x 16 B per sample of ONE frame
+    # scratch of the tensor-core pipeline: a 32-byte control block per frame + 3 x 16 B per sample of ONE frame
+    # (two list buffers, each shared by two sample classes, + the raw records)
     ws = lib.nb_render_fwd_workspace_bytes
     per_frame = 512 * 512 * 64 * 16
-    assert ws(1, 512 * 512, 64) == 256 + 2 * per_frame and ws(3, 512 * 512, 64) == ws(1, 512 * 512, 64)
+    assert ws(1, 512 * 512, 64) == 256 + 3 * per_frame and ws(3, 512 * 512, 64) == ws(1, 512 * 512, 64)
     assert ws(0, 10, 10) == 0 and ws(1, 1000, 192) >= 2 * 1000 * 192 * 16
     # f-4: nb_sample_pdf validates its sizes before it touches the device
     a = capi.nb_importance_args()

@@ -69,7 +69,7 @@ def test_empty_sample_skipping_is_bit_exact(name, precision):
     with skip_empty = 0 lists EVERY sample and produces identical maps."""
     scene, rkw, _ = golden_case(name)
     net, ren = G.make_net_and_renderer(scene)
-    ren.stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ren.stats = torch.zeros(8, dtype=torch.int64, device="cuda")
     B, n = scene["ray_o"].shape[:2]
     S = rkw["n_samples"]
     dense = G.render_product(scene, precision=precision, skip_empty=False, renderer=ren, net=net, **rkw)
@@ -127,7 +127,7 @@ def test_long_rays():
         sub[k] = scene[k][:, :64].contiguous()
     ref = O.render(sub, n_samples=192)
     net, ren = G.make_net_and_renderer(sub)
-    ren.stats = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ren.stats = torch.zeros(8, dtype=torch.int64, device="cuda")
     out = G.render_product(sub, precision="tc_fp16x3", n_samples=192, renderer=ren, net=net)
     assert int(ren.stats[3]) == 1 and int(ren.stats[0]) > 0          # one decoder launch of the list pipeline ran
     for k in ("rgb_map", "depth_map", "acc_map"):
