@@ -41,6 +41,8 @@ FLOP_PER_SAMPLE_FOLDED = 532224         # exact fold of feature_fc o latent_fc o
 # lo half of its input only on the 16-row density block)
 FLOP_PER_SAMPLE_ISSUED = {"tc_fp16": 2 * 16 * (23 * 256 + 2 * 17 * 256 + 22 * 144 + 9 * 16),
                           "tc_fp16x3": 2 * 16 * (67 * 256 + 2 * 49 * 256 + 22 * 144 + 16 * 16 + 9 * 16), "fp32": 532224}
+FLOP_L0_PER_KSTEP = 2 * 16 * 256        # algorithmic FLOPs of one layer-0 K-step (16 of fc_0's 352 inputs), per sample
+FLOP_BEYOND_L0 = FLOP_PER_SAMPLE_FOLDED - 22 * FLOP_L0_PER_KSTEP
 METRIC = "rays_per_s_512x512_64spp"
 
 
@@ -293,11 +295,18 @@ def run_product(args, rank, world, local_rank):
     if precision != "fp32" and kernel_launches:
         # only EXECUTED work is credited: 128-row tiles the kernel actually ran (padding rows included), per launch
         samples_per_launch = stats[0] * 128 / kernel_launches
+    # layer-0 K-steps the executed tiles actually ran (a tile whose samples see only coarse levels skips the fine levels'
+    # K-steps; those multiply exact zeros upstream and are NOT credited): 8 / 16 / 20 / 22 of 22 per tile
+    l0_ksteps = (stats[4] / max(1, stats[0])) if (precision != "fp32" and stats[0]) else 22.0
+    flop_exec = FLOP_BEYOND_L0 + l0_ksteps * FLOP_L0_PER_KSTEP
+    issued = FLOP_PER_SAMPLE_ISSUED[precision]
+    if precision != "fp32":
+        issued -= 2 * 16 * 256 * (3 if precision == "tc_fp16x3" else 1) * (22.0 - l0_ksteps)
     if kernel_ms:
-        tflops_exec = samples_per_launch * FLOP_PER_SAMPLE_FOLDED / (kernel_ms * 1e-3) / 1e12
+        tflops_exec = samples_per_launch * flop_exec / (kernel_ms * 1e-3) / 1e12
         tflops_written = samples_per_launch * FLOP_PER_SAMPLE_AS_WRITTEN / (kernel_ms * 1e-3) / 1e12
     else:
-        tflops_exec = value * S * FLOP_PER_SAMPLE_FOLDED / world / 1e12
+        tflops_exec = value * S * flop_exec / world / 1e12
         tflops_written = value * S * FLOP_PER_SAMPLE_AS_WRITTEN / world / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % precision)
@@ -308,13 +317,13 @@ def run_product(args, rank, world, local_rank):
         "frac": tflops_exec / peaks["tf_sustained"], "traffic": traffic,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (%s)" % peaks["src"],
         "frac_of_burst": tflops_exec / peaks["tf_burst"],
-        "flop_per_sample_executed": FLOP_PER_SAMPLE_FOLDED,
-        "note": "achieved/frac count only the ALGORITHMIC folded FLOPs (532224/sample); precision-emulation passes, "
-                "bias K-steps and padding rows the tensor pipe also executes are reported separately below",
-        "tensor_flop_per_sample_issued": FLOP_PER_SAMPLE_ISSUED[precision],
-        "tensor_tflops_issued": (tflops_exec * FLOP_PER_SAMPLE_ISSUED[precision] / FLOP_PER_SAMPLE_FOLDED),
-        "tensor_issued_frac_of_sustained": (tflops_exec * FLOP_PER_SAMPLE_ISSUED[precision] / FLOP_PER_SAMPLE_FOLDED)
-                                           / peaks["tf_sustained"],
+        "flop_per_sample_executed": flop_exec, "layer0_ksteps_per_tile": l0_ksteps,
+        "note": "achieved/frac count only the ALGORITHMIC folded FLOPs of executed work (532224/sample minus the layer-0 "
+                "K-steps a tile skipped); precision-emulation passes, bias K-steps and padding rows the tensor pipe also "
+                "executes are reported separately below",
+        "tensor_flop_per_sample_issued": issued,
+        "tensor_tflops_issued": (tflops_exec * issued / flop_exec),
+        "tensor_issued_frac_of_sustained": (tflops_exec * issued / flop_exec) / peaks["tf_sustained"],
         "achieved_if_counted_as_written": tflops_written,
         "kernel": ("render_tc_list_kernel<%d>" % (3 if precision == "tc_fp16x3" else 1)) if precision != "fp32"
                   else "render_f32_kernel (fp32 FFMA pipe, no tensor cores)",

@@ -23,6 +23,6 @@ try:
 except Exception as e:
     print("bench parse failed", e)
 PY
-timeout 300 python tools/trace_timeline.py tc_fp16x3 40 2 list > gpurun_out/${tag}_trace.txt 2> gpurun_out/${tag}_trace.err
+timeout 300 python tools/trace_timeline.py tc_fp16x3 40,100,200,280 1 > gpurun_out/${tag}_trace.txt 2> gpurun_out/${tag}_trace.err
 echo "trace rc=$?"
-tail -3 gpurun_out/${tag}_trace.txt
+tail -12 gpurun_out/${tag}_trace.txt

@@ -20,7 +20,7 @@ EPI = {1: "tile begin", 2: "PE written", 10: "acc L0", 11: "acc L1", 12: "acc L2
 
 def main():
     prec = sys.argv[1] if len(sys.argv) > 1 else "tc_fp16x3"
-    first = int(sys.argv[2]) if len(sys.argv) > 2 else 6
+    firsts = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [6]
     ntile = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     from oracle import synth
     from neuralbody_b200.lib.config import cfg
@@ -52,18 +52,25 @@ def main():
                 tile += 1
             events.append((clk, name, tile, names.get(code, str(code))))
     events.sort()
-    sel = [e for e in events if first <= e[2] < first + ntile]
-    t0 = sel[0][0]
-    last = {}
-    for clk, name, tile, what in sel:
-        d = clk - last.get(name, clk)
-        last[name] = clk
-        print("%9d  (+%6d)  %-5s tile %-3d %s" % (clk - t0, d, name, tile, what))
+    for first in firsts:
+        sel = [e for e in events if first <= e[2] < first + ntile]
+        if not sel:
+            continue
+        t0 = sel[0][0]
+        last = {}
+        print("---- tiles %d..%d of CTA 0" % (first, first + ntile - 1))
+        for clk, name, tile, what in sel:
+            d = clk - last.get(name, clk)
+            last[name] = clk
+            print("%9d  (+%6d)  %-5s tile %-3d %s" % (clk - t0, d, name, tile, what))
     # per-tile period of the MMA role
     begins = [e[0] for e in events if e[1] == "MMA" and e[3] == "tile begin"]
     if len(begins) > 3:
         per = [b - a for a, b in zip(begins[:-1], begins[1:])]
         print("MMA tile period (cycles): mean %.0f  min %d  max %d  over %d tiles" % (sum(per) / len(per), min(per), max(per), len(per)))
+        for lo in range(0, len(per), 40):
+            chunk = per[lo:lo + 40]
+            print("  tiles %3d..%3d: mean period %.0f" % (lo, lo + len(chunk) - 1, sum(chunk) / len(chunk)))
 
 
 if __name__ == "__main__":
