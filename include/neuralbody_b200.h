@@ -125,6 +125,10 @@ typedef struct nb_render_args {
     float* weights;        /* device (B,n,S) or NULL to skip */
     float* depth_map;      /* device (B,n)   */
     float* raw;            /* device (B,n,S,4) decoder output (rgb logits, sigma) or NULL; debugging / parity */
+    int   out_ray_stride;  /* 0: rgb_map / disp_map / acc_map / depth_map are dense arrays ((B,n,3) and (B,n)).  > 0: floats
+                              between consecutive rays in EACH of the four maps, so that they can be columns of one fused
+                              (B,n,stride) record -- e.g. the 24-byte [rgb | disp | acc | depth] slab a ray-sharded render
+                              all-gathers (stride 6, pointers slab+0, +3, +4, +5) */
     /* f-1, masked renderers (if_clight_renderer_mmsk.py:12-45; B = 1 only, as upstream): a sample is evaluated only if it
        projects into the foreground of every mask view; elsewhere raw = 0.  mask_msks NULL => no masking */
     const unsigned char* mask_msks;  /* device (nv, mask_H, mask_W) uint8 */
@@ -211,6 +215,14 @@ typedef struct nb_camera {
 int nb_gen_rays(const nb_camera* cam, float* ray_o /* device (H*W,3) */, float* ray_d /* device (H*W,3) */,
                 float* near /* device (H*W) */, float* far /* device (H*W) */, unsigned char* mask_at_box /* device (H*W) */,
                 void* stream);
+/* Same arithmetic for ONE RANK'S SHARD of a ray-sharded render: pixel chunk c (of `chunk` consecutive pixels)
+ * belongs to rank c % world; local ray j of rank `rank` is pixel ((j / chunk) * world + rank) * chunk + j % chunk.  Writes
+ * n_local rays with a FIXED shape (no mask compaction, so nothing synchronises with the host): a ray that misses the box --
+ * upstream drops it, image_rays :131-132 -- or lies past the last pixel becomes a dead ray (near = far = 0: every sample
+ * sits at the camera centre, outside the volume, and is skipped) with mask_at_box = 0. */
+int nb_gen_rays_sharded(const nb_camera* cam, int rank, int world, int chunk, int n_local,
+                        float* ray_o /* device (n_local,3) */, float* ray_d, float* near, float* far,
+                        unsigned char* mask_at_box /* device (n_local) */, void* stream);
 
 /* number of kernels nb_render_fwd enqueues per FRAME of a call: 1 for NB_PRECISION_FP32 (the single fused exact kernel),
  * 3 for the tensor-core precisions (classify, decoder, composite; plus one 32-byte memset per call). */
@@ -250,6 +262,12 @@ int    nb_render_bwd(const nb_render_bwd_args* args, void* stream);
  * d1_out fp32 [128][64].  variant bit0 swaps the descriptor's LBO/SBO, bit1 the fp16 pair order. */
 int nb_debug_tc_probe(const void* a0, const void* w0_packed, const void* w1_packed, float* d0_out, float* d1_out,
                       int variant, void* stream);
+/* The same idea for a CTA PAIR (tcgen05 cta_group::2, see csrc/nb_tc_probe2.cu): one 256-row tile, 128 rows per CTA of a
+ * 2-cluster, every B operand split by N halves across the two CTAs.  a0: device fp16 [256][64]; w0_halves: fp16 [2][128 x 80]
+ * packed (rank r holds rows 128 r .. of the 256 x 80 matrix, columns 64/65 = bias hi/lo); w1_halves: fp16 [2][72 x 128] packed;
+ * d0_out fp32 [256][256]; d1_out fp32 [256][144] (= relu(d0[:, :128]) w1^T, plus a second accumulation of each half's local
+ * rows 64..71 into columns 64..79). */
+int nb_debug_tc_probe2(const void* a0, const void* w0_halves, const void* w1_halves, float* d0_out, float* d1_out, void* stream);
 
 #ifdef __cplusplus
 }

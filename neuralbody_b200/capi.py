@@ -13,8 +13,8 @@ NB_NUM_LEVELS = 4
 
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
-           "nb_render_fwd_launches", "nb_render_fwd_workspace_bytes", "nb_debug_tc_probe", "nb_render_bwd", "nb_render_save_bytes",
-           "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays", "nb_sample_pdf"]
+           "nb_render_fwd_launches", "nb_render_fwd_workspace_bytes", "nb_debug_tc_probe", "nb_debug_tc_probe2", "nb_render_bwd", "nb_render_save_bytes",
+           "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays", "nb_gen_rays_sharded", "nb_sample_pdf"]
 
 
 class nb_volume_level(C.Structure):
@@ -47,7 +47,7 @@ class nb_render_args(C.Structure):
         ("weights_blob", C.c_void_p),
         ("white_bkgd", C.c_int), ("precision", C.c_int),
         ("rgb_map", C.c_void_p), ("disp_map", C.c_void_p), ("acc_map", C.c_void_p), ("weights", C.c_void_p),
-        ("depth_map", C.c_void_p), ("raw", C.c_void_p),
+        ("depth_map", C.c_void_p), ("raw", C.c_void_p), ("out_ray_stride", C.c_int),
         ("mask_msks", C.c_void_p), ("mask_RT", C.c_void_p), ("mask_Ks", C.c_void_p),
         ("mask_nv", C.c_int), ("mask_H", C.c_int), ("mask_W", C.c_int), ("mask_R0", C.c_void_p), ("mask_Th0", C.c_void_p),
         ("skip_empty", C.c_int), ("stats", C.c_void_p), ("save", C.c_void_p),
@@ -114,10 +114,14 @@ def load(path=None):
     lib.nb_decode_density.argtypes = [C.POINTER(nb_render_args), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.nb_gen_rays.restype = C.c_int
     lib.nb_gen_rays.argtypes = [C.POINTER(nb_camera)] + [C.c_void_p] * 6
+    lib.nb_gen_rays_sharded.restype = C.c_int
+    lib.nb_gen_rays_sharded.argtypes = [C.POINTER(nb_camera)] + [C.c_int] * 4 + [C.c_void_p] * 6
     lib.nb_sample_pdf.restype = C.c_int
     lib.nb_sample_pdf.argtypes = [C.POINTER(nb_importance_args), C.c_void_p]
     lib.nb_debug_tc_probe.restype = C.c_int
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
+    lib.nb_debug_tc_probe2.restype = C.c_int
+    lib.nb_debug_tc_probe2.argtypes = [C.c_void_p] * 6
     if lib.nb_abi_version() != 3:
         raise RuntimeError("libneuralbody_b200.so ABI version mismatch")
     if path in (_build.LIB_PATH, os.environ.get("NB_LIB_PATH")):

@@ -32,6 +32,7 @@ struct RenderParams {
     int white_bkgd;
     int skip_empty;            // tensor-core path: 1 = samples with all-zero features and sigma(empty) < 0 are not evaluated
     float *rgb_map, *disp_map, *acc_map, *weights, *depth_map, *raw;
+    int rgb_stride, map_stride;   // floats between consecutive rays in rgb_map / in the three scalar maps (3 / 1 when dense)
     unsigned long long* trace;
     const unsigned char* mask_msks; const float* mask_RT; const float* mask_Ks;   // f-1 mask views (null = none)
     int mask_nv, mask_H, mask_W;

@@ -342,12 +342,12 @@ __global__ void __launch_bounds__(NT, 1) render_f32_kernel(const __grid_constant
             }
             if (lane == 0) {
                 float add = P.white_bkgd ? __fsub_rn(1.f, o.acc) : 0.f;
-                P.rgb_map[ri * 3 + 0] = o.r + add;
-                P.rgb_map[ri * 3 + 1] = o.g + add;
-                P.rgb_map[ri * 3 + 2] = o.b + add;
-                P.depth_map[ri] = o.depth;
-                P.acc_map[ri] = o.acc;
-                P.disp_map[ri] = disparity(o.depth, o.acc);
+                P.rgb_map[ri * P.rgb_stride + 0] = o.r + add;
+                P.rgb_map[ri * P.rgb_stride + 1] = o.g + add;
+                P.rgb_map[ri * P.rgb_stride + 2] = o.b + add;
+                P.depth_map[ri * P.map_stride] = o.depth;
+                P.acc_map[ri * P.map_stride] = o.acc;
+                P.disp_map[ri * P.map_stride] = disparity(o.depth, o.acc);
             }
         }
         __syncthreads();

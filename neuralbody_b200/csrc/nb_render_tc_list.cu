@@ -738,12 +738,12 @@ __global__ void __launch_bounds__(COMP_WARPS * 32) composite_kernel(const __grid
     RayOut o = composite_ray(P.raw_ws + (size_t)ray * S, zs[warp], S, nrm, wout, lane);
     if (lane == 0) {
         const float add = P.white_bkgd ? __fsub_rn(1.f, o.acc) : 0.f;
-        P.rgb_map[rg * 3 + 0] = o.r + add;
-        P.rgb_map[rg * 3 + 1] = o.g + add;
-        P.rgb_map[rg * 3 + 2] = o.b + add;
-        P.depth_map[rg] = o.depth;
-        P.acc_map[rg] = o.acc;
-        P.disp_map[rg] = disparity(o.depth, o.acc);
+        P.rgb_map[rg * P.rgb_stride + 0] = o.r + add;
+        P.rgb_map[rg * P.rgb_stride + 1] = o.g + add;
+        P.rgb_map[rg * P.rgb_stride + 2] = o.b + add;
+        P.depth_map[rg * P.map_stride] = o.depth;
+        P.acc_map[rg * P.map_stride] = o.acc;
+        P.disp_map[rg * P.map_stride] = disparity(o.depth, o.acc);
     }
 }
 

@@ -153,6 +153,72 @@ __device__ __forceinline__ void mma_commit_multicast(uint64_t* bar, uint16_t cta
                  : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster (ranks 0 / 1, same TPC) execute ONE MMA of M = 256: each CTA's tensor core computes its own 128 rows
+// (A and the accumulator are CTA-local, at the same shared-memory / TMEM addresses in both CTAs) against the WHOLE B operand,
+// of which each CTA holds one half of the N rows in its own shared memory (rank 0: rows [0, N/2), rank 1: rows [N/2, N)).
+// Only the leader (rank 0) issues; completion is signalled to both CTAs with a multicast commit.
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result) {       // the same warp id in BOTH CTAs calls this
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void mma_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+// all MMAs this thread issued so far have completed in both CTAs -> arrive(1) on the mbarrier at this offset in every CTA of the mask
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
+// shared::cluster address of `local` (a shared::cta address of this CTA) in the CTA of rank `cta`
+__device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(cta));
+    return r;
+}
+// arrive(1) on an mbarrier of another CTA of the cluster (release at cluster scope: what this thread wrote before -- and
+// fenced to the async proxy -- is visible to whoever observes the phase flip with an acquire.cluster wait)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// wait on a LOCAL mbarrier that CTAs of the whole cluster arrive on
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t probes = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++probes > NB_WATCHDOG_PROBES) __trap();
+    }
+}
+
 // ---------------------------------------------------------------- TMEM <-> registers (warp w owns lanes 32*(w%4)..+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

@@ -273,6 +273,21 @@ class Renderer:
         if t is not None:
             self.__dict__.setdefault("_pool", {}).setdefault((tag, t.dtype, str(t.device)), []).append(t)
 
+    @staticmethod
+    def _out_stride(out, B, n):
+        """0 for dense output maps; the common ray stride (floats) when the caller's `out` tensors are columns of one fused
+        (B,n,stride) record, e.g. the [rgb | disp | acc | depth] slab of neuralbody_b200.dist (nb_render_args.out_ray_stride)."""
+        rgb = out['rgb_map']
+        if rgb.is_contiguous() and all(out[k].is_contiguous() for k in ('disp_map', 'acc_map', 'depth_map')):
+            return 0
+        st = int(rgb.stride(1))
+        ok = tuple(rgb.shape) == (B, n, 3) and rgb.stride(2) == 1 and rgb.stride(0) == st * n and all(
+            tuple(out[k].shape) == (B, n) and out[k].stride(1) == st and out[k].stride(0) == st * n
+            for k in ('disp_map', 'acc_map', 'depth_map'))
+        if not ok:
+            raise ValueError("`out` maps must be dense, or columns of one (B, n, stride) float32 record")
+        return st
+
     def _workspace(self, nbytes, dev):
         """Scratch for nb_render_fwd, grown on demand and reused by every later call on this device's stream."""
         cache = self.__dict__.setdefault("_ws_cache", {})
@@ -327,6 +342,7 @@ class Renderer:
             a.precision = precision
             a.rgb_map, a.disp_map = out['rgb_map'].data_ptr(), out['disp_map'].data_ptr()
             a.acc_map, a.depth_map = out['acc_map'].data_ptr(), out['depth_map'].data_ptr()
+            a.out_ray_stride = self._out_stride(out, B, n)
             a.weights = out['weights'].data_ptr() if 'weights' in out else None
             a.raw = raw.data_ptr() if raw is not None else None
             a.save = sv.data_ptr() if sv is not None else None
