@@ -30,17 +30,21 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source of the package for sm_100a (one nvcc per file, in parallel) and link one shared library."""
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA source of the package for sm_100a (one nvcc per file, in parallel) and link one shared library.
+    `defines` / `out`: an A/B variant (e.g. defines=("NB_LIST_CLUSTER=1",), out="libnb_c1.so" -> select it with NB_LIB_PATH)."""
+    if out is None and not force and not _stale():
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
     nvcc = find_nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj_dir = OBJ_DIR if out is None else OBJ_DIR + "_" + os.path.splitext(out)[0]
+    lib_path = LIB_PATH if out is None else os.path.join(HERE, out)
+    os.makedirs(obj_dir, exist_ok=True)
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-c", "-o", obj, os.path.join(CSRC, src)]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
@@ -51,7 +55,7 @@ def build(force=False, verbose=False):
     if verbose:
         for _, log in done:
             print(log)
-    res = subprocess.run([nvcc, "--shared", "-o", LIB_PATH] + [o for o, _ in done], capture_output=True, text=True)
+    res = subprocess.run([nvcc, "--shared", "-o", lib_path] + [o for o, _ in done], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
-    return LIB_PATH
+    return lib_path

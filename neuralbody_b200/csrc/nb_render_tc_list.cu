@@ -62,7 +62,11 @@ constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry
 #define NB_CORNER_BATCH 4
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
-constexpr int L3_GROUP = 7;                                        // layer-3 K-steps per ring slot (7 x 4.5 KB)
+#ifndef NB_L3_GROUP
+#define NB_L3_GROUP 4
+#endif
+constexpr int L3_GROUP = NB_L3_GROUP;                             // layer-3 K-steps per ring slot (<= 7: 4.5 KB each)
+static_assert(L3_GROUP >= 1 && L3_GROUP <= 7, "a slot holds at most 7 layer-3 steps");
 constexpr int L4_BYTES = kStepsL4 * (int)kStepHalves4 * 2;         // the rgb head's 9 N=16 steps stay resident (4.5 KB)
 
 // shared-memory map (bytes)
@@ -444,8 +448,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 }
                 const uint32_t sb = kStepHalves3 * 2;
                 const unsigned char* l3 = seq + sL3 * 2;
-                for (int g0 = 0; g0 < 21; g0 += L3_GROUP) push(l3 + (size_t)g0 * sb, L3_GROUP * sb);
-                push(reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb, sb);   // per-frame step 21
+                // steps 0..20 from the common stream in groups of L3_GROUP, the per-frame step 21 closes the last group
+                for (int g0 = 0; g0 < kStepsL3; g0 += L3_GROUP) {
+                    const int common = min(L3_GROUP, kStepsL3 - 1 - g0), last = g0 + L3_GROUP >= kStepsL3;
+                    const unsigned char* fr = reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb;
+                    if (common > 0) push(l3 + (size_t)g0 * sb, common * sb, last ? fr : nullptr, last ? sb : 0);
+                    else push(fr, sb);
+                }
             }
         }
     }
