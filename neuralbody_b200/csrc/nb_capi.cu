@@ -265,7 +265,7 @@ __global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f3
                               __half* __restrict__ seq, __half* __restrict__ frame_steps) {
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    // L0 / L1 / L2: N = 256; (hi, lo) planes grouped by 4 K-steps, then the bias step (see nb_layout.h)
+    // L0 / L1 / L2: N = 256, stored per CTA half (pair layout, nb_layout.h): (hi, lo) planes grouped by 4 K-steps, then the bias step
     for (int layer = 0; layer < 3; ++layer) {
         const int K = layer == 0 ? kFeat : kHidden;
         const int nks = K / 16;
@@ -274,33 +274,37 @@ __global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f3
         __half* dst = seq + (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
         for (int i = t0; i < (2 * nks + 1) * 256 * 16; i += stride) {
             const int sl = i / 4096, n = (i / 16) % 256, kk = i % 16;
+            const int half = n >> 7, nl = n & 127;
             if (sl < 2 * nks) {
                 const int ks = sl >> 1, lo = sl & 1;
                 const int k = ks * 16 + kk;
                 const float x = W[(size_t)n * K + (layer == 0 ? feat_tc_to_orig(k) : k)];
-                dst[step256_offset(ks, lo, nks) + step_offset(n, kk, 256)] = lo ? f16_lo(x) : f16_hi(x);
+                dst[pair_step_offset(ks, lo, half, nks) + step_offset(nl, kk, 128)] = lo ? f16_lo(x) : f16_hi(x);
             } else {
-                dst[bias256_offset(nks) + step_offset(n, kk, 256)] =
+                dst[pair_bias_offset(half, nks) + step_offset(nl, kk, 128)] =
                     kk == 0 ? f16_hi(Bv[n]) : kk == 1 ? f16_lo(Bv[n]) : __float2half_rn(0.f);
             }
         }
     }
-    // L3: N = 144.  common steps 0..20 -> seq, per-frame step 21 -> frame_steps[b]
+    // L3: N = 144 as two 72-row halves.  common steps 0..20 -> seq, per-frame step 21 -> frame_steps[b][half]
     for (int i = t0; i < (kStepsL3 - 1 + w.batch) * kN3 * 16; i += stride) {
         int st = i / (kN3 * 16);
-        const int n = (i / 16) % kN3, kk = i % 16;
+        const int r = (i / 16) % kN3, kk = i % 16;
+        const int half = r / (kN3 / 2), nl = r % (kN3 / 2);
+        // row of the logical 144-row layer this (half, local row) holds: colour row, alpha hi (128), alpha lo (129) or none (-1)
+        const int n = nl < 64 ? half * 64 + nl : (half == 0 && nl == 64) ? 128 : (half == 0 && nl == 65) ? 129 : -1;
         int b = 0;
         __half* dst;
-        if (st >= kStepsL3 - 1) { b = st - (kStepsL3 - 1); st = kStepsL3 - 1; dst = frame_steps + (size_t)b * kStepHalves3; }
-        else dst = seq + sL3 + (size_t)st * kStepHalves3;
+        if (st >= kStepsL3 - 1) { b = st - (kStepsL3 - 1); st = kStepsL3 - 1; dst = frame_steps + ((size_t)b * 2 + half) * kHalfTile3; }
+        else dst = seq + sL3 + pair_l3_offset(st, half);
         float v = 0.f;
         bool lo = false;
-        if (st < 16) {
+        if (n >= 0 && st < 16) {
             const int k = st * 16 + kk;
             if (n < kColor) v = f32[oWct + (size_t)k * kColor + n];
             else if (n == 128) v = w.alpha_w[k];
-            else if (n == 129) { v = w.alpha_w[k]; lo = true; }
-        } else {
+            else { v = w.alpha_w[k]; lo = true; }
+        } else if (n >= 0) {
             const int k2 = (st - 16) * 16 + kk;      // column of the per-point tile
             if (n < kColor) {
                 if (k2 < kXyzPE) v = w.view_w[n * 346 + 283 + k2];
@@ -310,21 +314,21 @@ __global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f3
             } else if (n == 128 && k2 == 92) v = w.alpha_b[0];
             else if (n == 129 && k2 == 92) { v = w.alpha_b[0]; lo = true; }
         }
-        dst[step_offset(n, kk, kN3)] = lo ? f16_lo(v) : f16_hi(v);
+        dst[step_offset(nl, kk, kN3 / 2)] = lo ? f16_lo(v) : f16_hi(v);
     }
-    // L4: N = 16
+    // L4: N = 16 as two 8-row halves; half 0 rows 0..2 = hi(rgb_fc), 3..5 = lo(rgb_fc); half 1 = zeros
     for (int i = t0; i < kStepsL4 * kN4 * 16; i += stride) {
-        const int st = i / (kN4 * 16), n = (i / 16) % kN4, kk = i % 16;
+        const int st = i / (kN4 * 16), r = (i / 16) % kN4, kk = i % 16;
+        const int half = r / 8, nl = r % 8;
         float v = 0.f;
         bool lo = false;
-        if (n < 6) {
-            const int c = n % 3;
-            lo = n >= 3;
+        if (half == 0 && nl < 6) {
+            const int c = nl % 3;
+            lo = nl >= 3;
             if (st < 8) v = w.rgb_w[c * kColor + st * 16 + kk];
             else if (kk == 0) v = w.rgb_b[c];
-            else { v = 0.f; }
         }
-        seq[sL4 + (size_t)st * kStepHalves4 + step_offset(n, kk, kN4)] = lo ? f16_lo(v) : f16_hi(v);
+        seq[sL4 + pair_l4_offset(st, half) + step_offset(nl, kk, 8)] = lo ? f16_lo(v) : f16_hi(v);
     }
 }
 

@@ -89,7 +89,36 @@ __host__ __device__ inline int feat_tc_to_orig(int j) {
 __host__ __device__ inline int class_segments(int c) { return c == 0 ? 6 : c == 1 ? 5 : c == 2 ? 4 : 2; }
 __host__ __device__ inline int class_ksteps(int c) { return c == 0 ? 22 : c == 1 ? 20 : c == 2 ? 16 : 8; }
 
-// N=256 layers: half-offset (from the layer base) of K-step ks, hi or lo plane, with nks K-steps in the layer
+// The tensor-core decoder runs on CTA PAIRS (tcgen05 cta_group::2): every B operand is split by N halves across the two CTAs'
+// shared memory, so each CTA streams only ITS half of every step -- half the bytes per SM.  A step of an N-wide layer is
+// therefore stored as two (N/2) x 16 tiles (same canonical K-major layout, N/2 rows), arranged so that what ONE CTA loads for
+// one ring slot is one contiguous run:
+//   N = 256 layers: group g of gs K-steps = [half 0: gs hi tiles, gs lo tiles][half 1: gs hi tiles, gs lo tiles]  (4 KB tiles);
+//                   bias step = [half 0 tile][half 1 tile]
+//   L3 (N = 144)  : [half 0: steps 0..20][half 1: steps 0..20] (72 x 16 tiles); the per-frame step 21 is [B][half][tile].
+//                   Rows of half 0: colour 0..63, alpha_fc hi, alpha_fc lo, 6 zero rows; half 1: colour 64..127, 8 zero rows
+//                   => accumulator columns [0,64) colour, 64 / 65 the density rows, [72,136) colour.
+//   L4 (N = 16)   : [half 0: 9 tiles of 8 x 16: rgb hi (3), rgb lo (3), 2 zero rows][half 1: zeros]
+constexpr int kHalfTile256 = 128 * 16;                     // halves in one (N/2 = 128) x 16 tile
+constexpr int kHalfTile3 = (kN3 / 2) * 16;                 // 72 x 16
+constexpr int kHalfTile4 = (kN4 / 2) * 16;                 // 8 x 16
+// half-offset (from the layer base) of the first tile CTA `half` loads for the group starting at K-step g0
+__host__ __device__ inline size_t pair_group_offset(int g0, int half, int nks) {
+    const int g = g0 >> 2;
+    const int gs = (nks - 4 * g) < 4 ? (nks - 4 * g) : 4;
+    return (size_t)8 * g * kStepHalves256 + (size_t)half * 2 * gs * kHalfTile256;
+}
+// half-offset of K-step ks, hi / lo plane, of CTA `half`
+__host__ __device__ inline size_t pair_step_offset(int ks, int lo, int half, int nks) {
+    const int g = ks >> 2;
+    const int gs = (nks - 4 * g) < 4 ? (nks - 4 * g) : 4;
+    return pair_group_offset(4 * g, half, nks) + (size_t)((lo ? gs : 0) + (ks & 3)) * kHalfTile256;
+}
+__host__ __device__ inline size_t pair_bias_offset(int half, int nks) { return (size_t)2 * nks * kStepHalves256 + (size_t)half * kHalfTile256; }
+__host__ __device__ inline size_t pair_l3_offset(int step, int half) { return (size_t)half * (kStepsL3 - 1) * kHalfTile3 + (size_t)step * kHalfTile3; }
+__host__ __device__ inline size_t pair_l4_offset(int step, int half) { return (size_t)half * kStepsL4 * kHalfTile4 + (size_t)step * kHalfTile4; }
+
+// N=256 layers: half-offset (from the layer base) of K-step ks, hi or lo plane, with nks K-steps in the layer (single-CTA order)
 __host__ __device__ inline size_t step256_offset(int ks, int lo, int nks) {
     const int g = ks >> 2;
     const int gsteps = (nks - 4 * g) < 4 ? (nks - 4 * g) : 4;

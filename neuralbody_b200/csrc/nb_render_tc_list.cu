@@ -11,11 +11,14 @@
 //                                warp-specialised tcgen05 pipeline (roles below).
 //   3. composite_kernel          raw2outputs (nerf_net_utils.py:6-51), one warp per ray.
 //
-// Decoder pipeline, one persistent CTA per SM, CTA pairs share the weight stream by TMA multicast:
+// Decoder pipeline, one persistent CTA per SM.  The two CTAs of a cluster (one TPC) work as a PAIR on 2 x 128 list rows: every
+// MMA is a tcgen05 cta_group::2 instruction of M = 256 issued by the leader CTA, whose B operand (the layer's weights) is split
+// by N halves across the two CTAs' shared memory -- each SM streams only HALF of the weight bytes from L2 (the per-SM ingest of
+// the 1 MB-per-tile weight stream, not the tensor pipe, bounded the single-CTA version) and reads half of them per MMA.
 //   warps  0..15  producers   trilinear gather of the 352 features into a ring of 64-channel layer-0 operand segments
 //   warps 16..19  epilogue    TMEM accumulator -> relu -> (hi, lo) fp16 operand of the next layer, IN PLACE (see below)
-//   warp  20      MMA issuer  one thread issues every tcgen05.mma
-//   warp  21      loader      one thread streams the pre-packed weights through a 3-slot shared-memory ring
+//   warp  20      MMA issuer  leader: one thread issues every tcgen05.mma for the pair; peer: relays its bulk-copy completions
+//   warp  21      loader      one thread streams this CTA's half of the pre-packed weights through a 3-slot shared-memory ring
 // (the warp scheduler favours high warp ids, so the latency-critical roles sit above the 16 throughput warps).
 //
 // TMEM (512 columns) is two 256-column regions R0 | R1 that swap roles every layer: layer l accumulates into one region
@@ -53,21 +56,16 @@ constexpr int PROD_WARPS = 16, EPI_WARP0 = 16, EPI_WARPS = 4, MMA_WARP = 20, LOA
 constexpr int NT = (LOAD_WARP + 1) * 32;                          // 704
 constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);
 constexpr int MAXS = 1024;                                         // samples per classification block
-#ifndef NB_LIST_CLUSTER
-#define NB_LIST_CLUSTER 2
-#endif
-constexpr int CLUSTER = NB_LIST_CLUSTER;       // CTAs that share one weight stream through TMA multicast (all tiles cost the same)
+constexpr int CLUSTER = 2;                     // a CTA pair (same TPC) executes every MMA together: tcgen05 cta_group::2, M = 256
 constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry .w = frame sample id | level bits << 28
 #ifndef NB_CORNER_BATCH
 #define NB_CORNER_BATCH 4
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
-#ifndef NB_L3_GROUP
-#define NB_L3_GROUP 4
-#endif
-constexpr int L3_GROUP = NB_L3_GROUP;                             // layer-3 K-steps per ring slot (<= 7: 4.5 KB each)
-static_assert(L3_GROUP >= 1 && L3_GROUP <= 7, "a slot holds at most 7 layer-3 steps");
-constexpr int L4_BYTES = kStepsL4 * (int)kStepHalves4 * 2;         // the rgb head's 9 N=16 steps stay resident (4.5 KB)
+constexpr int L3_SPLIT = 11;                                       // layer-3 K-steps in its first ring slot (2.25 KB per step and CTA)
+constexpr int L4_BYTES = kStepsL4 * kHalfTile4 * 2;                // this CTA's half of the rgb head's 9 N=16 steps stays resident
+constexpr int HALF_TILE_BYTES = kHalfTile256 * 2;                  // one K-step of an N = 256 layer, this CTA's 128 rows (4 KB)
+constexpr int L3_TILE_BYTES = kHalfTile3 * 2;                      // one K-step of layer 3, this CTA's 72 rows (2.25 KB)
 
 // shared-memory map (bytes)
 constexpr int OFF_SEG = 0;
@@ -77,9 +75,12 @@ constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;
 constexpr int OFF_L4 = OFF_RING + NUM_SLOTS * SLOT_BYTES;
 constexpr int OFF_XF = OFF_L4 + L4_BYTES;                          // FrameXf
 constexpr int OFF_BAR = OFF_XF + 128;
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + MAX_SEG_BUFS,
-       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_RGB_FULL, BAR_L4W_FULL, BAR_H_READY /* x4: one per 64 columns */,
-       NUM_BARS = BAR_H_READY + 4 };
+// W_FULL / L4W_FULL: this CTA's bulk copies landed.  W_PEER / L4W_PEER (leader only): the peer's did (relayed by the peer).
+// SEG_FULL / H_READY (leader only): producers / epilogue warps of BOTH CTAs arrive (the peer's remotely).  W_EMPTY / SEG_EMPTY /
+// ACC_FULL / RGB_FULL: the leader's tcgen05.commit, multicast to both CTAs.
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_W_PEER = 2 * NUM_SLOTS, BAR_SEG_FULL = 3 * NUM_SLOTS,
+       BAR_SEG_EMPTY = 3 * NUM_SLOTS + MAX_SEG_BUFS, BAR_ACC_FULL = 3 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_RGB_FULL, BAR_L4W_FULL,
+       BAR_L4W_PEER, BAR_H_READY /* x4: one per 64 columns */, NUM_BARS = BAR_H_READY + 4 };
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -87,7 +88,8 @@ static_assert(OFF_L4 % 128 == 0 && OFF_RING % 128 == 0 && OFF_PE % 128 == 0, "op
 
 // TMEM: two 256-column regions; K-step k of an activation operand occupies columns [16k, 16k+8) (hi) and [16k+8, 16k+16) (lo)
 constexpr uint32_t TM_R0 = 0, TM_R1 = 256;
-constexpr uint32_t TM_SIGMA = TM_R1 + 128;     // layer-3 accumulator columns 128..143: alpha_fc hi / lo rows
+// layer-3 accumulator (R1): columns [0,64) colour 0..63 | 64, 65 alpha_fc hi / lo rows | [72,136) colour 64..127 (nb_layout.h)
+constexpr uint32_t TM_SIGMA = TM_R1 + 64;
 constexpr uint32_t TM_RGB = TM_R1 + 192;       // layer-4 accumulator (16 columns), beyond layer 3's 144
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -212,14 +214,17 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     constexpr int NUM_SEG_BUFS = (NP == 3) ? 3 : 6;
     constexpr int SEG_BYTES = SEG_RING_BYTES / NUM_SEG_BUFS;
 
-    if (warp == MMA_WARP) tc::tmem_alloc<512>(tmem_slot);
+    if (warp == MMA_WARP) tc::tmem_alloc_pair<512>(tmem_slot);        // the same warp of both CTAs
     if (tid == LOAD_WARP * 32) {
-        for (int i = 0; i < NUM_SLOTS; ++i) { tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], CLUSTER); }
-        for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
+        for (int i = 0; i < NUM_SLOTS; ++i) {
+            tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], 1); tc::mbar_init(&bars[BAR_W_PEER + i], 1);
+        }
+        for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], CLUSTER * PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
         tc::mbar_init(&bars[BAR_RGB_FULL], 1);
         tc::mbar_init(&bars[BAR_L4W_FULL], 1);
-        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[BAR_H_READY + i], EPI_WARPS * 32);
+        tc::mbar_init(&bars[BAR_L4W_PEER], 1);
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[BAR_H_READY + i], CLUSTER * EPI_WARPS);
         tc::fence_mbar_init();
     }
     if (warp < PROD_WARPS) {
@@ -234,10 +239,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    if (CLUSTER > 1) tc::cluster_sync_all();      // the peer's mbarriers are initialised before any multicast lands
-    const uint32_t crank = CLUSTER > 1 ? tc::cluster_ctarank() : 0u;
+    tc::cluster_sync_all();                        // both CTAs' mbarriers are initialised before anything arrives on them
+    const uint32_t crank = tc::cluster_ctarank();
+    const bool leader = crank == 0;                // the leader's MMA thread issues for the pair
     constexpr uint16_t CMASK = (1u << CLUSTER) - 1;
     const uint32_t tmem = *tmem_slot;
+    const uint32_t leader_bars = tc::map_to_cta(bars, 0);             // shared::cluster address of the leader's barrier array
+    auto arrive_at_leader = [&](int bar) { tc::mbar_arrive_remote(leader_bars + 8u * (uint32_t)bar); };
     if (tid == 0 && P.stats) atomicMax(P.frame_clock + 0, ~global_ns());     // min(start) over the CTAs, as max(~start)
     // The frame's work: per sample class c (heaviest first) ceil(count_c / 128) tiles, rounded up to whole clusters so that the
     // CTAs of a cluster -- which walk the tiles in lockstep on one shared weight stream -- always work on the same class
@@ -402,7 +410,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 }
                 tc::fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bars[BAR_SEG_FULL + buf]);
+                if (lane == 0) arrive_at_leader(BAR_SEG_FULL + buf);
                 tr.ev(20 + seg);
             }
         }
@@ -412,97 +420,105 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)cc0 + cc1 + cc2 + cc3);
         }
     }
-    // ================================================================== LOADER
+    // ================================================================== LOADER (each CTA streams ITS half of every weight step)
     else if (warp == LOAD_WARP) {
         if (lane == 0) {
             uint32_t cnt = 0;
             const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
-            // the rgb head's weights stay resident: one plain bulk copy per CTA
+            // the rgb head's weights stay resident
             tc::mbar_arrive_expect_tx(&bars[BAR_L4W_FULL], L4_BYTES);
-            tc::bulk_g2s(smem + OFF_L4, seq + sL4 * 2, L4_BYTES, &bars[BAR_L4W_FULL]);
+            tc::bulk_g2s(smem + OFF_L4, seq + 2 * (sL4 + pair_l4_offset(0, (int)crank)), L4_BYTES, &bars[BAR_L4W_FULL]);
             auto push = [&](const unsigned char* src, uint32_t bytes, const unsigned char* src2 = nullptr, uint32_t bytes2 = 0) {
                 const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
                 unsigned char* dst = smem + OFF_RING + slot * SLOT_BYTES;
                 tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);
                 tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes + bytes2);
-                if (CLUSTER == 1) {
-                    tc::bulk_g2s(dst, src, bytes, &bars[BAR_W_FULL + slot]);
-                    if (bytes2) tc::bulk_g2s(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot]);
-                } else if (cnt % CLUSTER == crank) {      // the CTAs take turns issuing the copy for everybody
-                    tc::bulk_g2s_multicast(dst, src, bytes, &bars[BAR_W_FULL + slot], CMASK);
-                    if (bytes2) tc::bulk_g2s_multicast(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot], CMASK);
-                }
+                tc::bulk_g2s(dst, src, bytes, &bars[BAR_W_FULL + slot]);
+                if (bytes2) tc::bulk_g2s(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot]);
                 ++cnt;
             };
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
-                const int l0_ksteps = class_ksteps(tile_ref(tbase).cls);      // both CTAs of the cluster: same class
+                const int l0_ksteps = class_ksteps(tile_ref(tbase).cls);      // both CTAs of the pair: same class
                 for (int layer = 0; layer < 3; ++layer) {
                     const int nks = layer == 0 ? kKsL0 : kKsL12;
                     const unsigned char* base = seq + 2 * (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
                     for (int g0 = 0; g0 < (layer == 0 ? l0_ksteps : nks); g0 += 4) {
                         const int gs = (nks - g0) < 4 ? (nks - g0) : 4;
-                        push(base + 2 * step256_offset(g0, 0, nks), gs * STEP_BYTES);
-                        if (NP == 3) push(base + 2 * step256_offset(g0, 1, nks), gs * STEP_BYTES);
+                        // one slot = this CTA's gs hi tiles (+ gs lo tiles in the 3-pass mode), contiguous in the stream
+                        push(base + 2 * pair_group_offset(g0, (int)crank, nks), (NP == 3 ? 2 : 1) * gs * HALF_TILE_BYTES);
                     }
-                    push(base + 2 * bias256_offset(nks), STEP_BYTES);
+                    push(base + 2 * pair_bias_offset((int)crank, nks), HALF_TILE_BYTES);
                 }
-                const uint32_t sb = kStepHalves3 * 2;
-                const unsigned char* l3 = seq + sL3 * 2;
-                // steps 0..20 from the common stream in groups of L3_GROUP, the per-frame step 21 closes the last group
-                for (int g0 = 0; g0 < kStepsL3; g0 += L3_GROUP) {
-                    const int common = min(L3_GROUP, kStepsL3 - 1 - g0), last = g0 + L3_GROUP >= kStepsL3;
-                    const unsigned char* fr = reinterpret_cast<const unsigned char*>(P.wframe) + (size_t)P.frame * sb;
-                    if (common > 0) push(l3 + (size_t)g0 * sb, common * sb, last ? fr : nullptr, last ? sb : 0);
-                    else push(fr, sb);
-                }
+                const unsigned char* l3 = seq + 2 * (sL3 + pair_l3_offset(0, (int)crank));
+                push(l3, L3_SPLIT * L3_TILE_BYTES);
+                push(l3 + L3_SPLIT * L3_TILE_BYTES, (kStepsL3 - 1 - L3_SPLIT) * L3_TILE_BYTES,
+                     reinterpret_cast<const unsigned char*>(P.wframe) + ((size_t)P.frame * 2 + crank) * L3_TILE_BYTES, L3_TILE_BYTES);
             }
         }
     }
-    // ================================================================== MMA ISSUER
+    // ================================================================== MMA ISSUER (leader) / COPY RELAY (peer)
     else if (warp == MMA_WARP) {
-        if (lane == 0) {
+        if (lane == 0 && !leader) {
+            // The leader must know that THIS CTA's half of a weight slot has landed, but a bulk copy can only signal an mbarrier
+            // of its destination CTA: this thread watches the local W_FULL barriers in push order and forwards each completion.
+            tc::mbar_wait(&bars[BAR_L4W_FULL], 0);
+            arrive_at_leader(BAR_L4W_PEER);
+            uint32_t cnt = 0;
+            for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
+                const int pushes = (class_ksteps(tile_ref(tbase).cls) + 3) / 4 + 1 + 2 * (kKsL12 / 4 + 1) + 2;
+                for (int i = 0; i < pushes; ++i, ++cnt) {
+                    const uint32_t slot = cnt % NUM_SLOTS;
+                    tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
+                    arrive_at_leader(BAR_W_PEER + slot);
+                }
+            }
+        }
+        if (lane == 0 && leader) {
             uint32_t cnt = 0, hphase = 0, it = 0, gseg = 0;
             const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
             const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
             const uint32_t l4_addr = tc::smem_u32(smem + OFF_L4);
-            constexpr uint32_t ID256 = tc::make_idesc_f16(128, 256), ID3 = tc::make_idesc_f16(128, kN3),
-                               ID4 = tc::make_idesc_f16(128, kN4);
+            // M = 256: the pair's two 128-row tiles; N = the whole layer width, each CTA holding half of the B rows
+            constexpr uint32_t ID256 = tc::make_idesc_f16(256, 256), ID3 = tc::make_idesc_f16(256, kN3),
+                               ID4 = tc::make_idesc_f16(256, kN4);
             auto wait_slot = [&](uint32_t& slot) {
                 slot = cnt % NUM_SLOTS;
                 tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
+                tc::mbar_wait_cluster(&bars[BAR_W_PEER + slot], (cnt / NUM_SLOTS) & 1);
                 tc::tc_fence_after();
             };
             auto release_slot = [&](uint32_t slot) {
-                if (CLUSTER == 1) tc::mma_commit(&bars[BAR_W_EMPTY + slot]);
-                else tc::mma_commit_multicast(&bars[BAR_W_EMPTY + slot], CMASK);   // both CTAs' loaders wait for both consumers
+                tc::mma_commit_pair(&bars[BAR_W_EMPTY + slot], CMASK);      // both CTAs' loaders reuse the slot
                 ++cnt;
             };
             auto a_desc = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * CHUNK_BYTES, CHUNK_BYTES, 128); };
             auto a_seg = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * SEG_CHUNK_STRIDE, SEG_CHUNK_STRIDE, 128); };
-            auto b_desc = [&](uint32_t slot, int i, int N) {
-                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32, N * 16, 128);
+            // tile i of a slot holding 128-row half tiles of an N = 256 layer (K-chunks 2 KB apart)
+            auto b256 = [&](uint32_t slot, int i) {
+                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * HALF_TILE_BYTES, 128 * 16, 128);
             };
-            auto b_desc_rows = [&](uint32_t slot, int i, int N, int row0) {     // rows row0.. of step i (8-row groups are 128 B apart)
-                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * N * 32 + row0 * 16, N * 16, 128);
+            // step i of a layer-3 slot (72-row half tiles); row0: first local row of the rows used
+            auto b3 = [&](uint32_t slot, int i, int row0) {
+                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * L3_TILE_BYTES + row0 * 16, (kN3 / 2) * 16, 128);
             };
-            // the epilogue has converted columns [64 g, 64 g + 64) of the current activation region (K-steps 4g..4g+3)
+            auto b4 = [&](int ks) { return tc::make_smem_desc(l4_addr + ks * kHalfTile4 * 2, (kN4 / 2) * 16, 128); };
+            // the epilogues of BOTH CTAs have converted columns [64 g, 64 g + 64) of the current activation region (K-steps 4g..4g+3)
             auto wait_h = [&](int g) {
-                tc::mbar_wait(&bars[BAR_H_READY + g], (hphase >> g) & 1);
+                tc::mbar_wait_cluster(&bars[BAR_H_READY + g], (hphase >> g) & 1);
                 hphase ^= 1u << g;
                 tc::tc_fence_after();
             };
             Tracer tr;
             tr.init(P.trace, 1);
-            // layer 4 of the tile whose layer 3 was issued last: A = relu(colour hidden) in R1 (hi only), B resident
+            // layer 4 of the tile pair whose layer 3 was issued last: A = relu(colour hidden) in R1 (hi only), B resident
             auto issue_l4 = [&]() {
                 wait_h(0);
                 wait_h(1);
                 tr.ev(34);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    tc::mma_ts(tmem + TM_RGB, tmem + TM_R1 + 16 * ks, tc::make_smem_desc(l4_addr + ks * kN4 * 32, kN4 * 16, 128), ID4, ks > 0);
-                tc::mma_ss(tmem + TM_RGB, a_desc(ones_addr, 0), tc::make_smem_desc(l4_addr + 8 * kN4 * 32, kN4 * 16, 128), ID4, true);
-                tc::mma_commit(&bars[BAR_RGB_FULL]);
+                for (int ks = 0; ks < 8; ++ks) tc::mma_ts_pair(tmem + TM_RGB, tmem + TM_R1 + 16 * ks, b4(ks), ID4, ks > 0);
+                tc::mma_ss_pair(tmem + TM_RGB, a_desc(ones_addr, 0), b4(8), ID4, true);
+                tc::mma_commit_pair(&bars[BAR_RGB_FULL], CMASK);
             };
             // a 256 -> 256 layer: A = activations in region `rin` (TMEM), accumulator = region `rout`
             auto layer256 = [&](uint32_t rin, uint32_t rout, int code) {
@@ -510,69 +526,66 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 for (int g = 0; g < 4; ++g) {
                     wait_h(g);
                     if (g == 0) tr.ev(30 + code);
-                    wait_slot(slot);
+                    wait_slot(slot);                                            // [4 hi tiles | 4 lo tiles]
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t a = tmem + rin + 16 * (4 * g + i);
-                        tc::mma_ts(tmem + rout, a, b_desc(slot, i, 256), ID256, (g | i) != 0);
-                        if (NP == 3) tc::mma_ts(tmem + rout, a + 8, b_desc(slot, i, 256), ID256, true);
+                        tc::mma_ts_pair(tmem + rout, a, b256(slot, i), ID256, (g | i) != 0);
+                        if (NP == 3) tc::mma_ts_pair(tmem + rout, a + 8, b256(slot, i), ID256, true);
                     }
-                    release_slot(slot);
                     if (NP == 3) {
-                        wait_slot(slot);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            tc::mma_ts(tmem + rout, tmem + rin + 16 * (4 * g + i), b_desc(slot, i, 256), ID256, true);
-                        release_slot(slot);
+                            tc::mma_ts_pair(tmem + rout, tmem + rin + 16 * (4 * g + i), b256(slot, 4 + i), ID256, true);
                     }
+                    release_slot(slot);
                 }
                 wait_slot(slot);
-                tc::mma_ss(tmem + rout, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
+                tc::mma_ss_pair(tmem + rout, a_desc(ones_addr, 0), b256(slot, 0), ID256, true);
                 release_slot(slot);
-                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tc::mma_commit_pair(&bars[BAR_ACC_FULL], CMASK);
                 tr.ev(20 + code);
             };
             tc::mbar_wait(&bars[BAR_L4W_FULL], 0);
+            tc::mbar_wait_cluster(&bars[BAR_L4W_PEER], 0);
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
                 uint32_t slot;
                 tr.ev(1);
-                // ---- layer 0: A = gathered feature segments (shared memory), accumulator R0.  R0 held the previous tile's h2,
-                // whose last reader (its layer 3) was issued before: the tensor pipe executes in issue order.
+                // ---- layer 0: A = gathered feature segments (shared memory of each CTA), accumulator R0.  R0 held the previous
+                // tile's h2, whose last reader (its layer 3) was issued before: the tensor pipe executes in issue order.
                 const int nseg = class_segments(tile_ref(tbase).cls);
                 for (int seg = 0; seg < nseg; ++seg, ++gseg) {
                     const uint32_t buf = gseg % NUM_SEG_BUFS;
-                    tc::mbar_wait(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
+                    tc::mbar_wait_cluster(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
                     tc::tc_fence_after();
                     tr.ev(10 + seg);
                     const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * SEG_CHUNK_STRIDE;
                     const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
-                    wait_slot(slot);
+                    wait_slot(slot);                                            // [nks hi tiles | nks lo tiles]
                     for (int ks = 0; ks < nks; ++ks) {
-                        tc::mma_ss(tmem + TM_R0, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, (seg | ks) != 0);
-                        if (NP == 3) tc::mma_ss(tmem + TM_R0, a_seg(lo_addr, ks), b_desc(slot, ks, 256), ID256, true);
+                        tc::mma_ss_pair(tmem + TM_R0, a_seg(hi_addr, ks), b256(slot, ks), ID256, (seg | ks) != 0);
+                        if (NP == 3) tc::mma_ss_pair(tmem + TM_R0, a_seg(lo_addr, ks), b256(slot, ks), ID256, true);
+                    }
+                    if (NP == 3) {
+                        for (int ks = 0; ks < nks; ++ks)
+                            tc::mma_ss_pair(tmem + TM_R0, a_seg(hi_addr, ks), b256(slot, nks + ks), ID256, true);
                     }
                     release_slot(slot);
-                    if (NP == 3) {
-                        wait_slot(slot);
-                        for (int ks = 0; ks < nks; ++ks)
-                            tc::mma_ss(tmem + TM_R0, a_seg(hi_addr, ks), b_desc(slot, ks, 256), ID256, true);
-                        release_slot(slot);
-                    }
-                    tc::mma_commit(&bars[BAR_SEG_EMPTY + buf]);
+                    tc::mma_commit_pair(&bars[BAR_SEG_EMPTY + buf], CMASK);
                     // the previous tile's rgb head, once its layer-3 epilogue is through (it ran under the MMAs above)
                     if (seg == 0 && it > 0) issue_l4();
                 }
                 wait_slot(slot);
-                tc::mma_ss(tmem + TM_R0, a_desc(ones_addr, 0), b_desc(slot, 0, 256), ID256, true);
+                tc::mma_ss_pair(tmem + TM_R0, a_desc(ones_addr, 0), b256(slot, 0), ID256, true);
                 release_slot(slot);
-                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tc::mma_commit_pair(&bars[BAR_ACC_FULL], CMASK);
                 tr.ev(20);
                 layer256(TM_R0, TM_R1, 1);       // layer 1: h0 (R0) -> R1
                 layer256(TM_R1, TM_R0, 2);       // layer 2: h1 (R1) -> R0
-                // ---- layer 3: A = h2 (R0); accumulator R1[0..143]: 128 colour columns + alpha_fc hi / lo rows.  K-steps 0..15
-                // over h2 (TMEM), 16..21 over the per-point tile (shared memory); 7 steps per weight slot
+                // ---- layer 3: A = h2 (R0); accumulator R1[0..143].  K-steps 0..15 over h2 (TMEM), 16..21 over the per-point
+                // tile (shared memory); two weight slots (steps 0..10, 11..21)
                 for (int k = 0; k < kStepsL3; ++k) {
-                    if (k % L3_GROUP == 0) {
+                    if (k == 0 || k == L3_SPLIT) {
                         if (k) release_slot(slot);
                         wait_slot(slot);
                     }
@@ -580,19 +593,19 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         wait_h(k >> 2);
                         if (k == 0) tr.ev(33);
                     }
-                    const int i = k % L3_GROUP;
+                    const int i = k < L3_SPLIT ? k : k - L3_SPLIT;
                     if (k < 16) {
                         const uint32_t a = tmem + TM_R0 + 16 * k;
-                        tc::mma_ts(tmem + TM_R1, a, b_desc(slot, i, kN3), ID3, k != 0);
-                        // the lo half of the activations only matters on the density path: rows 128..143 of the step (alpha_fc
-                        // hi / lo + padding) -> accumulator columns 128..143; the 128 colour columns take the hi half alone
-                        if (NP == 3) tc::mma_ts(tmem + TM_SIGMA, a + 8, b_desc_rows(slot, i, kN3, 128), ID4, true);
+                        tc::mma_ts_pair(tmem + TM_R1, a, b3(slot, i, 0), ID3, k != 0);
+                        // the lo half of the activations only matters on the density path: local rows 64..71 of each CTA's half
+                        // (rank 0: alpha_fc hi / lo + zeros, rank 1: zeros) -> accumulator columns 64..79
+                        if (NP == 3) tc::mma_ts_pair(tmem + TM_SIGMA, a + 8, b3(slot, i, 64), ID4, true);
                     } else {
-                        tc::mma_ss(tmem + TM_R1, a_desc(pe_addr, k - 16), b_desc(slot, i, kN3), ID3, true);
+                        tc::mma_ss_pair(tmem + TM_R1, a_desc(pe_addr, k - 16), b3(slot, i, 0), ID3, true);
                     }
                 }
                 release_slot(slot);
-                tc::mma_commit(&bars[BAR_ACC_FULL]);
+                tc::mma_commit_pair(&bars[BAR_ACC_FULL], CMASK);
                 tr.ev(23);
                 ++it;
             }
@@ -611,9 +624,12 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         // accumulator region `reg` -> relu -> fp16 operand of the next layer, in place: the 16 fp32 columns of K-step k become
         // 8 columns of hi pairs [16k, 16k+8) and (3-pass mode, with_lo) 8 columns of lo pairs [16k+8, 16k+16).  H_READY[g]
         // is signalled after every 4 K-steps, so the issuer can start the next layer on the first converted quarter.
-        auto convert_region = [&](uint32_t reg, int nblocks, bool with_lo) {
+        auto convert_region = [&](uint32_t reg, int nblocks, bool with_lo, bool l3 = false) {
             uint32_t va[16], vb[16];
             const uint32_t base = lane_base + reg;
+            // layer 3's accumulator keeps its 128 colour columns as [0,64) and [72,136) (8 density columns in between): block k
+            // is read from there and written, compacted, to the operand position [16k, 16k+8) -- always behind the read front
+            auto src = [&](int k) { return base + 16 * k + ((l3 && k >= 4) ? 8 : 0); };
             auto convert_store = [&](const uint32_t (&v)[16], int k) {
                 uint32_t h[8];
                 if (NP == 3 && with_lo) {
@@ -638,17 +654,18 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 if ((k & 3) == 3) {
                     tc::tmem_st_wait();
                     tc::tc_fence_before();
-                    tc::mbar_arrive(&bars[BAR_H_READY + (k >> 2)]);
+                    __syncwarp();
+                    if (lane == 0) arrive_at_leader(BAR_H_READY + (k >> 2));     // one arrival per warp, 4 + 4 warps of the pair
                 }
             };
-            tc::tmem_ld16(base, va);
+            tc::tmem_ld16(src(0), va);
             tc::tmem_ld_wait(va);
             for (int k = 0; k < nblocks; k += 2) {
-                tc::tmem_ld16(base + 16 * (k + 1), vb);
+                tc::tmem_ld16(src(k + 1), vb);
                 convert_store(va, k);
                 chunk_done(k);
                 tc::tmem_ld_wait(vb);
-                if (k + 2 < nblocks) tc::tmem_ld16(base + 16 * (k + 2), va);
+                if (k + 2 < nblocks) tc::tmem_ld16(src(k + 2), va);
                 convert_store(vb, k + 1);
                 chunk_done(k + 1);
                 if (k + 2 < nblocks) tc::tmem_ld_wait(va);
@@ -698,7 +715,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 tc::tmem_ld_wait(v);
                 sigma = __uint_as_float(v[0]) + __uint_as_float(v[1]);
             }
-            convert_region(TM_R1, 8, false);     // relu(colour hidden), hi only: H_READY[0], H_READY[1]
+            convert_region(TM_R1, 8, false, true);     // relu(colour hidden), hi only: H_READY[0], H_READY[1]
             tr.ev(23);
             tc::mbar_wait(&bars[BAR_RGB_FULL], rcnt & 1); ++rcnt; tc::tc_fence_after();
             tr.ev(14);
@@ -717,10 +734,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     tc::tc_fence_before();
     __syncthreads();
     if (tid == 0 && P.stats) atomicMax(P.frame_clock + 1, global_ns());
-    if (CLUSTER > 1) tc::cluster_sync_all();      // no CTA exits while the peer may still multicast into it
+    tc::cluster_sync_all();                        // no CTA exits (or frees its TMEM) while the pair's MMAs may still touch it
     if (warp == MMA_WARP) {
         __syncwarp();
-        tc::tmem_dealloc<512>(tmem);
+        tc::tmem_dealloc_pair<512>(tmem);
     }
 }
 
