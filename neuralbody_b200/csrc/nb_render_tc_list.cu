@@ -59,9 +59,14 @@ constexpr int MAXS = 1024;                                         // samples pe
 constexpr int CLUSTER = 2;                     // a CTA pair (same TPC) executes every MMA together: tcgen05 cta_group::2, M = 256
 constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry .w = frame sample id | level bits << 28
 #ifndef NB_CORNER_BATCH
-#define NB_CORNER_BATCH 4
+#define NB_CORNER_BATCH 8
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
+// 704 threads x 88 registers = 61 952 of the SM's 65 536 (22 warps x 11 allocation units): __launch_bounds__(704, 1) alone makes
+// ptxas stop at 80, which costs the producers' gather either spills or half of its loads in flight
+#ifndef NB_DECODER_REGS
+#define NB_DECODER_REGS 88
+#endif
 constexpr int L3_SPLIT = 11;                                       // layer-3 K-steps in its first ring slot (2.25 KB per step and CTA)
 constexpr int L4_BYTES = kStepsL4 * kHalfTile4 * 2;                // this CTA's half of the rgb head's 9 N=16 steps stays resident
 constexpr int HALF_TILE_BYTES = kHalfTile256 * 2;                  // one K-step of an N = 256 layer, this CTA's 128 rows (4 KB)
@@ -204,7 +209,7 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
 
 // ------------------------------------------------------------------------------------------------ 2. decoder over the list
 template <int NP, typename VT>
-__global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __maxnreg__(NB_DECODER_REGS) render_tc_list_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);

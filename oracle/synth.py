@@ -341,7 +341,7 @@ def trained_like_rescale(w, volumes, seed=313, sigma_empty=-10.0, sigma_p95=30.0
 # ----------------------------------------------------------------------------- scene
 def make_scene(seed=313, H=512, W=512, scale=1.0, voxel_size=(0.005, 0.005, 0.005), all_hit=True,
                num_train_frame=60, latent_index=0, n_rays=None, azimuth_deg=20.0,
-               Rh=(0.3, -0.2, 0.1), Th=(0.1, 0.2, 1.0), th_shape=(1, 3), batch=1, ray_box_pad=0.15):
+               Rh=(0.3, -0.2, 0.1), Th=(0.1, 0.2, 1.0), th_shape=(1, 3), batch=1, ray_box_pad=0.15, volume_seed=None):
     """Build the batch dict of multi_view_dataset.py:157-180 (as default_collate would
     hand it to Renderer.render) + dense volumes + decoder weights.
 
@@ -359,8 +359,10 @@ def make_scene(seed=313, H=512, W=512, scale=1.0, voxel_size=(0.005, 0.005, 0.00
     Rm = _rodrigues(Rh)
     world = (verts.astype(np.float64) @ Rm.T + np.asarray(Th, np.float64) * 1.0).astype(np.float32)
     coord, out_sh, can_bounds, bounds, R, Th_f = prepare_input(world, Rh, Th, voxel_size)
-    volumes, fracs = make_volumes(coord, out_sh, seed)
-    weights = trained_like_rescale(make_weights(seed, num_train_frame), volumes, seed)
+    # volume_seed: other feature values on the same body (the frames of a multi-pose batch share the decoder, not the volume)
+    volumes, fracs = make_volumes(coord, out_sh, seed if volume_seed is None else volume_seed)
+    weights = trained_like_rescale(make_weights(seed, num_train_frame), make_volumes(coord, out_sh, seed)[0]
+                                   if volume_seed is not None else volumes, seed)
 
     ray_box = can_bounds.copy()
     ray_box[0] -= ray_box_pad

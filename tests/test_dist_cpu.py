@@ -37,6 +37,19 @@ def _worker(rank, world, port, n_rays, out_dir):
         batch = {k: scene[k] for k in ("coord", "out_sh", "bounds", "R", "Th", "latent_index", "ray_o", "ray_d", "near", "far")}
         full = nbdist.render_sharded(render_fn, batch, chunk=8)
         torch.save({k: v.clone() for k, v in full.items()}, os.path.join(out_dir, "rank%d.pt" % rank))
+        # the streaming form: double-buffered slabs the render writes into, one gather + un-permute per view
+        plan = nbdist.ShardPlan.get(n_rays, world, 8, "cpu")
+        local = plan.shard(batch, rank)
+        g = nbdist.FrameGatherer(n_rays, world, rank, "cpu", chunk=8)
+        frames = []
+        for view in range(3):
+            out = g.begin()
+            ret = render_fn(local)
+            for k in out:
+                out[k].copy_(ret[k])
+            frames.append(g.finish().clone())
+        g.drain()
+        torch.save(frames, os.path.join(out_dir, "frames%d.pt" % rank))
         if rank == 0:
             torch.save(render_fn(batch), os.path.join(out_dir, "single.pt"))
     finally:
@@ -53,6 +66,11 @@ def test_ray_sharded_render_equals_single_process(tmp_path, n_rays):
         for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
             assert got[k].shape == single[k].shape, k
             assert torch.equal(torch.nan_to_num(got[k]), torch.nan_to_num(single[k])), (r, k)
+        from neuralbody_b200 import dist as nbdist
+        for frame in torch.load(os.path.join(tmp_path, "frames%d.pt" % r)):
+            views = nbdist.slab_views(frame)
+            for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
+                assert torch.equal(torch.nan_to_num(views[k]), torch.nan_to_num(single[k])), (r, k)
 
 
 def test_interleaved_shards_cover_all_rays():

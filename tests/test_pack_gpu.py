@@ -100,3 +100,39 @@ def test_gen_rays_matches_reference_numpy():
         np.testing.assert_allclose(g_near.cpu().numpy()[sel_gpu], near.astype(np.float32)[sel_ref], rtol=1e-5, atol=1e-5)
         np.testing.assert_allclose(g_far.cpu().numpy()[sel_gpu], far.astype(np.float32)[sel_ref], rtol=1e-5, atol=1e-5)
         assert 0 < mask.sum() < H * W
+
+
+def test_sharded_ray_generation_matches_the_full_image():
+    """nb_gen_rays_sharded: rank r's fixed-shape shard holds exactly the pixels the interleaved plan gives it; box-hit rays carry
+    the bits nb_gen_rays writes, the others are dead rays (near = far = 0, mask 0)."""
+    import ctypes as C
+    from oracle import synth
+    from neuralbody_b200 import capi, rays, dist as nbdist
+    scene, _, _ = golden_case("eval_s64")
+    cb = scene["can_bounds"][0].numpy()
+    center = 0.5 * (cb[0] + cb[1]).astype(np.float64)
+    R, T = synth.look_at_camera(center, 0.9, 33.0)
+    H, W = 50, 70                                   # 3500 pixels: not a multiple of world * chunk
+    K = np.array([[95.0, 0, W / 2.0], [0, 99.0, H / 2.0], [0, 0, 1.0]])
+    RT = np.concatenate([R, T], 1)
+    ro, rd, near, far, m = rays.image_rays(RT, K, cb, H, W)
+    full = {k: torch.zeros((H * W,) + s, device="cuda") for k, s in (("ray_o", (3,)), ("ray_d", (3,)), ("near", ()), ("far", ()))}
+    full["ray_o"][m], full["ray_d"][m], full["near"][m], full["far"][m] = ro, rd, near, far
+    assert 0 < int(m.sum()) < H * W
+    world, chunk = 3, 64
+    seen = torch.zeros(H * W, dtype=torch.bool, device="cuda")
+    for rank in range(world):
+        sh = rays.ShardedRays(H, W, rank, world, chunk).generate(RT, K, cb)
+        idx, per = nbdist.shard_indices(H * W, rank, world, chunk)
+        assert sh.n_local == per
+        j = torch.arange(per, device="cuda")
+        pix = ((j // chunk) * world + rank) * chunk + j % chunk
+        ok = pix < H * W
+        hit = torch.zeros(per, dtype=torch.bool, device="cuda")
+        hit[ok] = m[pix[ok]]
+        assert torch.equal(sh.mask[0].bool(), hit)
+        for k in ("ray_o", "ray_d", "near", "far"):
+            assert torch.equal(getattr(sh, k)[0][hit], full[k][pix[hit]]), k
+        assert float(sh.near[0][~hit].abs().max()) == 0.0 and float(sh.far[0][~hit].abs().max()) == 0.0
+        seen[pix[ok]] = True
+    assert bool(seen.all())

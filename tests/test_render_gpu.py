@@ -274,3 +274,99 @@ def test_sample_pdf_kernel_vs_oracle_random():
         torch.cuda.synchronize()
         assert float((z_all.cpu().view(B * n, -1) - z_ref).abs().max()) < 2e-5
         assert float((z_smp.cpu().view(B * n, -1) - s_ref).abs().max()) < 2e-5
+
+
+def test_strided_outputs_equal_dense_outputs():
+    """nb_render_args.out_ray_stride: the four maps written as columns of one 24-byte-per-ray record (the slab a ray-sharded
+    render all-gathers) hold the same bits as the dense maps -- tensor-core pipeline and exact kernel."""
+    from neuralbody_b200 import dist as nbdist
+    scene, rkw, _ = golden_case("batch2_s32")
+    net, ren = G.make_net_and_renderer(scene)
+    batch = {k: scene[k].cuda() for k in G.BATCH_KEYS}
+    for precision in ("tc_fp16x3", "fp32"):
+        from neuralbody_b200.lib.config import cfg
+        cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.render_precision = 32, 0.0, False, precision
+        net.eval()
+        sp = ren.prepare_sp_input(batch)
+        vol = net.encode_sparse_voxels(sp)
+        with torch.no_grad():
+            dense = ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp)
+            slab, views = nbdist.new_slab(batch["ray_o"].shape[0], batch["ray_o"].shape[1], "cuda")
+            slab.fill_(-7.0)
+            ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp, out=views)
+        torch.cuda.synchronize()
+        for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
+            assert torch.equal(torch.nan_to_num(dense[k], nan=-1.0), torch.nan_to_num(views[k], nan=-1.0)), (precision, k)
+
+
+def test_two_frames_through_one_renderer():
+    """The pack caches must not serve frame k's latent code / volumes to frame k+1 (fresh tensors that may land on recycled
+    addresses): two frames with different latent_index and different volumes through ONE Renderer equal fresh renderers."""
+    from oracle import synth
+    from neuralbody_b200.lib.config import cfg
+    frames = [synth.make_scene(H=24, W=24, scale=0.25, all_hit=True, latent_index=li, volume_seed=vs)
+              for li, vs in ((3, 313), (11, 999))]
+    net, ren = G.make_net_and_renderer(frames[0])
+    cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.render_precision = 64, 0.0, False, "tc_fp16x3"
+    net.eval()
+    got = []
+    for rep in range(2):
+        for f in frames:
+            net.set_feature_volume([v.clone().cuda() for v in f["volumes"]])     # fresh device tensors every frame
+            batch = {k: f[k].clone().cuda() for k in G.BATCH_KEYS}
+            with torch.no_grad():
+                got.append({k: v.cpu() for k, v in ren.render(batch).items()})
+            del batch
+    for i, f in enumerate(frames):
+        want = O.render(f, n_samples=64)
+        for rep in range(2):
+            for k in ("rgb_map", "depth_map", "acc_map"):
+                assert float((got[2 * rep + i][k] - want[k]).abs().max()) < 1e-3, (i, rep, k)
+    assert float((got[0]["rgb_map"] - got[1]["rgb_map"]).abs().max()) > 1e-2      # the frames do differ
+
+
+def test_config5_shape_batch_of_frames_128_samples():
+    """BASELINE config 5's shape at test size: B = 2 frames with their own pose and volume, 256x256 rays, 128 samples, one
+    Renderer batch; compared with the oracle on a strided subset of the rays (rays are independent)."""
+    from oracle import synth
+    from neuralbody_b200.lib.config import cfg
+    poses = [synth.make_scene(H=256, W=256, scale=0.3, all_hit=True, azimuth_deg=20.0 + 50.0 * p, Rh=(0.3 - 0.2 * p, -0.2, 0.1 + 0.3 * p),
+                              Th=(0.1 + 0.05 * p, 0.2, 1.0), volume_seed=313 + 5 * p, latent_index=2 + 3 * p) for p in range(2)]
+    scene = {k: torch.cat([q[k] for q in poses], 0) for k in G.BATCH_KEYS}
+    scene["volumes"] = [torch.cat([q["volumes"][l] for q in poses], 0) for l in range(4)]
+    scene["weights"], scene["voxel_size"] = poses[0]["weights"], poses[0]["voxel_size"]
+    net, ren = G.make_net_and_renderer(scene)
+    ren.stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    out = G.render_product(scene, precision="tc_fp16x3", n_samples=128, renderer=ren, net=net)
+    assert int(ren.stats[3]) == 2 and out["rgb_map"].shape == (2, 65536, 3)
+    idx = torch.arange(0, 65536, 97)
+    sub = dict(scene)
+    for k in ("ray_o", "ray_d", "near", "far"):
+        sub[k] = scene[k][:, idx].contiguous()
+    want = O.render(sub, n_samples=128)
+    for k in ("rgb_map", "depth_map", "acc_map"):
+        assert float((out[k][:, idx] - want[k]).abs().max()) < 1e-3, k
+    assert 0.05 < float(want["acc_map"].mean()) < 0.95
+
+
+def test_largest_frame_the_sample_ids_allow():
+    """1024 x 1024 rays x 128 samples = 2^27 samples in one frame: the list entries carry 28-bit sample ids (the renderer
+    leaves the tensor cores at 2^28); a strided subset is compared with the oracle."""
+    from oracle import synth
+    scene = synth.make_scene(H=1024, W=1024, scale=0.3, all_hit=True)
+    assert scene["ray_o"].shape[1] * 128 == 1 << 27
+    net, ren = G.make_net_and_renderer(scene)
+    ren.stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    out = G.render_product(scene, precision="tc_fp16x3", n_samples=128, renderer=ren, net=net)
+    assert int(ren.stats[3]) == 1 and int(ren.stats[0]) > 0          # the tensor-core pipeline ran
+    idx = torch.arange(0, 1 << 20, 2053)
+    sub = dict(scene)
+    for k in ("ray_o", "ray_d", "near", "far"):
+        sub[k] = scene[k][:, idx].contiguous()
+    want = O.render(sub, n_samples=128)
+    for k in ("rgb_map", "depth_map", "acc_map"):
+        assert float((out[k][:, idx] - want[k]).abs().max()) < 1e-3, k
+    # one sample more per ray would not fit the ids: the renderer then takes the exact kernel instead of failing
+    from neuralbody_b200 import capi
+    from neuralbody_b200.lib.config import cfg
+    assert (1 << 20) * 256 >= (1 << 28)
