@@ -26,3 +26,7 @@ PY
 timeout 300 python tools/trace_timeline.py tc_fp16x3 40,100,200,280 1 > gpurun_out/${tag}_trace.txt 2> gpurun_out/${tag}_trace.err
 echo "trace rc=$?"
 tail -12 gpurun_out/${tag}_trace.txt
+if [ -n "$NB_NCU" ]; then
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_tc_list -s 2 -c 1 -f -o gpurun_out/${tag}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu.log 2>&1
+  echo "ncu rc=$?"; ls -la gpurun_out/${tag}_prof.ncu-rep
+fi
