@@ -195,29 +195,18 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t cta) 
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(cta));
     return r;
 }
-// arrive(1) on an mbarrier of another CTA of the cluster (release at cluster scope: what this thread wrote before -- and
-// fenced to the async proxy -- is visible to whoever observes the phase flip with an acquire.cluster wait)
+// arrive(1) on an mbarrier of another CTA of the cluster.  Default semantics (release at CTA scope), as CUTLASS's cross-CTA
+// arrives use: what the arriving thread hands over lives in ITS OWN SM (shared memory fenced to the async proxy, TMEM ordered
+// by tcgen05.wait / fence) and is consumed by that same SM's tensor core; the explicit .release.cluster form costs a
+// MEMBAR.ALL.GPU on every arrival (measured: it doubled the epilogue's time per 64-column chunk).
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, 1000000;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// wait on a LOCAL mbarrier that CTAs of the whole cluster arrive on
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-    uint32_t probes = 0;
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (++probes > NB_WATCHDOG_PROBES) __trap();
-    }
-}
+// wait on a LOCAL mbarrier that CTAs of the whole cluster arrive on.  Same instruction as mbar_wait (acquire at CTA scope,
+// as CUTLASS's 2-SM pipelines use): the waiter -- the MMA-issuing thread -- reads nothing through the generic proxy, and
+// the .acquire.cluster form makes ptxas append a CCTL.IVALL to every successful wait, i.e. it flushes the SM's L1 (which
+// the producers' gather lives on) some 45 times per tile.
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 
 // ---------------------------------------------------------------- TMEM <-> registers (warp w owns lanes 32*(w%4)..+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
