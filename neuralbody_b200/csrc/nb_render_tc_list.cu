@@ -62,11 +62,6 @@ constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry
 #define NB_CORNER_BATCH 8
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
-// 704 threads x 88 registers = 61 952 of the SM's 65 536 (22 warps x 11 allocation units): __launch_bounds__(704, 1) alone makes
-// ptxas stop at 80, which costs the producers' gather either spills or half of its loads in flight
-#ifndef NB_DECODER_REGS
-#define NB_DECODER_REGS 88
-#endif
 constexpr int L3_SPLIT = 11;                                       // layer-3 K-steps in its first ring slot (2.25 KB per step and CTA)
 constexpr int L4_BYTES = kStepsL4 * kHalfTile4 * 2;                // this CTA's half of the rgb head's 9 N=16 steps stays resident
 constexpr int HALF_TILE_BYTES = kHalfTile256 * 2;                  // one K-step of an N = 256 layer, this CTA's 128 rows (4 KB)
@@ -79,7 +74,8 @@ constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;
 constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;
 constexpr int OFF_L4 = OFF_RING + NUM_SLOTS * SLOT_BYTES;
 constexpr int OFF_XF = OFF_L4 + L4_BYTES;                          // FrameXf
-constexpr int OFF_BAR = OFF_XF + 128;
+constexpr int OFF_SCHED = OFF_XF + 128;                            // tile schedule of the frame (class counts and first tiles)
+constexpr int OFF_BAR = OFF_SCHED + 64;
 // W_FULL / L4W_FULL: this CTA's bulk copies landed.  W_PEER / L4W_PEER (leader only): the peer's did (relayed by the peer).
 // SEG_FULL / H_READY (leader only): producers / epilogue warps of BOTH CTAs arrive (the peer's remotely).  W_EMPTY / SEG_EMPTY /
 // ACC_FULL / RGB_FULL: the leader's tcgen05.commit, multicast to both CTAs.
@@ -209,7 +205,7 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
 
 // ------------------------------------------------------------------------------------------------ 2. decoder over the list
 template <int NP, typename VT>
-__global__ void __maxnreg__(NB_DECODER_REGS) render_tc_list_kernel(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
@@ -255,17 +251,29 @@ __global__ void __maxnreg__(NB_DECODER_REGS) render_tc_list_kernel(const __grid_
     // The frame's work: per sample class c (heaviest first) ceil(count_c / 128) tiles, rounded up to whole clusters so that the
     // CTAs of a cluster -- which walk the tiles in lockstep on one shared weight stream -- always work on the same class
     // (padding tiles have 0 rows).  Every role derives the same static schedule from the four list lengths.
-    const unsigned int cc0 = P.list_count[0], cc1 = P.list_count[1], cc2 = P.list_count[2], cc3 = P.list_count[3];   // (previous launch)
-    auto padded_tiles = [](unsigned int n) { return (int)(((n + TP - 1) / TP + CLUSTER - 1) / CLUSTER * CLUSTER); };
-    const int ts1 = padded_tiles(cc0), ts2 = ts1 + padded_tiles(cc1), ts3 = ts2 + padded_tiles(cc2);
-    const int n_tiles = ts3 + padded_tiles(cc3);
+    // (the schedule lives in shared memory, not in registers: it is read once per tile, and the producers' gather needs every
+    // register it can get for loads in flight)
+    struct Sched { unsigned int cnt[4]; int start[4]; int n_tiles; };
+    Sched* sched = reinterpret_cast<Sched*>(smem + OFF_SCHED);
+    if (tid == 0) {
+        int acc = 0;
+        for (int c = 0; c < 4; ++c) {
+            const unsigned int n = P.list_count[c];                         // written by classify_compact_kernel (previous launch)
+            sched->cnt[c] = n;
+            sched->start[c] = acc;
+            acc += (int)(((n + TP - 1) / TP + CLUSTER - 1) / CLUSTER * CLUSTER);
+        }
+        sched->n_tiles = acc;
+    }
+    __syncthreads();
+    const int n_tiles = sched->n_tiles;
     const int tile0 = (int)(blockIdx.x / CLUSTER) * CLUSTER;
     struct TileRef { int cls, nrows; const float4* ent; };
     auto tile_ref = [&](int tile) {
         TileRef r;
-        r.cls = tile >= ts3 ? 3 : tile >= ts2 ? 2 : tile >= ts1 ? 1 : 0;
-        const int lt = tile - (r.cls == 3 ? ts3 : r.cls == 2 ? ts2 : r.cls == 1 ? ts1 : 0);
-        const unsigned int cnt = r.cls == 3 ? cc3 : r.cls == 2 ? cc2 : r.cls == 1 ? cc1 : cc0;
+        r.cls = tile >= sched->start[3] ? 3 : tile >= sched->start[2] ? 2 : tile >= sched->start[1] ? 1 : 0;
+        const int lt = tile - sched->start[r.cls];
+        const unsigned int cnt = sched->cnt[r.cls];
         const long long rem = (long long)cnt - (long long)lt * TP;
         r.nrows = rem <= 0 ? 0 : rem < TP ? (int)rem : TP;
         const float4* buf = r.cls >= 2 ? P.list_a : P.list_b;
@@ -422,7 +430,7 @@ __global__ void __maxnreg__(NB_DECODER_REGS) render_tc_list_kernel(const __grid_
         if (tid == 0 && P.stats) {
             atomicAdd(P.stats + 0, (unsigned long long)real_tiles);
             atomicAdd(P.stats + 4, (unsigned long long)real_ksteps);
-            if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)cc0 + cc1 + cc2 + cc3);
+            if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)sched->cnt[0] + sched->cnt[1] + sched->cnt[2] + sched->cnt[3]);
         }
     }
     // ================================================================== LOADER (each CTA streams ITS half of every weight step)

@@ -288,6 +288,14 @@ class Renderer:
             raise ValueError("`out` maps must be dense, or columns of one (B, n, stride) float32 record")
         return st
 
+    def release(self):
+        """Drop every pooled / cached device buffer (activation records, backward scratch, workspace, packed blobs).  The pools
+        assume ONE stream drives this Renderer: call this only when no launch of it is in flight."""
+        self.__dict__.pop("_pool", None)
+        self.__dict__.pop("_ws_cache", None)
+        self._vol_key = self._vol_blob = self._vol_dims = self._vol_keep = None
+        self._w_key = self._w_blob = self._w_keep = None
+
     def _workspace(self, nbytes, dev):
         """Scratch for nb_render_fwd, grown on demand and reused by every later call on this device's stream."""
         cache = self.__dict__.setdefault("_ws_cache", {})
