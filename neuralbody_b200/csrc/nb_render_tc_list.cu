@@ -39,9 +39,20 @@ using tcr::Quad;
 using tcr::Tracer;
 
 constexpr int TP = 128;
-constexpr int NUM_SLOTS = 3;
-constexpr int STEP_BYTES = 8192;
-constexpr int SLOT_BYTES = 4 * STEP_BYTES;
+// weight ring: NB_NUM_SLOTS slots of NB_SLOT_KB KB.  32 KB slots take the hi AND lo tiles of a 4-K-step group of an N = 256 layer
+// (12 MMAs per hand-off); 16 KB slots take one plane (8 / 4 MMAs per hand-off) and leave room for a 4th layer-0 segment buffer.
+#ifndef NB_SLOT_KB
+#define NB_SLOT_KB 32
+#endif
+#ifndef NB_NUM_SLOTS
+#define NB_NUM_SLOTS 3
+#endif
+#ifndef NB_SEG_BUFS
+#define NB_SEG_BUFS 3
+#endif
+constexpr int NUM_SLOTS = NB_NUM_SLOTS;
+constexpr int SLOT_BYTES = NB_SLOT_KB * 1024;
+constexpr bool SPLIT_PLANES = SLOT_BYTES < 32768;                  // hi and lo tiles of a group travel in separate slots
 constexpr int CHUNK_BYTES = 2048;
 constexpr int SEG_CHUNKS = 8;
 constexpr int NUM_SEGS = 6;
@@ -49,8 +60,9 @@ constexpr int NUM_SEGS = 6;
 // core-matrix stride LBO is a free descriptor field), which rotates successive chunks by 4 banks: the 4 rows (two apart) x 8
 // channel quads a producer warp stores per instruction then cover every bank exactly twice (256 B = two wavefronts)
 constexpr int SEG_CHUNK_STRIDE = CHUNK_BYTES + 16;
-constexpr int SEG_RING_BYTES = 6 * SEG_CHUNKS * SEG_CHUNK_STRIDE;  // 96.75 KB: 3 x (hi+lo) or 6 x hi
-constexpr int MAX_SEG_BUFS = 6;
+constexpr int SEG_BUFS_3PASS = NB_SEG_BUFS;                        // (hi + lo) segment buffers in the 3-pass mode; hi-only mode: twice as many
+constexpr int SEG_RING_BYTES = 2 * SEG_BUFS_3PASS * SEG_CHUNKS * SEG_CHUNK_STRIDE;  // 96.75 KB at 3 buffers
+constexpr int MAX_SEG_BUFS = 2 * SEG_BUFS_3PASS;
 constexpr int PE_CHUNKS = 12;
 constexpr int PROD_WARPS = 16, EPI_WARP0 = 16, EPI_WARPS = 4, MMA_WARP = 20, LOAD_WARP = 21;
 constexpr int NT = (LOAD_WARP + 1) * 32;                          // 704
@@ -62,7 +74,7 @@ constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry
 #define NB_CORNER_BATCH 8
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
-constexpr int L3_SPLIT = 11;                                       // layer-3 K-steps in its first ring slot (2.25 KB per step and CTA)
+constexpr int L3_SPLIT = SPLIT_PLANES ? 7 : 11;                    // layer-3 K-steps per ring slot (2.25 KB per step and CTA)
 constexpr int L4_BYTES = kStepsL4 * kHalfTile4 * 2;                // this CTA's half of the rgb head's 9 N=16 steps stays resident
 constexpr int HALF_TILE_BYTES = kHalfTile256 * 2;                  // one K-step of an N = 256 layer, this CTA's 128 rows (4 KB)
 constexpr int L3_TILE_BYTES = kHalfTile3 * 2;                      // one K-step of layer 3, this CTA's 72 rows (2.25 KB)
@@ -92,6 +104,13 @@ constexpr uint32_t TM_R0 = 0, TM_R1 = 256;
 // layer-3 accumulator (R1): columns [0,64) colour 0..63 | 64, 65 alpha_fc hi / lo rows | [72,136) colour 64..127 (nb_layout.h)
 constexpr uint32_t TM_SIGMA = TM_R1 + 64;
 constexpr uint32_t TM_RGB = TM_R1 + 192;       // layer-4 accumulator (16 columns), beyond layer 3's 144
+
+// weight-ring pushes of one tile (the loader issues them, the peer's relay forwards their completions): layer 0 of a class with
+// `l0_ksteps` K-steps, layers 1 / 2, layer 3
+__host__ __device__ constexpr int pushes_per_tile(int l0_ksteps, int passes) {
+    const int planes = (SPLIT_PLANES && passes == 3) ? 2 : 1;
+    return ((l0_ksteps + 3) / 4) * planes + 1 + 2 * ((kKsL12 / 4) * planes + 1) + (kStepsL3 + L3_SPLIT - 1) / L3_SPLIT;
+}
 
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
@@ -212,7 +231,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     FrameXf* xf = reinterpret_cast<FrameXf*>(smem + OFF_XF);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = P.n_samples;
-    constexpr int NUM_SEG_BUFS = (NP == 3) ? 3 : 6;
+    constexpr int NUM_SEG_BUFS = (NP == 3) ? SEG_BUFS_3PASS : 2 * SEG_BUFS_3PASS;
     constexpr int SEG_BYTES = SEG_RING_BYTES / NUM_SEG_BUFS;
 
     if (warp == MMA_WARP) tc::tmem_alloc_pair<512>(tmem_slot);        // the same warp of both CTAs
@@ -437,6 +456,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     else if (warp == LOAD_WARP) {
         if (lane == 0) {
             uint32_t cnt = 0;
+            Tracer tr;
+            tr.init(P.trace, 3);
             const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
             // the rgb head's weights stay resident
             tc::mbar_arrive_expect_tx(&bars[BAR_L4W_FULL], L4_BYTES);
@@ -444,28 +465,40 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             auto push = [&](const unsigned char* src, uint32_t bytes, const unsigned char* src2 = nullptr, uint32_t bytes2 = 0) {
                 const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
                 unsigned char* dst = smem + OFF_RING + slot * SLOT_BYTES;
+                tr.ev(2);
                 tc::mbar_wait(&bars[BAR_W_EMPTY + slot], (round & 1) ^ 1);
+                tr.ev(3);
                 tc::mbar_arrive_expect_tx(&bars[BAR_W_FULL + slot], bytes + bytes2);
                 tc::bulk_g2s(dst, src, bytes, &bars[BAR_W_FULL + slot]);
                 if (bytes2) tc::bulk_g2s(dst + bytes, src2, bytes2, &bars[BAR_W_FULL + slot]);
                 ++cnt;
             };
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
+                tr.ev(1);
                 const int l0_ksteps = class_ksteps(tile_ref(tbase).cls);      // both CTAs of the pair: same class
                 for (int layer = 0; layer < 3; ++layer) {
                     const int nks = layer == 0 ? kKsL0 : kKsL12;
                     const unsigned char* base = seq + 2 * (layer == 0 ? sL0 : layer == 1 ? sL1 : sL2);
                     for (int g0 = 0; g0 < (layer == 0 ? l0_ksteps : nks); g0 += 4) {
                         const int gs = (nks - g0) < 4 ? (nks - g0) : 4;
-                        // one slot = this CTA's gs hi tiles (+ gs lo tiles in the 3-pass mode), contiguous in the stream
-                        push(base + 2 * pair_group_offset(g0, (int)crank, nks), (NP == 3 ? 2 : 1) * gs * HALF_TILE_BYTES);
+                        // this CTA's gs hi tiles (+ gs lo tiles in the 3-pass mode) are contiguous in the stream: one slot, or two
+                        const unsigned char* grp = base + 2 * pair_group_offset(g0, (int)crank, nks);
+                        if (SPLIT_PLANES) {
+                            push(grp, gs * HALF_TILE_BYTES);
+                            if (NP == 3) push(grp + gs * HALF_TILE_BYTES, gs * HALF_TILE_BYTES);
+                        } else {
+                            push(grp, (NP == 3 ? 2 : 1) * gs * HALF_TILE_BYTES);
+                        }
                     }
                     push(base + 2 * pair_bias_offset((int)crank, nks), HALF_TILE_BYTES);
                 }
                 const unsigned char* l3 = seq + 2 * (sL3 + pair_l3_offset(0, (int)crank));
-                push(l3, L3_SPLIT * L3_TILE_BYTES);
-                push(l3 + L3_SPLIT * L3_TILE_BYTES, (kStepsL3 - 1 - L3_SPLIT) * L3_TILE_BYTES,
-                     reinterpret_cast<const unsigned char*>(P.wframe) + ((size_t)P.frame * 2 + crank) * L3_TILE_BYTES, L3_TILE_BYTES);
+                const unsigned char* fr = reinterpret_cast<const unsigned char*>(P.wframe) + ((size_t)P.frame * 2 + crank) * L3_TILE_BYTES;
+                for (int g0 = 0; g0 < kStepsL3; g0 += L3_SPLIT) {     // steps 0..20 from the common stream, the per-frame step 21 last
+                    const int common = min(L3_SPLIT, kStepsL3 - 1 - g0), last = g0 + L3_SPLIT >= kStepsL3;
+                    if (common > 0) push(l3 + (size_t)g0 * L3_TILE_BYTES, common * L3_TILE_BYTES, last ? fr : nullptr, last ? L3_TILE_BYTES : 0);
+                    else push(fr, L3_TILE_BYTES);
+                }
             }
         }
     }
@@ -478,7 +511,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             arrive_at_leader(BAR_L4W_PEER);
             uint32_t cnt = 0;
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
-                const int pushes = (class_ksteps(tile_ref(tbase).cls) + 3) / 4 + 1 + 2 * (kKsL12 / 4 + 1) + 2;
+                const int pushes = pushes_per_tile(class_ksteps(tile_ref(tbase).cls), NP);
                 for (int i = 0; i < pushes; ++i, ++cnt) {
                     const uint32_t slot = cnt % NUM_SLOTS;
                     tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
@@ -494,10 +527,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             // M = 256: the pair's two 128-row tiles; N = the whole layer width, each CTA holding half of the B rows
             constexpr uint32_t ID256 = tc::make_idesc_f16(256, 256), ID3 = tc::make_idesc_f16(256, kN3),
                                ID4 = tc::make_idesc_f16(256, kN4);
+            Tracer tr;
+            tr.init(P.trace, 1);
             auto wait_slot = [&](uint32_t& slot) {
                 slot = cnt % NUM_SLOTS;
+                tr.ev(40);
                 tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
+                tr.ev(41);
                 tc::mbar_wait_cluster(&bars[BAR_W_PEER + slot], (cnt / NUM_SLOTS) & 1);
+                tr.ev(42);
                 tc::tc_fence_after();
             };
             auto release_slot = [&](uint32_t slot) {
@@ -517,12 +555,12 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             auto b4 = [&](int ks) { return tc::make_smem_desc(l4_addr + ks * kHalfTile4 * 2, (kN4 / 2) * 16, 128); };
             // the epilogues of BOTH CTAs have converted columns [64 g, 64 g + 64) of the current activation region (K-steps 4g..4g+3)
             auto wait_h = [&](int g) {
+                tr.ev(44);
                 tc::mbar_wait_cluster(&bars[BAR_H_READY + g], (hphase >> g) & 1);
+                tr.ev(45);
                 hphase ^= 1u << g;
                 tc::tc_fence_after();
             };
-            Tracer tr;
-            tr.init(P.trace, 1);
             // layer 4 of the tile pair whose layer 3 was issued last: A = relu(colour hidden) in R1 (hi only), B resident
             auto issue_l4 = [&]() {
                 wait_h(0);
@@ -539,7 +577,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 for (int g = 0; g < 4; ++g) {
                     wait_h(g);
                     if (g == 0) tr.ev(30 + code);
-                    wait_slot(slot);                                            // [4 hi tiles | 4 lo tiles]
+                    wait_slot(slot);                                            // [4 hi tiles | 4 lo tiles], or the hi tiles alone
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t a = tmem + rin + 16 * (4 * g + i);
@@ -547,9 +585,10 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         if (NP == 3) tc::mma_ts_pair(tmem + rout, a + 8, b256(slot, i), ID256, true);
                     }
                     if (NP == 3) {
+                        if (SPLIT_PLANES) { release_slot(slot); wait_slot(slot); }      // the lo tiles come in their own slot
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            tc::mma_ts_pair(tmem + rout, tmem + rin + 16 * (4 * g + i), b256(slot, 4 + i), ID256, true);
+                            tc::mma_ts_pair(tmem + rout, tmem + rin + 16 * (4 * g + i), b256(slot, (SPLIT_PLANES ? 0 : 4) + i), ID256, true);
                     }
                     release_slot(slot);
                 }
@@ -574,14 +613,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     tr.ev(10 + seg);
                     const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * SEG_CHUNK_STRIDE;
                     const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
-                    wait_slot(slot);                                            // [nks hi tiles | nks lo tiles]
+                    wait_slot(slot);                                            // [nks hi tiles | nks lo tiles], or the hi tiles alone
                     for (int ks = 0; ks < nks; ++ks) {
                         tc::mma_ss_pair(tmem + TM_R0, a_seg(hi_addr, ks), b256(slot, ks), ID256, (seg | ks) != 0);
                         if (NP == 3) tc::mma_ss_pair(tmem + TM_R0, a_seg(lo_addr, ks), b256(slot, ks), ID256, true);
                     }
                     if (NP == 3) {
+                        if (SPLIT_PLANES) { release_slot(slot); wait_slot(slot); }
                         for (int ks = 0; ks < nks; ++ks)
-                            tc::mma_ss_pair(tmem + TM_R0, a_seg(hi_addr, ks), b256(slot, nks + ks), ID256, true);
+                            tc::mma_ss_pair(tmem + TM_R0, a_seg(hi_addr, ks), b256(slot, (SPLIT_PLANES ? 0 : nks) + ks), ID256, true);
                     }
                     release_slot(slot);
                     tc::mma_commit_pair(&bars[BAR_SEG_EMPTY + buf], CMASK);
@@ -596,9 +636,9 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 layer256(TM_R0, TM_R1, 1);       // layer 1: h0 (R0) -> R1
                 layer256(TM_R1, TM_R0, 2);       // layer 2: h1 (R1) -> R0
                 // ---- layer 3: A = h2 (R0); accumulator R1[0..143].  K-steps 0..15 over h2 (TMEM), 16..21 over the per-point
-                // tile (shared memory); two weight slots (steps 0..10, 11..21)
+                // tile (shared memory); L3_SPLIT steps per weight slot
                 for (int k = 0; k < kStepsL3; ++k) {
-                    if (k == 0 || k == L3_SPLIT) {
+                    if (k % L3_SPLIT == 0) {
                         if (k) release_slot(slot);
                         wait_slot(slot);
                     }
@@ -606,7 +646,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         wait_h(k >> 2);
                         if (k == 0) tr.ev(33);
                     }
-                    const int i = k < L3_SPLIT ? k : k - L3_SPLIT;
+                    const int i = k % L3_SPLIT;
                     if (k < 16) {
                         const uint32_t a = tmem + TM_R0 + 16 * k;
                         tc::mma_ts_pair(tmem + TM_R1, a, b3(slot, i, 0), ID3, k != 0);

@@ -40,7 +40,9 @@ def main():
             ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vol, sp, trace=trace)
     torch.cuda.synchronize()
     t = trace.cpu().view(4, 4096)
-    roles = [("PROD", PROD, 13, 1), ("MMA", MMA, None, 1), ("EPI", EPI, None, 1)]
+    MMA.update({40: "slot wait", 41: "slot: own half landed", 42: "slot: peer half landed", 44: "h wait", 45: "h ready"})
+    LOAD = {1: "tile begin", 2: "push: wait for a free slot", 3: "push: slot free, copy issued"}
+    roles = [("PROD", PROD, 13, 1), ("MMA", MMA, None, 1), ("EPI", EPI, None, 1), ("LOAD", LOAD, None, 1)]
     events = []
     for r, (name, names, _, begin_code) in enumerate(roles):
         tile = -1
