@@ -286,49 +286,27 @@ __global__ void stream_kernel(nb_decoder_weights w, const float* __restrict__ f3
             }
         }
     }
-    // L3: N = 144 as two 72-row halves.  common steps 0..20 -> seq, per-frame step 21 -> frame_steps[b][half]
+    // L3: the folded colour layer, N = 128 as two 64-row halves.  common steps 0..20 -> seq, per-frame step 21 -> frame_steps[b][half]
     for (int i = t0; i < (kStepsL3 - 1 + w.batch) * kN3 * 16; i += stride) {
         int st = i / (kN3 * 16);
-        const int r = (i / 16) % kN3, kk = i % 16;
-        const int half = r / (kN3 / 2), nl = r % (kN3 / 2);
-        // row of the logical 144-row layer this (half, local row) holds: colour row, alpha hi (128), alpha lo (129) or none (-1)
-        const int n = nl < 64 ? half * 64 + nl : (half == 0 && nl == 64) ? 128 : (half == 0 && nl == 65) ? 129 : -1;
+        const int n = (i / 16) % kN3, kk = i % 16;
+        const int half = n / (kN3 / 2), nl = n % (kN3 / 2);
         int b = 0;
         __half* dst;
         if (st >= kStepsL3 - 1) { b = st - (kStepsL3 - 1); st = kStepsL3 - 1; dst = frame_steps + ((size_t)b * 2 + half) * kHalfTile3; }
         else dst = seq + sL3 + pair_l3_offset(st, half);
         float v = 0.f;
         bool lo = false;
-        if (n >= 0 && st < 16) {
-            const int k = st * 16 + kk;
-            if (n < kColor) v = f32[oWct + (size_t)k * kColor + n];
-            else if (n == 128) v = w.alpha_w[k];
-            else { v = w.alpha_w[k]; lo = true; }
-        } else if (n >= 0) {
+        if (st < 16) {
+            v = f32[oWct + (size_t)(st * 16 + kk) * kColor + n];
+        } else {
             const int k2 = (st - 16) * 16 + kk;      // column of the per-point tile
-            if (n < kColor) {
-                if (k2 < kXyzPE) v = w.view_w[n * 346 + 283 + k2];
-                else if (k2 >= 64 && k2 < 64 + kViewPE) v = w.view_w[n * 346 + 256 + (k2 - 64)];
-                else if (k2 == 92) v = bc[b * kColor + n];
-                else if (k2 == 93) { v = bc[b * kColor + n]; lo = true; }
-            } else if (n == 128 && k2 == 92) v = w.alpha_b[0];
-            else if (n == 129 && k2 == 92) { v = w.alpha_b[0]; lo = true; }
+            if (k2 < kXyzPE) v = w.view_w[n * 346 + 283 + k2];
+            else if (k2 >= 64 && k2 < 64 + kViewPE) v = w.view_w[n * 346 + 256 + (k2 - 64)];
+            else if (k2 == 92) v = bc[b * kColor + n];
+            else if (k2 == 93) { v = bc[b * kColor + n]; lo = true; }
         }
         dst[step_offset(nl, kk, kN3 / 2)] = lo ? f16_lo(v) : f16_hi(v);
-    }
-    // L4: N = 16 as two 8-row halves; half 0 rows 0..2 = hi(rgb_fc), 3..5 = lo(rgb_fc); half 1 = zeros
-    for (int i = t0; i < kStepsL4 * kN4 * 16; i += stride) {
-        const int st = i / (kN4 * 16), r = (i / 16) % kN4, kk = i % 16;
-        const int half = r / 8, nl = r % 8;
-        float v = 0.f;
-        bool lo = false;
-        if (half == 0 && nl < 6) {
-            const int c = nl % 3;
-            lo = nl >= 3;
-            if (st < 8) v = w.rgb_w[c * kColor + st * 16 + kk];
-            else if (kk == 0) v = w.rgb_b[c];
-        }
-        seq[sL4 + pair_l4_offset(st, half) + step_offset(nl, kk, 8)] = lo ? f16_lo(v) : f16_hi(v);
     }
 }
 

@@ -68,7 +68,7 @@ constexpr size_t kF32Floats = oSigmaEmpty + 4;
 constexpr size_t kF16ByteOffset = ((kF32Floats * 4 + 255) / 256) * 256;
 constexpr int kKsL0 = 22, kKsL12 = 16;                     // K-steps of layers 0 and 1/2 (without the bias step)
 constexpr int kStepsL3 = 22, kStepsL4 = 9;
-constexpr int kN3 = 144, kN4 = 16;
+constexpr int kN3 = 128, kN4 = 16;                        // (kN4: the former tensor-core rgb head; its slot in the blob is unused)
 constexpr int kPeK = 96;                                   // per-point tile width of L3
 constexpr size_t kStepHalves256 = 256 * 16, kStepHalves3 = kN3 * 16, kStepHalves4 = kN4 * 16;
 constexpr size_t sL0 = 0;
@@ -95,10 +95,10 @@ __host__ __device__ inline int class_ksteps(int c) { return c == 0 ? 22 : c == 1
 // one ring slot is one contiguous run:
 //   N = 256 layers: group g of gs K-steps = [half 0: gs hi tiles, gs lo tiles][half 1: gs hi tiles, gs lo tiles]  (4 KB tiles);
 //                   bias step = [half 0 tile][half 1 tile]
-//   L3 (N = 144)  : [half 0: steps 0..20][half 1: steps 0..20] (72 x 16 tiles); the per-frame step 21 is [B][half][tile].
-//                   Rows of half 0: colour 0..63, alpha_fc hi, alpha_fc lo, 6 zero rows; half 1: colour 64..127, 8 zero rows
-//                   => accumulator columns [0,64) colour, 64 / 65 the density rows, [72,136) colour.
-//   L4 (N = 16)   : [half 0: 9 tiles of 8 x 16: rgb hi (3), rgb lo (3), 2 zero rows][half 1: zeros]
+//   L3 (N = 128)  : the folded colour layer: [half 0: steps 0..20][half 1: steps 0..20] (64 x 16 tiles); the per-frame step 21
+//                   is [B][half][tile].  alpha_fc (1 x 256) and rgb_fc (3 x 128) are NOT in the stream: the epilogue applies them
+//                   in fp32 to the accumulators it converts anyway (a 1- or 3-wide layer costs the tensor pipe a full
+//                   instruction slot per K-step -- measured ~200 cycles each -- for a few hundred FMAs per row).
 constexpr int kHalfTile256 = 128 * 16;                     // halves in one (N/2 = 128) x 16 tile
 constexpr int kHalfTile3 = (kN3 / 2) * 16;                 // 72 x 16
 constexpr int kHalfTile4 = (kN4 / 2) * 16;                 // 8 x 16

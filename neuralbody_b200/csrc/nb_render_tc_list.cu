@@ -52,6 +52,10 @@ constexpr int TP = 128;
 #endif
 constexpr int NUM_SLOTS = NB_NUM_SLOTS;
 constexpr int SLOT_BYTES = NB_SLOT_KB * 1024;
+#ifndef NB_PROD_WAIT_NS
+#define NB_PROD_WAIT_NS 200
+#endif
+constexpr unsigned PROD_WAIT_NS = NB_PROD_WAIT_NS;                 // sleep between the producers' probes for a free segment buffer
 constexpr bool SPLIT_PLANES = SLOT_BYTES < 32768;                  // hi and lo tiles of a group travel in separate slots
 constexpr int CHUNK_BYTES = 2048;
 constexpr int SEG_CHUNKS = 8;
@@ -75,36 +79,35 @@ constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
 constexpr int L3_SPLIT = SPLIT_PLANES ? 7 : 11;                    // layer-3 K-steps per ring slot (2.25 KB per step and CTA)
-constexpr int L4_BYTES = kStepsL4 * kHalfTile4 * 2;                // this CTA's half of the rgb head's 9 N=16 steps stays resident
+constexpr int HEAD_FLOATS = kHidden + 4 + 3 * kColor + 4;           // alpha_fc (256 + bias) and rgb_fc (3 x 128 + bias), fp32, resident
 constexpr int HALF_TILE_BYTES = kHalfTile256 * 2;                  // one K-step of an N = 256 layer, this CTA's 128 rows (4 KB)
-constexpr int L3_TILE_BYTES = kHalfTile3 * 2;                      // one K-step of layer 3, this CTA's 72 rows (2.25 KB)
+constexpr int L3_TILE_BYTES = kHalfTile3 * 2;                      // one K-step of layer 3, this CTA's 64 rows (2 KB)
 
 // shared-memory map (bytes)
 constexpr int OFF_SEG = 0;
 constexpr int OFF_ONES = OFF_SEG + SEG_RING_BYTES;
 constexpr int OFF_PE = OFF_ONES + 2 * CHUNK_BYTES;
 constexpr int OFF_RING = OFF_PE + PE_CHUNKS * CHUNK_BYTES;
-constexpr int OFF_L4 = OFF_RING + NUM_SLOTS * SLOT_BYTES;
-constexpr int OFF_XF = OFF_L4 + L4_BYTES;                          // FrameXf
+constexpr int OFF_HEAD = OFF_RING + NUM_SLOTS * SLOT_BYTES;        // [alpha_w 256 | alpha_b 4 | rgb_w 3 x 128 | rgb_b 4] floats
+constexpr int OFF_XF = OFF_HEAD + HEAD_FLOATS * 4;                 // FrameXf
 constexpr int OFF_SCHED = OFF_XF + 128;                            // tile schedule of the frame (class counts and first tiles)
 constexpr int OFF_BAR = OFF_SCHED + 64;
-// W_FULL / L4W_FULL: this CTA's bulk copies landed.  W_PEER / L4W_PEER (leader only): the peer's did (relayed by the peer).
-// SEG_FULL / H_READY (leader only): producers / epilogue warps of BOTH CTAs arrive (the peer's remotely).  W_EMPTY / SEG_EMPTY /
-// ACC_FULL / RGB_FULL: the leader's tcgen05.commit, multicast to both CTAs.
-enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_W_PEER = 2 * NUM_SLOTS, BAR_SEG_FULL = 3 * NUM_SLOTS,
-       BAR_SEG_EMPTY = 3 * NUM_SLOTS + MAX_SEG_BUFS, BAR_ACC_FULL = 3 * NUM_SLOTS + 2 * MAX_SEG_BUFS, BAR_RGB_FULL, BAR_L4W_FULL,
-       BAR_L4W_PEER, BAR_H_READY /* x4: one per 64 columns */, NUM_BARS = BAR_H_READY + 4 };
+// W_FULL[slot]: this CTA's bulk copy landed (transaction bytes + the loader's arrival) AND, on the leader, the peer's did (a
+// second arrival, relayed by the peer: a bulk copy can only signal an mbarrier of its destination CTA).  SEG_FULL / H_READY
+// (leader only): producers / epilogue warps of BOTH CTAs arrive (the peer's remotely).  W_EMPTY / SEG_EMPTY / ACC_FULL: the
+// leader's tcgen05.commit, multicast to both CTAs.
+enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + MAX_SEG_BUFS,
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS /* x2, see below */, BAR_H_READY = BAR_ACC_FULL + 2 /* x4: one per 64 columns */,
+       NUM_BARS = BAR_H_READY + 4 };
+// ACC_FULL alternates between two barriers (layers 0 / 2 -> [0], layers 1 / 3 -> [1]): the issuer can run a whole layer 0 of
+// the next tile ahead of the epilogue, and with one barrier it could complete two phases before the epilogue looked at the first.
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-static_assert(OFF_L4 % 128 == 0 && OFF_RING % 128 == 0 && OFF_PE % 128 == 0, "operand alignment");
+static_assert(OFF_RING % 128 == 0 && OFF_PE % 128 == 0 && OFF_HEAD % 16 == 0, "operand alignment");
 
 // TMEM: two 256-column regions; K-step k of an activation operand occupies columns [16k, 16k+8) (hi) and [16k+8, 16k+16) (lo)
-constexpr uint32_t TM_R0 = 0, TM_R1 = 256;
-// layer-3 accumulator (R1): columns [0,64) colour 0..63 | 64, 65 alpha_fc hi / lo rows | [72,136) colour 64..127 (nb_layout.h)
-constexpr uint32_t TM_SIGMA = TM_R1 + 64;
-constexpr uint32_t TM_RGB = TM_R1 + 192;       // layer-4 accumulator (16 columns), beyond layer 3's 144
-
+constexpr uint32_t TM_R0 = 0, TM_R1 = 256;     // (layer 3 accumulates its 128 colour columns into R1[0,128))
 // weight-ring pushes of one tile (the loader issues them, the peer's relay forwards their completions): layer 0 of a class with
 // `l0_ksteps` K-steps, layers 1 / 2, layer 3
 __host__ __device__ constexpr int pushes_per_tile(int l0_ksteps, int passes) {
@@ -236,14 +239,14 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
 
     if (warp == MMA_WARP) tc::tmem_alloc_pair<512>(tmem_slot);        // the same warp of both CTAs
     if (tid == LOAD_WARP * 32) {
+        const bool lead = tc::cluster_ctarank() == 0;
         for (int i = 0; i < NUM_SLOTS; ++i) {
-            tc::mbar_init(&bars[BAR_W_FULL + i], 1); tc::mbar_init(&bars[BAR_W_EMPTY + i], 1); tc::mbar_init(&bars[BAR_W_PEER + i], 1);
+            tc::mbar_init(&bars[BAR_W_FULL + i], lead ? 2 : 1);      // the leader's also counts the peer's relayed completion
+            tc::mbar_init(&bars[BAR_W_EMPTY + i], 1);
         }
         for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], CLUSTER * PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
-        tc::mbar_init(&bars[BAR_RGB_FULL], 1);
-        tc::mbar_init(&bars[BAR_L4W_FULL], 1);
-        tc::mbar_init(&bars[BAR_L4W_PEER], 1);
+        tc::mbar_init(&bars[BAR_ACC_FULL + 1], 1);
         for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[BAR_H_READY + i], CLUSTER * EPI_WARPS);
         tc::fence_mbar_init();
     }
@@ -254,6 +257,12 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             *reinterpret_cast<uint4*>(o + CHUNK_BYTES + (tid >> 3) * 128 + (tid & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
         load_frame_xf(P, xf, tid);
+        // the two narrow heads, fp32: alpha_fc (latent_xyzc.py:104) and rgb_fc (:124) are applied by the epilogue
+        float* head = reinterpret_cast<float*>(smem + OFF_HEAD);
+        for (int i = tid; i < HEAD_FLOATS; i += PROD_WARPS * 32) {
+            const int j = i - (kHidden + 4);
+            head[i] = i < kHidden + 4 ? __ldg(P.wf32 + oAlphaW + i) : __ldg(P.wf32 + oRgbW + j);     // [alpha_w | alpha_b] / [rgb_w | rgb_b]
+        }
         tc::fence_proxy_async();
     }
     tc::tc_fence_before();
@@ -344,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             int cur_lvl = -1;
             for (int seg = 0; seg < nseg; ++seg, ++gseg) {
                 const uint32_t buf = gseg % NUM_SEG_BUFS;
-                tc::mbar_wait(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1);
+                tc::mbar_wait_backoff(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1, PROD_WAIT_NS);
                 tr.ev(10 + seg);
                 // this thread's (row, channel quad) slot of the hi plane; the lo plane follows SEG_CHUNKS chunk strides later
                 const uint32_t dst = seg_base + buf * SEG_BYTES + so0;
@@ -459,9 +468,6 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             Tracer tr;
             tr.init(P.trace, 3);
             const unsigned char* seq = reinterpret_cast<const unsigned char*>(P.wf16);
-            // the rgb head's weights stay resident
-            tc::mbar_arrive_expect_tx(&bars[BAR_L4W_FULL], L4_BYTES);
-            tc::bulk_g2s(smem + OFF_L4, seq + 2 * (sL4 + pair_l4_offset(0, (int)crank)), L4_BYTES, &bars[BAR_L4W_FULL]);
             auto push = [&](const unsigned char* src, uint32_t bytes, const unsigned char* src2 = nullptr, uint32_t bytes2 = 0) {
                 const uint32_t slot = cnt % NUM_SLOTS, round = cnt / NUM_SLOTS;
                 unsigned char* dst = smem + OFF_RING + slot * SLOT_BYTES;
@@ -506,36 +512,38 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     else if (warp == MMA_WARP) {
         if (lane == 0 && !leader) {
             // The leader must know that THIS CTA's half of a weight slot has landed, but a bulk copy can only signal an mbarrier
-            // of its destination CTA: this thread watches the local W_FULL barriers in push order and forwards each completion.
-            tc::mbar_wait(&bars[BAR_L4W_FULL], 0);
-            arrive_at_leader(BAR_L4W_PEER);
+            // of its destination CTA: this thread watches the local W_FULL barriers in push order and forwards each completion
+            // as the second arrival of the leader's W_FULL barrier of the same slot.
             uint32_t cnt = 0;
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
                 const int pushes = pushes_per_tile(class_ksteps(tile_ref(tbase).cls), NP);
                 for (int i = 0; i < pushes; ++i, ++cnt) {
                     const uint32_t slot = cnt % NUM_SLOTS;
                     tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
-                    arrive_at_leader(BAR_W_PEER + slot);
+                    arrive_at_leader(BAR_W_FULL + slot);
                 }
             }
         }
         if (lane == 0 && leader) {
-            uint32_t cnt = 0, hphase = 0, it = 0, gseg = 0;
+            uint32_t cnt = 0, hphase = 0, gseg = 0;
             const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
             const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
-            const uint32_t l4_addr = tc::smem_u32(smem + OFF_L4);
             // M = 256: the pair's two 128-row tiles; N = the whole layer width, each CTA holding half of the B rows
-            constexpr uint32_t ID256 = tc::make_idesc_f16(256, 256), ID3 = tc::make_idesc_f16(256, kN3),
-                               ID4 = tc::make_idesc_f16(256, kN4);
+            constexpr uint32_t ID256 = tc::make_idesc_f16(256, 256), ID3 = tc::make_idesc_f16(256, kN3);
             Tracer tr;
             tr.init(P.trace, 1);
+            // The tensor pipe queues only a few instructions, so whatever the issuer does between two MMAs beyond ~the queue's
+            // worth of cycles is a bubble (the trace showed ~750 cycles of barrier round trips per 1536-cycle group).  Hence:
+            // ONE barrier per weight slot, and the barriers of the NEXT group are probed (non-blocking) in the middle of the
+            // current group's MMAs; only a probe that failed is waited for.
+            bool slot_seen = false;                          // the next slot's phase was already observed complete
+            auto probe_slot = [&]() {
+                slot_seen = tc::mbar_test(&bars[BAR_W_FULL + cnt % NUM_SLOTS], (cnt / NUM_SLOTS) & 1);
+            };
             auto wait_slot = [&](uint32_t& slot) {
                 slot = cnt % NUM_SLOTS;
-                tr.ev(40);
-                tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1);
-                tr.ev(41);
-                tc::mbar_wait_cluster(&bars[BAR_W_PEER + slot], (cnt / NUM_SLOTS) & 1);
-                tr.ev(42);
+                if (!slot_seen) { tr.ev(40); tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1); tr.ev(42); }
+                slot_seen = false;
                 tc::tc_fence_after();
             };
             auto release_slot = [&](uint32_t slot) {
@@ -548,28 +556,19 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             auto b256 = [&](uint32_t slot, int i) {
                 return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * HALF_TILE_BYTES, 128 * 16, 128);
             };
-            // step i of a layer-3 slot (72-row half tiles); row0: first local row of the rows used
-            auto b3 = [&](uint32_t slot, int i, int row0) {
-                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * L3_TILE_BYTES + row0 * 16, (kN3 / 2) * 16, 128);
+            auto b3 = [&](uint32_t slot, int i) {            // step i of a layer-3 slot (64-row half tiles)
+                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * L3_TILE_BYTES, (kN3 / 2) * 16, 128);
             };
-            auto b4 = [&](int ks) { return tc::make_smem_desc(l4_addr + ks * kHalfTile4 * 2, (kN4 / 2) * 16, 128); };
             // the epilogues of BOTH CTAs have converted columns [64 g, 64 g + 64) of the current activation region (K-steps 4g..4g+3)
+            uint32_t h_seen = 0;                             // bit g: chunk g's phase was already observed complete
+            auto probe_h = [&](int g) {
+                if (tc::mbar_test(&bars[BAR_H_READY + g], (hphase >> g) & 1)) h_seen |= 1u << g;
+            };
             auto wait_h = [&](int g) {
-                tr.ev(44);
-                tc::mbar_wait_cluster(&bars[BAR_H_READY + g], (hphase >> g) & 1);
-                tr.ev(45);
+                if (!((h_seen >> g) & 1)) { tr.ev(44); tc::mbar_wait_cluster(&bars[BAR_H_READY + g], (hphase >> g) & 1); tr.ev(45); }
+                h_seen &= ~(1u << g);
                 hphase ^= 1u << g;
                 tc::tc_fence_after();
-            };
-            // layer 4 of the tile pair whose layer 3 was issued last: A = relu(colour hidden) in R1 (hi only), B resident
-            auto issue_l4 = [&]() {
-                wait_h(0);
-                wait_h(1);
-                tr.ev(34);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks) tc::mma_ts_pair(tmem + TM_RGB, tmem + TM_R1 + 16 * ks, b4(ks), ID4, ks > 0);
-                tc::mma_ss_pair(tmem + TM_RGB, a_desc(ones_addr, 0), b4(8), ID4, true);
-                tc::mma_commit_pair(&bars[BAR_RGB_FULL], CMASK);
             };
             // a 256 -> 256 layer: A = activations in region `rin` (TMEM), accumulator = region `rout`
             auto layer256 = [&](uint32_t rin, uint32_t rout, int code) {
@@ -586,20 +585,20 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     }
                     if (NP == 3) {
                         if (SPLIT_PLANES) { release_slot(slot); wait_slot(slot); }      // the lo tiles come in their own slot
+                        else if (g < 3) probe_h(g + 1);                                 // (probes ride under the 8 MMAs just queued)
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             tc::mma_ts_pair(tmem + rout, tmem + rin + 16 * (4 * g + i), b256(slot, (SPLIT_PLANES ? 0 : 4) + i), ID256, true);
                     }
                     release_slot(slot);
+                    probe_slot();
                 }
                 wait_slot(slot);
                 tc::mma_ss_pair(tmem + rout, a_desc(ones_addr, 0), b256(slot, 0), ID256, true);
                 release_slot(slot);
-                tc::mma_commit_pair(&bars[BAR_ACC_FULL], CMASK);
+                tc::mma_commit_pair(&bars[BAR_ACC_FULL + (code & 1)], CMASK);
                 tr.ev(20 + code);
             };
-            tc::mbar_wait(&bars[BAR_L4W_FULL], 0);
-            tc::mbar_wait_cluster(&bars[BAR_L4W_PEER], 0);
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
                 uint32_t slot;
                 tr.ev(1);
@@ -625,8 +624,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     }
                     release_slot(slot);
                     tc::mma_commit_pair(&bars[BAR_SEG_EMPTY + buf], CMASK);
-                    // the previous tile's rgb head, once its layer-3 epilogue is through (it ran under the MMAs above)
-                    if (seg == 0 && it > 0) issue_l4();
+                    probe_slot();
                 }
                 wait_slot(slot);
                 tc::mma_ss_pair(tmem + TM_R0, a_desc(ones_addr, 0), b256(slot, 0), ID256, true);
@@ -635,11 +633,11 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 tr.ev(20);
                 layer256(TM_R0, TM_R1, 1);       // layer 1: h0 (R0) -> R1
                 layer256(TM_R1, TM_R0, 2);       // layer 2: h1 (R1) -> R0
-                // ---- layer 3: A = h2 (R0); accumulator R1[0..143].  K-steps 0..15 over h2 (TMEM), 16..21 over the per-point
-                // tile (shared memory); L3_SPLIT steps per weight slot
+                // ---- layer 3 (the folded colour layer, N = 128): A = h2 (R0) for K-steps 0..15, the per-point tile (shared memory)
+                // for 16..21; accumulator R1[0,128); L3_SPLIT steps per weight slot.  (R1 held h1, last read by layer 2.)
                 for (int k = 0; k < kStepsL3; ++k) {
                     if (k % L3_SPLIT == 0) {
-                        if (k) release_slot(slot);
+                        if (k) { release_slot(slot); }
                         wait_slot(slot);
                     }
                     if (k < 16 && (k & 3) == 0) {
@@ -647,22 +645,15 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         if (k == 0) tr.ev(33);
                     }
                     const int i = k % L3_SPLIT;
-                    if (k < 16) {
-                        const uint32_t a = tmem + TM_R0 + 16 * k;
-                        tc::mma_ts_pair(tmem + TM_R1, a, b3(slot, i, 0), ID3, k != 0);
-                        // the lo half of the activations only matters on the density path: local rows 64..71 of each CTA's half
-                        // (rank 0: alpha_fc hi / lo + zeros, rank 1: zeros) -> accumulator columns 64..79
-                        if (NP == 3) tc::mma_ts_pair(tmem + TM_SIGMA, a + 8, b3(slot, i, 64), ID4, true);
-                    } else {
-                        tc::mma_ss_pair(tmem + TM_R1, a_desc(pe_addr, k - 16), b3(slot, i, 0), ID3, true);
-                    }
+                    if (k < 16) tc::mma_ts_pair(tmem + TM_R1, tmem + TM_R0 + 16 * k, b3(slot, i), ID3, k != 0);
+                    else tc::mma_ss_pair(tmem + TM_R1, a_desc(pe_addr, k - 16), b3(slot, i), ID3, true);
+                    if (k < 12 && (k & 3) == 1) probe_h((k >> 2) + 1);
                 }
                 release_slot(slot);
-                tc::mma_commit_pair(&bars[BAR_ACC_FULL], CMASK);
+                tc::mma_commit_pair(&bars[BAR_ACC_FULL + 1], CMASK);
+                probe_slot();
                 tr.ev(23);
-                ++it;
             }
-            if (it > 0) issue_l4();
         }
     }
     // ================================================================== EPILOGUE (thread = tile row)
@@ -670,22 +661,33 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         const int row = tid - EPI_WARP0 * 32;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         unsigned char* PE = smem + OFF_PE;
-        uint32_t acnt = 0, rcnt = 0;
+        const float* head = reinterpret_cast<const float*>(smem + OFF_HEAD);     // [alpha_w 256 | alpha_b 4 | rgb_w 384 | rgb_b 4]
+        uint32_t acnt = 0;                       // accumulators consumed so far: layer l of a tile uses barrier l & 1
         Tracer tr;
         tr.init(row == 0 ? P.trace : nullptr, 2);
-        auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL], acnt & 1); ++acnt; tc::tc_fence_after(); };
+        auto wait_acc = [&]() { tc::mbar_wait(&bars[BAR_ACC_FULL + (acnt & 1)], (acnt >> 1) & 1); ++acnt; tc::tc_fence_after(); };
         // accumulator region `reg` -> relu -> fp16 operand of the next layer, in place: the 16 fp32 columns of K-step k become
-        // 8 columns of hi pairs [16k, 16k+8) and (3-pass mode, with_lo) 8 columns of lo pairs [16k+8, 16k+16).  H_READY[g]
-        // is signalled after every 4 K-steps, so the issuer can start the next layer on the first converted quarter.
-        auto convert_region = [&](uint32_t reg, int nblocks, bool with_lo, bool l3 = false) {
+        // 8 columns of hi pairs [16k, 16k+8) and (3-pass mode) 8 columns of lo pairs [16k+8, 16k+16).  H_READY[g] is signalled
+        // after every 4 K-steps, so the issuer can start the next layer on the first converted quarter.  SIGMA: this is h2 --
+        // also accumulate alpha_fc . relu(x) in fp32 (latent_xyzc.py:104), exactly, instead of a 1-wide tensor-core layer.
+        auto convert_region = [&](uint32_t reg, bool sigma_too) {
             uint32_t va[16], vb[16];
             const uint32_t base = lane_base + reg;
-            // layer 3's accumulator keeps its 128 colour columns as [0,64) and [72,136) (8 density columns in between): block k
-            // is read from there and written, compacted, to the operand position [16k, 16k+8) -- always behind the read front
-            auto src = [&](int k) { return base + 16 * k + ((l3 && k >= 4) ? 8 : 0); };
+            float sig = 0.f;
             auto convert_store = [&](const uint32_t (&v)[16], int k) {
                 uint32_t h[8];
-                if (NP == 3 && with_lo) {
+                if (sigma_too) {
+                    const float4* aw = reinterpret_cast<const float4*>(head + 16 * k);      // same address in every lane: broadcast
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w4 = aw[q];
+                        sig = fmaf(fmaxf(__uint_as_float(v[4 * q + 0]), 0.f), w4.x, sig);
+                        sig = fmaf(fmaxf(__uint_as_float(v[4 * q + 1]), 0.f), w4.y, sig);
+                        sig = fmaf(fmaxf(__uint_as_float(v[4 * q + 2]), 0.f), w4.z, sig);
+                        sig = fmaf(fmaxf(__uint_as_float(v[4 * q + 3]), 0.f), w4.w, sig);
+                    }
+                }
+                if (NP == 3) {
                     uint32_t l[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -711,18 +713,19 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     if (lane == 0) arrive_at_leader(BAR_H_READY + (k >> 2));     // one arrival per warp, 4 + 4 warps of the pair
                 }
             };
-            tc::tmem_ld16(src(0), va);
+            tc::tmem_ld16(base, va);
             tc::tmem_ld_wait(va);
-            for (int k = 0; k < nblocks; k += 2) {
-                tc::tmem_ld16(src(k + 1), vb);
+            for (int k = 0; k < 16; k += 2) {
+                tc::tmem_ld16(base + 16 * (k + 1), vb);
                 convert_store(va, k);
                 chunk_done(k);
                 tc::tmem_ld_wait(vb);
-                if (k + 2 < nblocks) tc::tmem_ld16(src(k + 2), va);
+                if (k + 2 < 16) tc::tmem_ld16(base + 16 * (k + 2), va);
                 convert_store(vb, k + 1);
                 chunk_done(k + 1);
-                if (k + 2 < nblocks) tc::tmem_ld_wait(va);
+                if (k + 2 < 16) tc::tmem_ld_wait(va);
             }
+            return sig;
         };
 
         for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             tr.ev(1);
             {
                 // the per-point tile of layer 3: [PE(xyz) 63 | 0 | PE(view) 27 | 0 | 1 | 1 | 0 | 0].  The previous tile's layer 3
-                // has read it: this thread waited for that tile's RGB_FULL, which is committed after every earlier MMA.
+                // has read it: this thread waited for that layer's ACC_FULL, which is committed after all of its MMAs.
                 __half* peh = reinterpret_cast<__half*>(PE);
                 auto put = [&](int k, float v) {
                     peh[((k >> 3) * 16 + (row >> 3)) * 64 + (row & 7) * 8 + (k & 7)] = __float2half_rn(v);
@@ -752,35 +755,48 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             }
             tr.ev(2);
             wait_acc(); tr.ev(10);
-            convert_region(TM_R0, 16, true);     // h0
+            convert_region(TM_R0, false);        // h0
             tr.ev(20);
             wait_acc(); tr.ev(11);
-            convert_region(TM_R1, 16, true);     // h1
+            convert_region(TM_R1, false);        // h1
             tr.ev(21);
             wait_acc(); tr.ev(12);
-            convert_region(TM_R0, 16, true);     // h2
+            const float sigma = convert_region(TM_R0, true) + head[kHidden];     // h2, and sigma = alpha_fc . h2 + bias
             tr.ev(22);
             wait_acc(); tr.ev(13);
-            float sigma;
+            // ---- the colour head: rgb = rgb_fc . relu(layer-3 accumulator) + bias (latent_xyzc.py:122-124), fp32, straight from TMEM
+            float cr = head[kHidden + 4 + 3 * kColor + 0], cg = head[kHidden + 4 + 3 * kColor + 1], cb = head[kHidden + 4 + 3 * kColor + 2];
             {
-                uint32_t v[8];
-                tc::tmem_ld8(lane_base + TM_SIGMA, v);
-                tc::tmem_ld_wait(v);
-                sigma = __uint_as_float(v[0]) + __uint_as_float(v[1]);
+                const float* rw = head + kHidden + 4;
+                uint32_t va[16], vb[16];
+                const uint32_t base = lane_base + TM_R1;
+                auto accumulate = [&](const uint32_t (&v)[16], int k) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(rw + 16 * k + 4 * q);
+                        const float4 w1 = *reinterpret_cast<const float4*>(rw + kColor + 16 * k + 4 * q);
+                        const float4 w2 = *reinterpret_cast<const float4*>(rw + 2 * kColor + 16 * k + 4 * q);
+                        const float x0 = fmaxf(__uint_as_float(v[4 * q + 0]), 0.f), x1 = fmaxf(__uint_as_float(v[4 * q + 1]), 0.f);
+                        const float x2 = fmaxf(__uint_as_float(v[4 * q + 2]), 0.f), x3 = fmaxf(__uint_as_float(v[4 * q + 3]), 0.f);
+                        cr = fmaf(x3, w0.w, fmaf(x2, w0.z, fmaf(x1, w0.y, fmaf(x0, w0.x, cr))));
+                        cg = fmaf(x3, w1.w, fmaf(x2, w1.z, fmaf(x1, w1.y, fmaf(x0, w1.x, cg))));
+                        cb = fmaf(x3, w2.w, fmaf(x2, w2.z, fmaf(x1, w2.y, fmaf(x0, w2.x, cb))));
+                    }
+                };
+                tc::tmem_ld16(base, va);
+                tc::tmem_ld_wait(va);
+                for (int k = 0; k < 8; k += 2) {
+                    tc::tmem_ld16(base + 16 * (k + 1), vb);
+                    accumulate(va, k);
+                    tc::tmem_ld_wait(vb);
+                    if (k + 2 < 8) tc::tmem_ld16(base + 16 * (k + 2), va);
+                    accumulate(vb, k + 1);
+                    if (k + 2 < 8) tc::tmem_ld_wait(va);
+                }
             }
-            convert_region(TM_R1, 8, false, true);     // relu(colour hidden), hi only: H_READY[0], H_READY[1]
+            if (smp >= 0) P.raw_ws[smp] = make_float4(cr, cg, cb, sigma);
             tr.ev(23);
-            tc::mbar_wait(&bars[BAR_RGB_FULL], rcnt & 1); ++rcnt; tc::tc_fence_after();
-            tr.ev(14);
-            {
-                uint32_t v[8];
-                tc::tmem_ld8(lane_base + TM_RGB, v);
-                tc::tmem_ld_wait(v);
-                if (smp >= 0)
-                    P.raw_ws[smp] = make_float4(__uint_as_float(v[0]) + __uint_as_float(v[3]), __uint_as_float(v[1]) + __uint_as_float(v[4]),
-                                                __uint_as_float(v[2]) + __uint_as_float(v[5]), sigma);
-            }
-            tc::tc_fence_before();      // (TM_RGB is next written by the next tile's layer 1, issued after this thread's next H_READY)
+            // R1 is next written by the next tile's layer 1, issued after this thread's next H_READY arrival (fenced there)
         }
     }
 
