@@ -268,6 +268,10 @@ int nb_debug_tc_probe(const void* a0, const void* w0_packed, const void* w1_pack
  * d0_out fp32 [256][256]; d1_out fp32 [256][144] (= relu(d0[:, :128]) w1^T, plus a second accumulation of each half's local
  * rows 64..71 into columns 64..79). */
 int nb_debug_tc_probe2(const void* a0, const void* w0_halves, const void* w1_halves, float* d0_out, float* d1_out, void* stream);
+/* Timing probe (csrc/nb_tc_bench.cu): n_mma back-to-back tcgen05.mma of M = 128 (one CTA) or M = 256 (CTA pair, variant bit 1), N
+ * columns, K = 16, A from shared memory or (variant bit 0) TMEM.  out: device i64[2] = cycles until the last issue returned /
+ * until the commit arrived.  tools/mma_rate.py prints the table. */
+int nb_debug_mma_rate(int variant, int n_mma, int N, long long* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,7 @@ NB_NUM_LEVELS = 4
 
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
-           "nb_render_fwd_launches", "nb_render_fwd_workspace_bytes", "nb_debug_tc_probe", "nb_debug_tc_probe2", "nb_render_bwd", "nb_render_save_bytes",
+           "nb_render_fwd_launches", "nb_render_fwd_workspace_bytes", "nb_debug_tc_probe", "nb_debug_tc_probe2", "nb_debug_mma_rate", "nb_render_bwd", "nb_render_save_bytes",
            "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays", "nb_gen_rays_sharded", "nb_sample_pdf"]
 
 
