@@ -67,7 +67,7 @@ extern "C" int nb_debug_mma_rate(int variant, int n_mma, int N, long long* out, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = pair ? 1 : 0;
         e = cudaLaunchKernelEx(&cfg, mmabench::mma_rate_kernel, variant, n_mma, N, out);
     }
     if (e != cudaSuccess) { set_error("nb_debug_mma_rate: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
