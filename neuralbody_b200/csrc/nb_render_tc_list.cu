@@ -68,7 +68,11 @@ constexpr int SEG_BUFS_3PASS = NB_SEG_BUFS;                        // (hi + lo) 
 constexpr int SEG_RING_BYTES = 2 * SEG_BUFS_3PASS * SEG_CHUNKS * SEG_CHUNK_STRIDE;  // 96.75 KB at 3 buffers
 constexpr int MAX_SEG_BUFS = 2 * SEG_BUFS_3PASS;
 constexpr int PE_CHUNKS = 12;
-constexpr int PROD_WARPS = 16, EPI_WARP0 = 16, EPI_WARPS = 4, MMA_WARP = 20, LOAD_WARP = 21;
+// NB_EPI_LOW = 1 (A/B builds): the epilogue warps take the LOWEST warp ids instead of sitting above the producers
+#ifndef NB_EPI_LOW
+#define NB_EPI_LOW 0
+#endif
+constexpr int PROD_WARPS = 16, EPI_WARPS = 4, PROD_WARP0 = NB_EPI_LOW ? 4 : 0, EPI_WARP0 = NB_EPI_LOW ? 0 : 16, MMA_WARP = 20, LOAD_WARP = 21;
 constexpr int NT = (LOAD_WARP + 1) * 32;                          // 704
 constexpr int PTS_PER_GROUP = TP / (PROD_WARPS * 4);
 constexpr int MAXS = 1024;                                         // samples per classification block
@@ -250,16 +254,18 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[BAR_H_READY + i], CLUSTER * EPI_WARPS);
         tc::fence_mbar_init();
     }
-    if (warp < PROD_WARPS) {
-        if (tid < TP) {
+    const int pwarp = warp - PROD_WARP0, ptid = tid - PROD_WARP0 * 32;       // producer-relative ids
+    const bool is_producer = pwarp >= 0 && pwarp < PROD_WARPS;
+    if (is_producer) {
+        if (ptid < TP) {
             unsigned char* o = smem + OFF_ONES;
-            *reinterpret_cast<uint4*>(o + (tid >> 3) * 128 + (tid & 7) * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
-            *reinterpret_cast<uint4*>(o + CHUNK_BYTES + (tid >> 3) * 128 + (tid & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(o + (ptid >> 3) * 128 + (ptid & 7) * 16) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(o + CHUNK_BYTES + (ptid >> 3) * 128 + (ptid & 7) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
-        load_frame_xf(P, xf, tid);
+        load_frame_xf(P, xf, ptid);
         // the two narrow heads, fp32: alpha_fc (latent_xyzc.py:104) and rgb_fc (:124) are applied by the epilogue
         float* head = reinterpret_cast<float*>(smem + OFF_HEAD);
-        for (int i = tid; i < HEAD_FLOATS; i += PROD_WARPS * 32) {
+        for (int i = ptid; i < HEAD_FLOATS; i += PROD_WARPS * 32) {
             const int j = i - (kHidden + 4);
             head[i] = i < kHidden + 4 ? __ldg(P.wf32 + oAlphaW + i) : __ldg(P.wf32 + oRgbW + j);     // [alpha_w | alpha_b] / [rgb_w | rgb_b]
         }
@@ -310,13 +316,13 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     };
 
     // ================================================================== PRODUCERS
-    if (warp < PROD_WARPS) {
+    if (is_producer) {
         const unsigned char* volbase = reinterpret_cast<const unsigned char*>(P.volume);
-        const int grp = warp * 4 + (lane >> 3);
+        const int grp = pwarp * 4 + (lane >> 3);
         const int t = lane & 7;
         uint32_t gseg = 0;                             // segments produced so far (ring position)
         Tracer tr;
-        tr.init((warp == 0 && lane == 0) ? P.trace : nullptr, 0);
+        tr.init((pwarp == 0 && lane == 0) ? P.trace : nullptr, 0);
         const uint32_t seg_base = tc::smem_u32(smem + OFF_SEG);
         // An 8-lane group owns the ADJACENT tile rows 2 grp and 2 grp + 1 (a warp: 8 consecutive rows); lane t owns channels
         // 4t..4t+3 of every 32-channel unit, so one corner of one row is one contiguous 128-byte (fp32) run.  Consecutive list
@@ -455,7 +461,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 tr.ev(20 + seg);
             }
         }
-        if (tid == 0 && P.stats) {
+        if (ptid == 0 && P.stats) {
             atomicAdd(P.stats + 0, (unsigned long long)real_tiles);
             atomicAdd(P.stats + 4, (unsigned long long)real_ksteps);
             if (blockIdx.x == 0) atomicAdd(P.stats + 1, (unsigned long long)sched->cnt[0] + sched->cnt[1] + sched->cnt[2] + sched->cnt[3]);
