@@ -852,6 +852,9 @@ template <int NP, typename VT>
 static cudaError_t launch_list(const RenderParams& p, int grid, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(render_tc_list_kernel<NP, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    // what the 228 KB array does not spend on shared memory is the L1 the producers' gather lives on: ask for the smallest carve-out
+    e = cudaFuncSetAttribute(render_tc_list_kernel<NP, VT>, cudaFuncAttributePreferredSharedMemoryCarveout, (SMEM_BYTES + 1024) * 100 / (228 * 1024) + 1);
+    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(NT);
