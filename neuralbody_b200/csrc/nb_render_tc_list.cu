@@ -40,15 +40,17 @@ using tcr::Tracer;
 
 constexpr int TP = 128;
 // weight ring: NB_NUM_SLOTS slots of NB_SLOT_KB KB.  32 KB slots take the hi AND lo tiles of a 4-K-step group of an N = 256 layer
-// (12 MMAs per hand-off); 16 KB slots take one plane (8 / 4 MMAs per hand-off) and leave room for a 4th layer-0 segment buffer.
+// (12 MMAs per hand-off); 16 KB slots take one plane (8 / 4 MMAs per hand-off).  Measured (profiles/r02_ab_*.txt): in pair
+// mode two 32 KB slots feed the issuer as well as three, and the 32 KB saved buy a 4th layer-0 segment buffer (+2.5 %);
+// 16 KB slots lose 8-13 % to the extra hand-offs.
 #ifndef NB_SLOT_KB
 #define NB_SLOT_KB 32
 #endif
 #ifndef NB_NUM_SLOTS
-#define NB_NUM_SLOTS 3
+#define NB_NUM_SLOTS 2
 #endif
 #ifndef NB_SEG_BUFS
-#define NB_SEG_BUFS 3
+#define NB_SEG_BUFS 4
 #endif
 constexpr int NUM_SLOTS = NB_NUM_SLOTS;
 constexpr int SLOT_BYTES = NB_SLOT_KB * 1024;
@@ -79,7 +81,7 @@ constexpr int MAXS = 1024;                                         // samples pe
 constexpr int CLUSTER = 2;                     // a CTA pair (same TPC) executes every MMA together: tcgen05 cta_group::2, M = 256
 constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry .w = frame sample id | level bits << 28
 #ifndef NB_CORNER_BATCH
-#define NB_CORNER_BATCH 8
+#define NB_CORNER_BATCH 4
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
 constexpr int L3_SPLIT = SPLIT_PLANES ? 7 : 11;                    // layer-3 K-steps per ring slot (2.25 KB per step and CTA)
