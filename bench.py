@@ -70,12 +70,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -85,6 +85,11 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+
+    def mark(self):
+        """Start of the timed region: rows before it (warm-up, same load) are only used if the region is too short to
+        yield 3 samples of its own."""
+        self.first = len(self.rows)
 
     def stop(self):
         if not self.proc:
@@ -97,7 +102,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[self.first:] if len(self.rows) - self.first >= 3 else self.rows
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx = float(r[2])
                 for nme, v in zip(names, r[5:9]):
@@ -370,11 +376,12 @@ def run_c2(args, rank, world, local_rank):
         bit_identical = bit_identity_check(prod, full, vol, sp_input, frame, world)
 
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()       # before the warm-up: nvidia-smi needs ~0.3 s to produce its first row
     launches0 = [0]
 
     def before():
-        if rank == 0:
-            sampler.start()
+        sampler.mark()
         launches0[0] = ren.launches
         ren.stats.zero_()
 
@@ -576,11 +583,12 @@ def run_c4(args, rank, world, local_rank):
     hit_rays = float(hits)
 
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()       # before the warm-up: nvidia-smi needs ~0.3 s to produce its first row
     launches0 = [0]
 
     def before():
-        if rank == 0:
-            sampler.start()
+        sampler.mark()
         launches0[0] = ren.launches
         ren.stats.zero_()
 
@@ -674,11 +682,12 @@ def run_c5(args, rank, world, local_rank):
             nbdist.gather_slabs(slab, out=gathered)
 
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()       # before the warm-up: nvidia-smi needs ~0.3 s to produce its first row
     launches0 = [0]
 
     def before():
-        if rank == 0:
-            sampler.start()
+        sampler.mark()
         launches0[0] = ren.launches
         ren.stats.zero_()
 
@@ -772,10 +781,12 @@ def run_c3(args, rank, world, local_rank):
         return loss
 
     sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()       # before the warm-up: nvidia-smi needs ~0.3 s to produce its first row
     launches0 = [0]
 
     def before():
-        sampler.start()
+        sampler.mark()
         launches0[0] = ren.launches
 
     total_ms, step_ms = time_steps(args, dev, 1, step, before)
