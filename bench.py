@@ -760,6 +760,7 @@ def run_c3(args, rank, world, local_rank):
     ni = args.importance
     cfg.render_importance = ni
     cfg.render_return_weights = True
+    cfg.render_train_precision = args.train_precision
     vols = [v.to(dev).requires_grad_(True) for v in scene["volumes"]]
     net.set_feature_volume(vols)
     host = {k: scene[k].pin_memory() for k in KEYS}
@@ -810,20 +811,25 @@ def run_c3(args, rank, world, local_rank):
     e2e_ms = e0.elapsed_time(e1)
     peaks = load_peaks()
     pts = 1024 * (S + (S + ni if ni else 0))          # coarse pass + fine pass over the merged depths
-    flops = pts * FLOP_PER_SAMPLE_FOLDED * 3            # forward + 2x for the backward (dgrad + wgrad)
+    listed = ren.train_listed_samples()[-(2 if ni else 1):] if args.train_precision == "tc_tf32x3" else []
+    pts_exec = sum(c for c, _ in listed) if listed else pts      # the exact kernels evaluate every sample
+    flops = pts_exec * FLOP_PER_SAMPLE_FOLDED * 3       # forward + 2x for the backward (dgrad + wgrad), executed samples only
     ms = total_ms / args.steps
     tf = flops / (ms * 1e-3) / 1e12
     value = 1024 * args.steps / (total_ms * 1e-3)
     line = {
         "metric": "train_rays_per_s_fwd_bwd", "value": value, "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 (exact kernels: the gradient path)", "data": "synthetic",
+        "dtype": ("tf32x2 (hi+lo TF32 pairs, 3 tcgen05 passes, fp32 accumulate)" if args.train_precision == "tc_tf32x3"
+                  else "f32 (exact FFMA kernels)"), "data": "synthetic",
         "config": {"workload": "BASELINE configs[2]: one N_rand = 1024 training chunk of the synth-313 frame, %d coarse%s samples, "
                                "net.train(), perturb = 1, loss = mse(rgb_map) (+ mse(rgb0)), forward + backward through nb_render_fwd / "
                                "nb_sample_pdf / nb_render_bwd" % (S, (" + %d importance" % ni) if ni else ""),
-                   "points_per_step": pts, "l2": "256 MiB written between timed steps (untimed)"},
+                   "train_precision": args.train_precision, "points_per_step": pts, "points_evaluated_per_step": pts_exec,
+                   "empty_sample_skipping": ("exact, forward and backward (sigma_empty < 0): %s listed" % ["%d of %d" % lc for lc in listed]) if listed else "off",
+                   "l2": "256 MiB written between timed steps (untimed)"},
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["tf_sustained"],
-                     "traffic": None, "flop_model": "points x 532224 folded FLOP x 3 (forward + dgrad + wgrad)",
+                     "traffic": None, "flop_model": "evaluated points x 532224 folded FLOP x 3 (forward + dgrad + wgrad)",
                      "kernel": "whole step (forward with activation record, sample_pdf, backward)", "kernel_ms": ms},
         "cpu_baseline": None,
         "e2e": {"value": 1024 * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
@@ -850,6 +856,7 @@ def main():
     ap.add_argument("--views", type=int, default=144, help="c4: views of the spiral path per step (cfg.num_render_views)")
     ap.add_argument("--poses", type=int, default=8, help="c5: SMPL poses (frames) per step")
     ap.add_argument("--c5-size", type=int, default=1024, help="c5: image side")
+    ap.add_argument("--train-precision", default="tc_tf32x3", choices=["tc_tf32x3", "fp32"], help="c3: precision of the gradient path")
     ap.add_argument("--importance", type=int, default=128, help="c3: importance samples of the fine pass (0 = coarse only)")
     args = ap.parse_args()
     if args.steps is None:

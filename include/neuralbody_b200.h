@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NB_ABI_VERSION 3
+#define NB_ABI_VERSION 4
 
 #define NB_OK               0
 #define NB_ERR_BAD_ARG     (-1)
@@ -39,6 +39,8 @@ extern "C" {
 #define NB_PRECISION_FP32      0   /* exact: fp32 FFMA everywhere (GPU-side oracle, fallback)            */
 #define NB_PRECISION_TC_FP16   1   /* tcgen05 tensor cores: fp16 operands, fp32 accumulate in TMEM       */
 #define NB_PRECISION_TC_FP16X3 2   /* tcgen05, density path as hi+lo fp16 pairs, 3 MMA passes: ~fp32-accurate */
+#define NB_PRECISION_TC_TF32X3 3   /* training: sample list + tcgen05 kind::tf32 GEMM chains, hi+lo TF32 pairs, 3 passes (fp32-grade);
+                                      writes the activation record nb_render_bwd consumes; needs `save` and `raw` */
 
 #define NB_NUM_LEVELS   4          /* SparseConvNet returns 4 dense volumes, latent_xyzc.py:179-204     */
 #define NB_FEAT_DIM     352        /* 32+64+128+128 channels, latent_xyzc.py:20                         */
@@ -225,14 +227,16 @@ int nb_gen_rays_sharded(const nb_camera* cam, int rank, int world, int chunk, in
                         unsigned char* mask_at_box /* device (n_local) */, void* stream);
 
 /* number of kernels nb_render_fwd enqueues per FRAME of a call: 1 for NB_PRECISION_FP32 (the single fused exact kernel),
- * 3 for the tensor-core precisions (classify, decoder, composite; plus one 32-byte memset per call). */
+ * 3 for the tensor-core inference precisions (classify, decoder, composite; plus one 32-byte memset per call), 9 for
+ * NB_PRECISION_TC_TF32X3 (colour-matrix build, classify, gather, 4 GEMMs, rgb head, composite). */
 int nb_render_fwd_launches(int precision);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of the fused render (training, BASELINE config 3).  Replaces PyTorch autograd through
  * raw2outputs (nerf_net_utils.py:6-51), Network.calculate_density_color (latent_xyzc.py:91-126) and
  * F.grid_sample (latent_xyzc.py:62-72) as driven by Trainer.train (lib/train/trainers/trainer.py:46-53).
- * Usage: run nb_render_fwd with NB_PRECISION_FP32, an fp32 volume blob, `raw` and `save` set; then call
+ * Usage: run nb_render_fwd with NB_PRECISION_TC_TF32X3 (tensor cores, exact empty-sample skipping in both passes) or
+ * NB_PRECISION_FP32 (the exact FFMA kernels; fp32 volume blob only), `raw` and `save` set; then call
  * nb_render_bwd with the same nb_render_args and the output gradients.  Gradients are ACCUMULATED into the
  * caller's (zeroed) buffers: `grads` mirrors nb_decoder_weights (same shapes; latent_index unused),
  * d_volumes[l] is the NCDHW fp32 gradient of level l (what autograd hands back to the SparseConvNet). */
@@ -250,8 +254,13 @@ typedef struct nb_render_bwd_args {
     size_t workspace_bytes;
 } nb_render_bwd_args;
 
-size_t nb_render_save_bytes(int batch, int n_rays, int n_samples);
-size_t nb_render_bwd_workspace_bytes(int batch, int n_rays, int n_samples);
+size_t nb_render_save_bytes(int batch, int n_rays, int n_samples);            /* NB_PRECISION_FP32 */
+size_t nb_render_bwd_workspace_bytes(int batch, int n_rays, int n_samples);   /* NB_PRECISION_FP32 */
+/* the same two sizes for the precision (and volume dimensions) of a forward call: NB_PRECISION_FP32 as above;
+ * NB_PRECISION_TC_TF32X3: record = list + 1364 floats per sample of the batch (worst case: every sample listed), backward
+ * scratch = 1268 floats per sample + a channels-last copy of the volume gradients */
+size_t nb_render_save_bytes_for(const nb_render_args* fwd);
+size_t nb_render_bwd_workspace_bytes_for(const nb_render_args* fwd);
 int    nb_render_bwd(const nb_render_bwd_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -272,6 +281,11 @@ int nb_debug_tc_probe2(const void* a0, const void* w0_halves, const void* w1_hal
  * columns, K = 16, A from shared memory or (variant bit 0) TMEM.  out: device i64[2] = cycles until the last issue returned /
  * until the commit arrived.  tools/mma_rate.py prints the table. */
 int nb_debug_mma_rate(int variant, int n_mma, int N, long long* out, void* stream);
+/* The training path's GEMM in isolation (csrc/nb_train.cu): c (M,N) = epilogue(a b^T), fp32 in and out, 3 x TF32 passes.
+ * a: (M,K) if a_k_contiguous else (K,M); b: (N,K) if b_k_contiguous else (K,N); N % 16 == 0, leading dimensions % 4 == 0.
+ * splits > 1 splits the reduction over CTAs and ACCUMULATES into c (zero it first).  bias (N) / mask (M,N) may be NULL. */
+int nb_debug_gemm_tf32x3(const float* a, const float* b, float* c, int M, int N, int K, int a_k_contiguous, int b_k_contiguous,
+                         int splits, const float* bias, int relu, const float* mask, void* stream);
 
 #ifdef __cplusplus
 }

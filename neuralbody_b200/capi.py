@@ -8,13 +8,13 @@ from . import _build
 
 NB_OK = 0
 NB_DTYPE_F32, NB_DTYPE_F16 = 0, 1
-NB_PRECISION_FP32, NB_PRECISION_TC_FP16, NB_PRECISION_TC_FP16X3 = 0, 1, 2
+NB_PRECISION_FP32, NB_PRECISION_TC_FP16, NB_PRECISION_TC_FP16X3, NB_PRECISION_TC_TF32X3 = 0, 1, 2, 3
 NB_NUM_LEVELS = 4
 
 EXPORTS = ["nb_abi_version", "nb_last_error", "nb_has_precision", "nb_packed_volume_bytes", "nb_packed_volume_level_offset",
            "nb_pack_volume", "nb_packed_weights_bytes", "nb_pack_weights", "nb_render_fwd",
            "nb_render_fwd_launches", "nb_render_fwd_workspace_bytes", "nb_debug_tc_probe", "nb_debug_tc_probe2", "nb_debug_mma_rate", "nb_render_bwd", "nb_render_save_bytes",
-           "nb_render_bwd_workspace_bytes", "nb_decode_density", "nb_gen_rays", "nb_gen_rays_sharded", "nb_sample_pdf"]
+           "nb_render_bwd_workspace_bytes", "nb_render_save_bytes_for", "nb_render_bwd_workspace_bytes_for", "nb_debug_gemm_tf32x3", "nb_decode_density", "nb_gen_rays", "nb_gen_rays_sharded", "nb_sample_pdf"]
 
 
 class nb_volume_level(C.Structure):
@@ -110,6 +110,12 @@ def load(path=None):
     lib.nb_render_save_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.nb_render_bwd_workspace_bytes.restype = C.c_size_t
     lib.nb_render_bwd_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.nb_render_save_bytes_for.restype = C.c_size_t
+    lib.nb_render_save_bytes_for.argtypes = [C.POINTER(nb_render_args)]
+    lib.nb_render_bwd_workspace_bytes_for.restype = C.c_size_t
+    lib.nb_render_bwd_workspace_bytes_for.argtypes = [C.POINTER(nb_render_args)]
+    lib.nb_debug_gemm_tf32x3.restype = C.c_int
+    lib.nb_debug_gemm_tf32x3.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.nb_decode_density.restype = C.c_int
     lib.nb_decode_density.argtypes = [C.POINTER(nb_render_args), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.nb_gen_rays.restype = C.c_int
@@ -122,7 +128,7 @@ def load(path=None):
     lib.nb_debug_tc_probe.argtypes = [C.c_void_p] * 5 + [C.c_int, C.c_void_p]
     lib.nb_debug_tc_probe2.restype = C.c_int
     lib.nb_debug_tc_probe2.argtypes = [C.c_void_p] * 6
-    if lib.nb_abi_version() != 3:
+    if lib.nb_abi_version() != 4:
         raise RuntimeError("libneuralbody_b200.so ABI version mismatch")
     if path in (_build.LIB_PATH, os.environ.get("NB_LIB_PATH")):
         _lib = lib

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include "nb_internal.h"
+#include "nb_train.h"
 
 namespace nb {
 
@@ -320,7 +321,7 @@ int nb_abi_version(void) { return NB_ABI_VERSION; }
 const char* nb_last_error(void) { return g_err; }
 int nb_has_precision(int precision) {
     if (precision == NB_PRECISION_FP32) return 1;
-    if (precision == NB_PRECISION_TC_FP16 || precision == NB_PRECISION_TC_FP16X3) return tc_available() ? 1 : 0;
+    if (precision == NB_PRECISION_TC_FP16 || precision == NB_PRECISION_TC_FP16X3 || precision == NB_PRECISION_TC_TF32X3) return tc_available() ? 1 : 0;
     return 0;
 }
 
@@ -418,7 +419,7 @@ int nb_pack_weights(const nb_decoder_weights* w, void* out_blob, size_t out_byte
     return NB_OK;
 }
 
-int nb_render_fwd_launches(int precision) { return precision == NB_PRECISION_FP32 ? 1 : 3; }
+int nb_render_fwd_launches(int precision) { return precision == NB_PRECISION_FP32 ? 1 : precision == NB_PRECISION_TC_TF32X3 ? 9 : 3; }
 
 size_t nb_render_fwd_workspace_bytes(int batch, int n_rays, int n_samples) {
     if (batch <= 0 || n_rays <= 0 || n_samples <= 0) return 0;
@@ -479,7 +480,7 @@ int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out) {
         return NB_ERR_BAD_ARG;
     }
     p.rays_per_group = p.tiles_per_group = p.n_groups = p.groups_per_frame = 0;
-    p.frame = 0; p.list_a = p.list_b = nullptr; p.list_cap = 0; p.list_count = nullptr; p.frame_clock = nullptr; p.raw_ws = nullptr;
+    p.frame = 0; p.train_list = 0; p.list_a = p.list_b = nullptr; p.list_cap = 0; p.list_count = nullptr; p.frame_clock = nullptr; p.raw_ws = nullptr;
 
     return NB_OK;
 }
@@ -533,11 +534,12 @@ int nb_render_fwd(const nb_render_args* a, void* stream) {
     const int stp = nbi_fill_render_params(a, &p);
     if (stp != NB_OK) return stp;
     if (a->save && a->mask_msks) { set_error("nb_render_fwd: mask views are an inference feature (no activation record)"); return NB_ERR_UNSUPPORTED; }
-    if (a->save && a->precision != NB_PRECISION_FP32) {
-        set_error("nb_render_fwd: the activation record for nb_render_bwd is written by the exact kernel only (NB_PRECISION_FP32)");
+    if (a->save && a->precision != NB_PRECISION_FP32 && a->precision != NB_PRECISION_TC_TF32X3) {
+        set_error("nb_render_fwd: the activation record for nb_render_bwd is written by NB_PRECISION_FP32 and NB_PRECISION_TC_TF32X3 only");
         return NB_ERR_UNSUPPORTED;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (a->precision == NB_PRECISION_TC_TF32X3) return launch_train_fwd(p, a->volume_dtype, st);
     if (a->precision == NB_PRECISION_FP32) return launch_render_f32(p, a->volume_dtype, st);
     if (a->precision == NB_PRECISION_TC_FP16 || a->precision == NB_PRECISION_TC_FP16X3) {
         const int passes = a->precision == NB_PRECISION_TC_FP16X3 ? 3 : 1;

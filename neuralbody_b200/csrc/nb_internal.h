@@ -46,6 +46,8 @@ struct RenderParams {
     int groups_per_frame;
     // list pipeline (nb_render_tc_list.cu): one frame per launch
     int frame;                 // frame of this launch
+    int train_list;            // training path (nb_train.cu): ONE list for all classes and frames (list_a upwards, list_count[3]),
+                               // entry ids count samples across the whole batch; raw_ws stays the frame's
     // sample lists: entries (world xyz, frame sample id | level bits << 28), one list per sample CLASS (= finest occupied
     // level, nb_layout.h class_segments).  Two buffers of list_cap entries hold two classes each, growing towards each other:
     // class 3 from the start of A upwards, class 2 from the end of A downwards, class 1 / class 0 likewise in B.

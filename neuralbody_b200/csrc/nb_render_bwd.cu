@@ -13,6 +13,7 @@
 // Training chunks are small (N_rand = 1024 rays), so this path is sized for correctness and simplicity:
 // fp32 FFMA, no tensor cores; the forward hot path is untouched.
 #include "nb_device.cuh"
+#include "nb_train.h"
 
 namespace nb {
 namespace bwd {
@@ -25,6 +26,8 @@ struct BwdParams {
     float* ws;                      // (B*n*S, kGradDim) scratch
     nb_decoder_weights w;           // raw decoder tensors
     float* d_vol[4];                // NCDHW fp32, caller-zeroed, accumulated into
+    float* d_raw_out;               // composite backward writes d(rgb logits, sigma) of sample i at d_raw_out + i * d_raw_stride
+    int d_raw_stride;
 };
 
 constexpr int kBwdMaxSamples = 256;     // coarse + importance samples of a fine pass (64 + 128) fit
@@ -76,7 +79,7 @@ __global__ void composite_bwd_kernel(const BwdParams Q) {
         o.y = w * dC[1] * c1 * (1.f - c1);
         o.z = w * dC[2] * c2 * (1.f - c2);
         o.w = (rw.w > 0.f) ? dalpha * dist * e : 0.f;
-        *reinterpret_cast<float4*>(Q.ws + (ri * S + s) * kGradDim + kGradRaw) = o;
+        *reinterpret_cast<float4*>(Q.d_raw_out + (ri * S + s) * Q.d_raw_stride) = o;
     }
 }
 
@@ -388,6 +391,31 @@ __global__ void unfold_stage3(const Unfold U) {     // d view_fc[:, :256], d lat
 }
 
 }  // namespace bwd
+
+void launch_composite_bwd(const RenderParams& p, const float* raw, const float* d_rgb, const float* d_depth, const float* d_acc,
+                          float* d_raw_out, int d_raw_stride, cudaStream_t stream) {
+    bwd::BwdParams Q{};
+    Q.f = p; Q.raw = raw; Q.d_rgb = d_rgb; Q.d_depth = d_depth; Q.d_acc = d_acc;
+    Q.d_raw_out = d_raw_out; Q.d_raw_stride = d_raw_stride;
+    const size_t nrays = (size_t)p.batch * p.n_rays;
+    bwd::composite_bwd_kernel<<<(unsigned)((nrays + 127) / 128), 128, 0, stream>>>(Q);
+}
+
+int launch_unfold(const nb_decoder_weights& w, const nb_decoder_weights& g, const float* dWcx, const float* dbc, float* T, float* dT,
+                  float* u, float* du, cudaStream_t stream) {
+    bwd::Unfold U;
+    U.w = w; U.g = g; U.dWcx = dWcx; U.dbc = dbc; U.T = T; U.dT = dT; U.u = u; U.du = du;
+    const int B = w.batch;
+    const int n1 = kColor * kHidden + B * kHidden + kColor;
+    bwd::unfold_stage1<<<(n1 + 127) / 128, 128, 0, stream>>>(U);
+    const int n2 = kColor * kHidden + kHidden * kHidden + kHidden + B * kHidden;
+    bwd::unfold_stage2<<<(n2 + 127) / 128, 128, 0, stream>>>(U);
+    const int n3 = kColor * kHidden + kHidden * 384 + kHidden + B * 128;
+    bwd::unfold_stage3<<<(n3 + 127) / 128, 128, 0, stream>>>(U);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("unfold launch failed: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
+    return NB_OK;
+}
 }  // namespace nb
 
 using namespace nb;
@@ -404,12 +432,39 @@ extern "C" size_t nb_render_save_bytes(int batch, int n_rays, int n_samples) {
 
 extern "C" int nbi_fill_render_params(const nb_render_args* a, nb::RenderParams* out);   // nb_capi.cu (internal)
 
+extern "C" size_t nb_render_save_bytes_for(const nb_render_args* f) {
+    if (!f) return 0;
+    if (f->precision == NB_PRECISION_TC_TF32X3) return train_save_bytes(f->batch, f->n_rays, f->n_samples);
+    return nb_render_save_bytes(f->batch, f->n_rays, f->n_samples);
+}
+extern "C" size_t nb_render_bwd_workspace_bytes_for(const nb_render_args* f) {
+    if (!f) return 0;
+    if (f->precision == NB_PRECISION_TC_TF32X3) {
+        nb::RenderParams p;
+        if (nbi_fill_render_params(f, &p) != NB_OK) return 0;
+        return train_bwd_workspace_bytes(p);
+    }
+    return nb_render_bwd_workspace_bytes(f->batch, f->n_rays, f->n_samples);
+}
+
 extern "C" int nb_render_bwd(const nb_render_bwd_args* a, void* stream) {
     if (!a || !a->fwd || !a->save || !a->raw || !a->workspace || !a->weights || !a->grads) {
         set_error("nb_render_bwd: null argument");
         return NB_ERR_BAD_ARG;
     }
     const nb_render_args* f = a->fwd;
+    if (f->precision == NB_PRECISION_TC_TF32X3) {
+        if (f->n_samples > bwd::kBwdMaxSamples) { set_error("nb_render_bwd: n_samples <= %d supported (got %d)", bwd::kBwdMaxSamples, f->n_samples); return NB_ERR_UNSUPPORTED; }
+        if (a->workspace_bytes < nb_render_bwd_workspace_bytes_for(f)) { set_error("nb_render_bwd: workspace too small (see nb_render_bwd_workspace_bytes_for)"); return NB_ERR_BAD_ARG; }
+        nb::RenderParams p;
+        int st = nbi_fill_render_params(f, &p);
+        if (st != NB_OK) return st;
+        trn::TrainBwd t;
+        t.save = a->save; t.raw = a->raw; t.d_rgb = a->d_rgb_map; t.d_depth = a->d_depth_map; t.d_acc = a->d_acc_map;
+        t.weights = a->weights; t.grads = a->grads; t.workspace = (float*)a->workspace;
+        for (int l = 0; l < 4; ++l) t.d_vol[l] = a->d_volumes[l];
+        return launch_train_bwd(p, t, (cudaStream_t)stream);
+    }
     if (f->precision != NB_PRECISION_FP32 || f->volume_dtype != NB_DTYPE_F32) {
         set_error("nb_render_bwd: the training path runs the exact kernel (NB_PRECISION_FP32 + fp32 volume)");
         return NB_ERR_UNSUPPORTED;
@@ -425,6 +480,7 @@ extern "C" int nb_render_bwd(const nb_render_bwd_args* a, void* stream) {
     Q.save = a->save; Q.raw = a->raw;
     Q.d_rgb = a->d_rgb_map; Q.d_depth = a->d_depth_map; Q.d_acc = a->d_acc_map;
     Q.ws = (float*)a->workspace;
+    Q.d_raw_out = Q.ws + kGradRaw; Q.d_raw_stride = kGradDim;
     Q.w = *a->weights;
     for (int l = 0; l < 4; ++l) Q.d_vol[l] = a->d_volumes[l];
     cudaStream_t s = (cudaStream_t)stream;
@@ -472,16 +528,8 @@ extern "C" int nb_render_bwd(const nb_render_bwd_args* a, void* stream) {
     colsum(kGradW, kColor, dbc, (size_t)f->n_rays * f->n_samples);           // per frame
     bwd::view_wgrad_kernel<<<(unsigned)nrays, kColor, 0, s>>>(Q, NB_G(g.view_w));
 
-    bwd::Unfold U;
-    U.w = *a->weights; U.g = g; U.dWcx = dWcx; U.dbc = dbc; U.T = T; U.dT = dT; U.u = u; U.du = du;
-    const int B = f->batch;
-    const int n1 = kColor * kHidden + B * kHidden + kColor;
-    bwd::unfold_stage1<<<(n1 + 127) / 128, 128, 0, s>>>(U);
-    const int n2 = kColor * kHidden + kHidden * kHidden + kHidden + B * kHidden;
-    bwd::unfold_stage2<<<(n2 + 127) / 128, 128, 0, s>>>(U);
-    const int n3 = kColor * kHidden + kHidden * 384 + kHidden + B * 128;
-    bwd::unfold_stage3<<<(n3 + 127) / 128, 128, 0, s>>>(U);
-
+    st = launch_unfold(*a->weights, g, dWcx, dbc, T, dT, u, du, s);
+    if (st != NB_OK) return st;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("nb_render_bwd: %s", cudaGetErrorString(e)); return NB_ERR_CUDA; }
     return NB_OK;

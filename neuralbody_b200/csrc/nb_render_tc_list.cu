@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
     // robustly negative sigma on all-zero features => such a sample has compositing weight exactly 0 and is not evaluated
     const bool can_skip = P.skip_empty && sigma_empty < -1e-3f;
     const uint32_t* occ_base = reinterpret_cast<const uint32_t*>(P.volume);
+    const uint32_t id0 = P.train_list ? (uint32_t)b * (uint32_t)P.n_rays * (uint32_t)S : 0u;   // training lists span the batch
 
     float4 gm[CLS_PER_THREAD];
     int cls[CLS_PER_THREAD];                          // 0..3 = finest occupied level (list class), -1 = not listed
@@ -194,8 +195,8 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
                     }
                 }
             }
-            if (inside && (lm != 0u || !can_skip)) cls[k] = lm ? __ffs((int)lm) - 1 : 3;
-            gm[k].w = __uint_as_float((uint32_t)((r0 + ry) * S + s) | (lm << 28));
+            if (inside && (lm != 0u || !can_skip)) cls[k] = (lm && !P.train_list) ? __ffs((int)lm) - 1 : 3;
+            gm[k].w = __uint_as_float(((uint32_t)((r0 + ry) * S + s) + id0) | (lm << 28));
         }
         const int slot = k * (CLS_THREADS / 32) + warp;
 #pragma unroll
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(CLS_THREADS) classify_compact_kernel(const __g
             const size_t at = (c & 1) ? (size_t)sbase[c] + local : P.list_cap - (size_t)sbase[c] - stotal[c] + local;
             buf[at] = gm[k];
         } else if (live[k]) {
-            P.raw_ws[__float_as_uint(gm[k].w) & ID_MASK] = empty;
+            P.raw_ws[(__float_as_uint(gm[k].w) & ID_MASK) - id0] = empty;
         }
     }
 }
@@ -884,6 +885,18 @@ size_t render_tc_list_workspace_bytes(int batch, int n_rays, int n_samples) {
 
 bool render_tc_list_supported(const RenderParams& p) {
     return p.n_samples <= tcl::MAXS && (size_t)p.n_rays * p.n_samples <= (size_t)tcl::ID_MASK;
+}
+
+// the two frame-level kernels the training path (nb_train.cu) shares with this pipeline
+void launch_classify(RenderParams& p, cudaStream_t stream) {
+    p.rays_per_group = tcl::MAXS / p.n_samples;
+    p.tiles_per_group = 0;
+    p.groups_per_frame = (p.n_rays + p.rays_per_group - 1) / p.rays_per_group;
+    p.n_groups = p.groups_per_frame * p.batch;
+    tcl::classify_compact_kernel<<<p.groups_per_frame, tcl::CLS_THREADS, 0, stream>>>(p);
+}
+void launch_composite(RenderParams& p, cudaStream_t stream) {
+    tcl::composite_kernel<<<(p.n_rays + tcl::COMP_WARPS - 1) / tcl::COMP_WARPS, tcl::COMP_WARPS * 32, 0, stream>>>(p);
 }
 
 int launch_render_tc_list(const RenderParams& p_in, int volume_dtype, int passes, void* workspace, size_t workspace_bytes,

@@ -77,6 +77,16 @@ class Renderer:
             raise ValueError("cfg.render_precision must be one of %s" % sorted(_PRECISIONS))
         return _PRECISIONS[name]
 
+    def _train_precision(self, B, n, S):
+        """Precision of a call autograd records: 'tc_tf32x3' (default: sample list + tcgen05 TF32 GEMM chains, exact empty-sample
+        skipping in forward and backward) or 'fp32' (the exact FFMA kernels)."""
+        name = str(self._opt("render_train_precision", "tc_tf32x3"))
+        if name not in ("tc_tf32x3", "fp32"):
+            raise ValueError("cfg.render_train_precision must be 'tc_tf32x3' or 'fp32'")
+        if name == "tc_tf32x3" and S <= 256 and B * n * S < (1 << 28) and self.lib.nb_has_precision(capi.NB_PRECISION_TC_TF32X3):
+            return capi.NB_PRECISION_TC_TF32X3
+        return capi.NB_PRECISION_FP32
+
     def _volume_dtype(self, precision):
         name = str(self._opt("render_volume_dtype", "auto"))
         if name == "auto":
@@ -216,7 +226,7 @@ class Renderer:
         params = self.net.decoder_tensors()
         needs_grad = torch.is_grad_enabled() and (any(t.requires_grad for t in params) or
                                                   any(v.requires_grad for v in feature_volume))
-        precision = capi.NB_PRECISION_FP32 if needs_grad else self._precision()
+        precision = self._train_precision(B, n, S) if needs_grad else self._precision()
         skip_empty = bool(self._opt("render_skip_empty", True))
         if precision != capi.NB_PRECISION_FP32 and (S > 1024 or n * S >= (1 << 28)):
             # the tensor-core pipeline works on a frame-wide sample list: rays of up to 1024 samples, < 2^28 samples per frame
@@ -288,11 +298,17 @@ class Renderer:
             raise ValueError("`out` maps must be dense, or columns of one (B, n, stride) float32 record")
         return st
 
+    def train_listed_samples(self):
+        """[(listed, total)] of the most recent training-precision forward calls (the coarse and the fine pass of a hierarchical
+        step): how many samples the exact empty-sample skipping left for the GEMM chains.  Synchronises; diagnostics / bench."""
+        return [(int(sv[:4].view(torch.int32)[3].item()), total) for sv, total in self.__dict__.get("_train_records", [])]
+
     def release(self):
         """Drop every pooled / cached device buffer (activation records, backward scratch, workspace, packed blobs).  The pools
         assume ONE stream drives this Renderer: call this only when no launch of it is in flight."""
         self.__dict__.pop("_pool", None)
         self.__dict__.pop("_ws_cache", None)
+        self.__dict__.pop("_train_records", None)
         self._vol_key = self._vol_blob = self._vol_dims = self._vol_keep = None
         self._w_key = self._w_blob = self._w_keep = None
 
@@ -324,14 +340,14 @@ class Renderer:
                 if call["want_weights"]:
                     out['weights'] = torch.empty((B, n, S), dtype=torch.float32, device=dev)
             raw = torch.empty((B, n, S, 4), dtype=torch.float32, device=dev) if call["want_raw"] else None
+            a = capi.nb_render_args()
+            a.batch, a.n_rays, a.n_samples = B, n, S
+            a.precision = precision
             sv = None
             if save:
                 # the activation record (5.2 KB per sample) and the backward scratch are hundreds of MB per training chunk:
                 # they are recycled through a small per-renderer pool instead of going back to the allocator every step
-                sv = self._pool_take("save", self.lib.nb_render_save_bytes(B, n, S) // 4, torch.float32, dev)
-
-            a = capi.nb_render_args()
-            a.batch, a.n_rays, a.n_samples = B, n, S
+                sv = self._pool_take("save", self.lib.nb_render_save_bytes_for(C.byref(a)) // 4, torch.float32, dev)
             a.ray_o, a.ray_d = call["ray_o"].data_ptr(), call["ray_d"].data_ptr()
             a.near, a.far = call["near"].data_ptr(), call["far"].data_ptr()
             a.t_vals = t_vals.data_ptr()
@@ -363,7 +379,7 @@ class Renderer:
                 a.mask_nv, a.mask_H, a.mask_W = int(msks.shape[0]), int(msks.shape[1]), int(msks.shape[2])
             a.stats = call["stats"].data_ptr() if call["stats"] is not None else None
             ws = None
-            if precision != capi.NB_PRECISION_FP32:   # classify -> decoder over the frame's sample list -> composite (3 launches / frame)
+            if precision in (capi.NB_PRECISION_TC_FP16, capi.NB_PRECISION_TC_FP16X3):   # classify -> decoder over the frame's sample list -> composite
                 ws = self._workspace(self.lib.nb_render_fwd_workspace_bytes(B, n, S), dev)
                 a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
             a.trace = call["trace"].data_ptr() if call["trace"] is not None else None   # diagnostics (tools/trace_timeline.py)
@@ -372,6 +388,10 @@ class Renderer:
             self.launches += B * self.lib.nb_render_fwd_launches(precision)
             if save:   # everything nb_render_bwd needs stays alive with the autograd node
                 call["args"], call["save"], call["raw"] = a, sv, raw
+                if precision == capi.NB_PRECISION_TC_TF32X3:     # diagnostics: list lengths of the last records (train_listed_samples)
+                    recs = self.__dict__.setdefault("_train_records", [])
+                    recs.append((sv, B * n * S))
+                    del recs[:-4]
                 call["keep"] = (vol_blob, w_blob, t_vals, out)
         if raw is not None and call["want_raw"] and not save:
             out = dict(out)
@@ -399,7 +419,7 @@ class Renderer:
             g.latent_index, g.num_train_frame, g.batch = w[0].latent_index, w[0].num_train_frame, B
             want_vol = any(needs[:len(vols)])
             gvols = [torch.zeros_like(v, dtype=torch.float32, device=dev) for v in vols] if want_vol else [None] * len(vols)
-            nbytes = self.lib.nb_render_bwd_workspace_bytes(B, n, S)
+            nbytes = self.lib.nb_render_bwd_workspace_bytes_for(C.pointer(call["args"]))
             ws = self._pool_take("bwd_ws", nbytes, torch.uint8, dev)
             ba = capi.nb_render_bwd_args()
             ba.fwd = C.pointer(call["args"])

@@ -37,7 +37,9 @@ def _rel_l2(a, b):
 
 
 @pytest.mark.gpu
-def test_backward_matches_oracle_autograd(case):
+@pytest.mark.parametrize("train_precision", ["tc_tf32x3", "fp32"])
+def test_backward_matches_oracle_autograd(case, train_precision):
+    """Both training precisions: the tcgen05 TF32x3 GEMM chains over the sample list (default) and the exact FFMA kernels."""
     import gpu_utils as Gu
     from neuralbody_b200.lib.config import cfg
     scene, t_rand, G, pg, vg, ret_ref, _ = case
@@ -45,13 +47,14 @@ def test_backward_matches_oracle_autograd(case):
     net, ren = Gu.make_net_and_renderer(scene, dev)
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.raw_noise_std = grad_case.N_SAMPLES, 1.0, True, 0
     cfg.render_precision, cfg.render_volume_dtype, cfg.chunk = "tc_fp16x3", "auto", 0
+    cfg.render_train_precision = train_precision
     net.train()
     vols = [v.to(dev).requires_grad_(True) for v in scene["volumes"]]
     net.set_feature_volume(vols)
     batch = {k: scene[k].to(dev) for k in Gu.BATCH_KEYS}
     sp = ren.prepare_sp_input(batch)
     out = ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], vols, sp, t_rand=t_rand.to(dev))
-    # forward of the training path = exact kernel
+    # forward of the training path: exact kernel, or 3 x TF32 passes (fp32-grade)
     for k in ("rgb_map", "depth_map", "acc_map"):
         assert float((out[k].detach().cpu() - ret_ref[k].detach()).abs().max()) < 1e-4, k
     loss = grad_case.loss_of(out, {k: v.to(dev) for k, v in G.items()})
@@ -64,7 +67,7 @@ def test_backward_matches_oracle_autograd(case):
         report[k] = _rel_l2(sd[k].grad.cpu(), pg[k])
     for l, v in enumerate(vols):
         report["vol%d" % l] = _rel_l2(v.grad.cpu(), vg[l])
-    print(report)
+    print(train_precision, report)
     bad = {k: e for k, e in report.items() if not e <= 1e-3}
     assert not bad, bad
     # rows of the latent table other than latent_index get exactly zero gradient
@@ -112,7 +115,8 @@ def test_hierarchical_oracle_autograd_matches_reference_fingerprints(hier_case):
 
 
 @pytest.mark.gpu
-def test_hierarchical_backward_matches_oracle_autograd(hier_case):
+@pytest.mark.parametrize("train_precision", ["tc_tf32x3", "fp32"])
+def test_hierarchical_backward_matches_oracle_autograd(hier_case, train_precision):
     """loss(rgb_map, depth_map, acc_map, rgb0).backward() through render_rays_hierarchical: two nb_render_bwd calls (the fine
     one over S + N_importance caller-supplied depths) accumulate into the same parameters / volumes."""
     import gpu_utils as Gu
@@ -123,6 +127,7 @@ def test_hierarchical_backward_matches_oracle_autograd(hier_case):
     cfg.N_samples, cfg.perturb, cfg.white_bkgd, cfg.raw_noise_std = grad_case.N_SAMPLES, 1.0, True, 0
     cfg.render_precision, cfg.render_volume_dtype, cfg.chunk = "tc_fp16x3", "auto", 0
     cfg.render_importance = grad_case.N_IMPORTANCE
+    cfg.render_train_precision = train_precision
     net.train()
     try:
         vols = [v.to(dev).requires_grad_(True) for v in scene["volumes"]]
