@@ -790,7 +790,9 @@ def run_c3(args, rank, world, local_rank):
         sampler.mark()
         launches0[0] = ren.launches
 
+    allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     total_ms, step_ms = time_steps(args, dev, 1, step, before)
+    device_allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - allocs0      # cudaMalloc calls inside the timed steps
     clocks = sampler.stop()
     loss_pin = torch.empty((), dtype=torch.float32).pin_memory()
 
@@ -837,6 +839,7 @@ def run_c3(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": ren.launches - launches0[0], "clocks": clocks, "step_ms": step_ms,
         "grad_norm_fc0": float(dict(net.named_parameters())["fc_0.weight"].grad.norm()),
+        "cuda_mallocs_in_timed_steps": device_allocs, "median_step_ms": sorted(step_ms)[len(step_ms) // 2],
     }
     print(json.dumps(line))
 
