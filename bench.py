@@ -769,7 +769,21 @@ def run_c3(args, rank, world, local_rank):
     target_h = torch.rand((1, 1024, 3)).pin_memory()
     target = target_h.to(dev)
 
+    dbg = os.environ.get("NB_C3_DEBUG")
+    if dbg == "nogc":
+        import gc
+        gc.disable()
+    dbg_prev = [None]
+
     def step(b=batch, tgt=target, sp_in=sp):
+        if dbg:      # allocator / gc activity per step (stderr)
+            import gc
+            ms_ = torch.cuda.memory_stats(dev)
+            cur = (ms_.get("num_device_alloc", 0), ms_.get("num_device_free", 0), ms_.get("num_alloc_retries", 0),
+                   ms_.get("reserved_bytes.all.current", 0) >> 20, ms_.get("allocated_bytes.all.current", 0) >> 20, sum(s_["collections"] for s_ in gc.get_stats()))
+            if dbg_prev[0] != cur:
+                print("c3 debug: dev_alloc %d dev_free %d retries %d reserved %d MB allocated %d MB gc %d" % cur, file=sys.stderr)
+            dbg_prev[0] = cur
         for p in net.parameters():
             p.grad = None
         for v in vols:
