@@ -31,7 +31,11 @@ namespace trn {
 
 // ================================================================================================ the GEMM
 constexpr int GT = 256;                      // threads
-constexpr int KCH = 32;                      // reduction elements per stage (4 MMAs of K = 8 per pass)
+#ifndef NB_TRN_KCH
+#define NB_TRN_KCH 16
+#endif
+constexpr int KCH = NB_TRN_KCH;              // reduction elements per stage (KCH / 8 MMAs of K = 8 per pass); 16 -> two CTAs per SM
+constexpr int CTAS_PER_SM = KCH <= 16 ? 2 : 1;
 // K-major no-swizzle operand planes: a core matrix is 8 rows x 16 B.  Row groups sit SBO = 144 B apart (not 128) and the
 // 4-element K chunks LBO = rows/8 * 144 + 16 B apart: both strides are free descriptor fields, and these values make the
 // transposing 4-byte stores of a row-contiguous operand and the 16-byte stores of a K-contiguous one bank-conflict-free.
@@ -41,11 +45,16 @@ constexpr int KCH = 32;                      // reduction elements per stage (4 
 constexpr int SBO = NB_TRN_SBO;
 __host__ __device__ constexpr int lbo_bytes(int rows) { return rows / 8 * SBO + 16; }
 constexpr int A_ROWS = 128, B_ROWS = 256;
-constexpr int A_PLANE = (KCH / 4) * lbo_bytes(A_ROWS);    // 18560
-constexpr int B_PLANE = (KCH / 4) * lbo_bytes(B_ROWS);    // 36992
-constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // hi + lo of both operands: 111104
-constexpr int GEMM_SMEM = 2 * STAGE_BYTES;                // 222208
-static_assert(GEMM_SMEM <= 232448 - 64, "shared memory budget");
+constexpr int A_PLANE = (KCH / 4) * lbo_bytes(A_ROWS);    // 9280 at KCH = 16
+constexpr int B_PLANE = (KCH / 4) * lbo_bytes(B_ROWS);    // 18496
+constexpr int STAGE_BYTES = 2 * A_PLANE + 2 * B_PLANE;    // hi + lo of both operands: 55552
+constexpr int GEMM_SMEM = 2 * STAGE_BYTES;                // 111104: two CTAs per SM (one's epilogue and hand-offs hide behind the other's MMAs)
+static_assert(CTAS_PER_SM * (GEMM_SMEM + 2048) <= 232448, "shared memory budget");
+constexpr int KC_TPR = KCH / 4;                           // K-contiguous operand: threads per row
+constexpr int KC_ROWS = GT / KC_TPR;                      //   rows per pass of the CTA
+constexpr int RC_NKC = KCH / 4;                           // row-contiguous operand: 4-element K chunks per stage (one warp each)
+constexpr int RC_WPK = (GT / 32) / RC_NKC;                //   warps sharing a K chunk (they split the 32-row blocks)
+template <int R> struct TileRegs { static constexpr int N = R * KCH / 1024; };   // float4 per thread and R x KCH tile
 
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {   // D f32, A/B tf32 (format 2), K-major both
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -62,22 +71,22 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
 // A 256-thread CTA moves one R x 32 tile per call, 16 bytes per load.
 template <int R, bool KC>
 __device__ __forceinline__ void load_tile(const float* __restrict__ p, long long ld, int row0, int rows_valid, int k0, int k_end,
-                                          float4 (&v)[R / 32], int tid) {
+                                          float4 (&v)[TileRegs<R>::N], int tid) {
     if (KC) {
-        const int c = tid & 7, r = tid >> 3;
+        const int c = tid % KC_TPR, r = tid / KC_TPR;
         const int gk = k0 + 4 * c;
 #pragma unroll
-        for (int i = 0; i < R / 32; ++i) {
-            const int grow = row0 + r + 32 * i;
+        for (int i = 0; i < TileRegs<R>::N; ++i) {
+            const int grow = row0 + r + KC_ROWS * i;
             v[i] = (grow < rows_valid && gk < k_end) ? __ldg(reinterpret_cast<const float4*>(p + (long long)grow * ld + gk))
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     } else {
         const int w = tid >> 5, lane = tid & 31, m4 = lane & 7, kk = lane >> 3;
-        const int gk = k0 + 4 * w + kk;
+        const int gk = k0 + 4 * (w % RC_NKC) + kk;
 #pragma unroll
-        for (int i = 0; i < R / 32; ++i) {
-            const int grow = row0 + 32 * i + 4 * m4;
+        for (int i = 0; i < TileRegs<R>::N; ++i) {
+            const int grow = row0 + 32 * (w / RC_NKC + RC_WPK * i) + 4 * m4;
             v[i] = (grow < rows_valid && gk < k_end) ? __ldg(reinterpret_cast<const float4*>(p + (long long)gk * ld + grow))
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -89,13 +98,13 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 }
 template <int R, bool KC>
 __device__ __forceinline__ void store_tile(unsigned char* __restrict__ hi_plane, unsigned char* __restrict__ lo_plane,
-                                           const float4 (&v)[R / 32], int tid) {
+                                           const float4 (&v)[TileRegs<R>::N], int tid) {
     constexpr int LBO = lbo_bytes(R);
     if (KC) {
-        const int c = tid & 7, r = tid >> 3;
+        const int c = tid % KC_TPR, r = tid / KC_TPR;
 #pragma unroll
-        for (int i = 0; i < R / 32; ++i) {
-            const int row = r + 32 * i;
+        for (int i = 0; i < TileRegs<R>::N; ++i) {
+            const int row = r + KC_ROWS * i;
             const int off = c * LBO + (row >> 3) * SBO + (row & 7) * 16;
             float4 h, l;
             split_tf32(v[i].x, h.x, l.x); split_tf32(v[i].y, h.y, l.y); split_tf32(v[i].z, h.z, l.z); split_tf32(v[i].w, h.w, l.w);
@@ -105,12 +114,12 @@ __device__ __forceinline__ void store_tile(unsigned char* __restrict__ hi_plane,
     } else {
         const int w = tid >> 5, lane = tid & 31, m4 = lane & 7, kk = lane >> 3;
 #pragma unroll
-        for (int i = 0; i < R / 32; ++i) {
+        for (int i = 0; i < TileRegs<R>::N; ++i) {
             const float x[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int row = 32 * i + 4 * m4 + j;
-                const int off = w * LBO + (row >> 3) * SBO + (row & 7) * 16 + kk * 4;
+                const int row = 32 * (w / RC_NKC + RC_WPK * i) + 4 * m4 + j;
+                const int off = (w % RC_NKC) * LBO + (row >> 3) * SBO + (row & 7) * 16 + kk * 4;
                 float h, l;
                 split_tf32(x[j], h, l);
                 *reinterpret_cast<float*>(hi_plane + off) = h;
@@ -121,7 +130,7 @@ __device__ __forceinline__ void store_tile(unsigned char* __restrict__ hi_plane,
 }
 
 template <bool A_KC, bool B_KC>
-__global__ void __launch_bounds__(GT, 1) gemm_tf32x3_kernel(const __grid_constant__ GemmArgs G) {
+__global__ void __launch_bounds__(GT, CTAS_PER_SM) gemm_tf32x3_kernel(const __grid_constant__ GemmArgs G) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bars[2];
     __shared__ uint32_t tmem_slot;
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(GT, 1) gemm_tf32x3_kernel(const __grid_constan
     const uint32_t idesc = make_idesc_tf32(128, nt);
     constexpr int LBO_A = lbo_bytes(A_ROWS), LBO_B = lbo_bytes(B_ROWS);
 
-    float4 va[A_ROWS / 32], vb[B_ROWS / 32];
+    float4 va[TileRegs<A_ROWS>::N], vb[TileRegs<B_ROWS>::N];
     load_tile<A_ROWS, A_KC>(G.a, G.lda, m0, M, kbeg, kend, va, tid);
     load_tile<B_ROWS, B_KC>(G.b, G.ldb, n0, G.N, kbeg, kend, vb, tid);
     uint32_t phase[2] = {0u, 0u};
@@ -706,7 +715,7 @@ int launch_train_bwd(const RenderParams& p, const TrainBwd& t, cudaStream_t stre
         }
     }
     // 5. weight gradients: dW[out][in] += G^T X, split over the list
-    const int splits = 36;
+    const int splits = 74;      // 2 x 2 tiles x 74 = two CTAs on every SM
     GemmArgs wg{};
     wg.dyn_k = sv.count; wg.atomic = 1; wg.relu_cols = 0;
     wg.a = G0; wg.lda = kHidden; wg.M = kHidden; wg.b = sv.F; wg.ldb = kFeat; wg.N = kFeat; wg.c = G_(g.fc0_w); wg.ldc = kFeat;
@@ -716,7 +725,7 @@ int launch_train_bwd(const RenderParams& p, const TrainBwd& t, cudaStream_t stre
     wg.a = G2; wg.b = sv.H1; wg.c = G_(g.fc2_w);
     if ((st = launch_gemm(wg, false, false, kHidden, splits, stream)) != NB_OK) return st;
     wg.a = G3; wg.lda = kWS; wg.M = kWS; wg.b = sv.H2X; wg.ldb = kH2X; wg.N = kH2X; wg.c = dwcol; wg.ldc = kH2X;
-    if ((st = launch_gemm(wg, false, false, kWS, 2 * splits, stream)) != NB_OK) return st;
+    if ((st = launch_gemm(wg, false, false, kWS, splits, stream)) != NB_OK) return st;
     // 6. bias gradients
     const unsigned int spf = (unsigned int)p.n_rays * p.n_samples;
     const int rows_per = 512, cs_grid = (int)((pmax + rows_per - 1) / rows_per);

@@ -392,7 +392,9 @@ class Renderer:
                     recs = self.__dict__.setdefault("_train_records", [])
                     recs.append((sv, B * n * S))
                     del recs[:-4]
-                call["keep"] = (vol_blob, w_blob, t_vals, out)
+                # NOT the output tensors: they carry grad_fn -> this call's autograd node -> ctx.call, a reference cycle only the
+                # cyclic garbage collector can free (measured: ~7 MB leaked per training step and a 50-130 ms gc pause every few steps)
+                call["keep"] = (vol_blob, w_blob, t_vals)
         if raw is not None and call["want_raw"] and not save:
             out = dict(out)
             out['raw'] = raw
@@ -411,7 +413,13 @@ class Renderer:
                 return None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
             d_rgb, d_depth, d_acc = cf(d_rgb), cf(d_depth), cf(d_acc)
             w = self._weights_struct(params, call["latent_index"], dev)
-            gparams = [torch.zeros_like(t, dtype=torch.float32, device=dev) for t in params]
+            # one zero-filled buffer for the 17 parameter gradients (one fill launch instead of 17), 16-byte aligned views
+            sizes = [(t.numel() + 3) // 4 * 4 for t in params]
+            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            gparams, o = [], 0
+            for t, sz in zip(params, sizes):
+                gparams.append(flat[o:o + t.numel()].view(t.shape))
+                o += sz
             g = capi.nb_decoder_weights()
             names = [f[0] for f in capi.nb_decoder_weights._fields_][:17]
             for name, t in zip(names, gparams):
