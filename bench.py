@@ -795,6 +795,41 @@ def run_c3(args, rank, world, local_rank):
         loss.backward()
         return loss
 
+    if dbg == "cycles":     # which objects of a step only the cyclic collector frees
+        import gc
+        for _ in range(3):
+            step()
+        gc.collect()
+        gc.disable()
+        gc.set_debug(gc.DEBUG_SAVEALL)
+        a0 = torch.cuda.memory_allocated()
+        step()
+        step()
+        a1 = torch.cuda.memory_allocated()
+        found = gc.collect()
+        kinds = {}
+        for o in gc.garbage:
+            kinds[type(o).__name__] = kinds.get(type(o).__name__, 0) + 1
+        print("c3 cycles: allocated %d -> %d, %d garbage objects %s" % (a0, a1, found, sorted(kinds.items(), key=lambda kv: -kv[1])[:12]), file=sys.stderr)
+        shown = 0
+        for o in gc.garbage:
+            if isinstance(o, torch.Tensor) and shown < 16:
+                shown += 1
+                refs = []
+                for r in gc.get_referrers(o):
+                    if r is gc.garbage:
+                        continue
+                    refs.append(type(r).__name__ + (":" + ",".join(str(k) for k, v in r.items() if v is o) if isinstance(r, dict) else ""))
+                print("  tensor", tuple(o.shape), o.dtype, type(o.grad_fn).__name__ if o.grad_fn is not None else None, "<-", refs[:6], file=sys.stderr)
+        for o in gc.garbage:
+            if isinstance(o, dict) and len(o) < 40 and shown < 40:
+                shown += 1
+                print("  dict", [str(k)[:24] for k in o.keys()][:24], file=sys.stderr)
+            elif type(o).__name__ in ("function", "cell", "frame", "method") and shown < 60:
+                shown += 1
+                print("  ", type(o).__name__, getattr(o, "__qualname__", ""), file=sys.stderr)
+        raise SystemExit(0)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()       # before the warm-up: nvidia-smi needs ~0.3 s to produce its first row
