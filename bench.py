@@ -291,7 +291,10 @@ class Product:
 
 def time_steps(args, dev, world, step_fn, before_step=None):
     """W warm-up steps, then K timed steps: barrier + synchronize on both sides, CUDA events, L2 flushed (untimed) before
-    every timed step.  Returns (total_ms, per-step list)."""
+    every timed step.  Returns (total_ms, per-step list).  After the warm-up the interpreter's live objects are moved out of the
+    cyclic collector's reach (gc.freeze): a full collection walks every container object of the process (~1e6 with torch
+    imported, 50-130 ms) and fired every few steps of the autograd configuration (c3), inside the timed region."""
+    import gc
     import torch.distributed as dist
 
     def barrier():
@@ -303,6 +306,8 @@ def time_steps(args, dev, world, step_fn, before_step=None):
     for _ in range(args.warmup):
         step_fn()
     barrier()
+    gc.collect()
+    gc.freeze()
     if before_step:
         before_step()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
