@@ -64,27 +64,40 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md), in-process through NVML (pynvml) from a
+    background thread.  The `nvidia-smi -lms` loop it replaces holds a driver lock for tens of ms per query: invisible to the
+    3-launch steps of c2, but it stalled the ~400 launches of a c3 step every 50 ms (measured: 60-130 ms steps among 6.5 ms ones)."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
-    def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu, self.first = [], None, gpu_index, 0
+    def __init__(self, gpu_index=0, period_s=0.05):
+        self.rows, self.gpu, self.first, self.period = [], gpu_index, 0, period_s
+        self.nv, self.h, self.th, self.stop_flag, self.mx = None, None, None, False, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.th = threading.Thread(target=self._run, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                self.rows.append((sm, mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def mark(self):
         """Start of the timed region: rows before it (warm-up, same load) are only used if the region is too short to
@@ -92,28 +105,19 @@ class ClockSampler:
         self.first = len(self.rows)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self.stop_flag = True
+        self.th.join(timeout=1.0)
         rows = self.rows[self.first:] if len(self.rows) - self.first >= 3 else self.rows
-        for r in rows:
-            try:
-                sm.append(float(r[1])); mx = float(r[2])
-                for nme, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                pass
-        sm.sort()
+        sm = sorted(r[0] for r in rows)
+        reasons = set()
+        for _, mask in rows:
+            for name, attr in self.REASONS:
+                if mask & int(getattr(self.nv, attr)):
+                    reasons.add(name)
         med = sm[len(sm) // 2] if sm else None
-        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": self.mx, "reasons": sorted(reasons), "samples": len(sm), "source": "NVML, in-process, every %d ms" % int(self.period * 1e3)}
 
 
 def host_info():
