@@ -797,11 +797,17 @@ def run_c3(args, rank, world, local_rank):
             p.grad = None
         for v in vols:
             v.grad = None
+        t0 = time.perf_counter()
         out = ren.get_pixel_value(b["ray_o"], b["ray_d"], b["near"], b["far"], vols, sp_in, b)
+        t1 = time.perf_counter()
         loss = ((out["rgb_map"] - tgt) ** 2).mean()
         if "rgb0" in out:
             loss = loss + ((out["rgb0"] - tgt) ** 2).mean()          # img_loss0, if_nerf_clight.py:29-32
         loss.backward()
+        t2 = time.perf_counter()
+        if dbg and t2 - t0 > 0.03:
+            import gc
+            print("c3 slow step (host): forward %.1f ms, backward %.1f ms, gc %s" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, gc.get_count()), file=sys.stderr)
         return loss
 
     if dbg == "cycles":     # which objects of a step only the cyclic collector frees
