@@ -244,7 +244,7 @@ class Renderer:
             "out_sh": [int(v) for v in sp_input['out_sh']], "voxel_size": [float(v) for v in cfg.voxel_size],
             "t_rand": None if t_rand is None else _f32c(t_rand, dev), "white_bkgd": bool(cfg.white_bkgd),
             "z_vals": None if z_vals is None else _f32c(z_vals.detach(), dev),
-            "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "out": out, "trace": trace,
+            "feature_volume": list(feature_volume), "want_raw": want_raw or needs_grad, "user_raw": bool(want_raw), "out": out, "trace": trace,
             "want_weights": (bool(self._opt("render_return_weights", True)) if want_weights is None else bool(want_weights))
                             or needs_grad,
             "skip_empty": skip_empty, "stats": getattr(self, "stats", None),
@@ -339,7 +339,14 @@ class Renderer:
                 }
                 if call["want_weights"]:
                     out['weights'] = torch.empty((B, n, S), dtype=torch.float32, device=dev)
-            raw = torch.empty((B, n, S, 4), dtype=torch.float32, device=dev) if call["want_raw"] else None
+            raw = None
+            if call["want_raw"]:
+                if save and not call.get("user_raw"):
+                    # internal to the autograd node: recycled like the activation record (a fresh 1-3 MB tensor per call comes
+                    # out of the caching allocator's large pool, where it splits the blocks the 100 MB volume gradients reuse)
+                    raw = self._pool_take("raw", B * n * S * 4, torch.float32, dev)[:B * n * S * 4].view(B, n, S, 4)
+                else:
+                    raw = torch.empty((B, n, S, 4), dtype=torch.float32, device=dev)
             a = capi.nb_render_args()
             a.batch, a.n_rays, a.n_samples = B, n, S
             a.precision = precision
@@ -413,13 +420,9 @@ class Renderer:
                 return None if t is None else t.to(device=dev, dtype=torch.float32).contiguous()
             d_rgb, d_depth, d_acc = cf(d_rgb), cf(d_depth), cf(d_acc)
             w = self._weights_struct(params, call["latent_index"], dev)
-            # one zero-filled buffer for the 17 parameter gradients (one fill launch instead of 17), 16-byte aligned views
-            sizes = [(t.numel() + 3) // 4 * 4 for t in params]
-            flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
-            gparams, o = [], 0
-            for t, sz in zip(params, sizes):
-                gparams.append(flat[o:o + t.numel()].view(t.shape))
-                o += sz
+            # 17 small tensors (they stay in the allocator's small pool), zeroed by one multi-tensor launch
+            gparams = [torch.empty_like(t, dtype=torch.float32, device=dev) for t in params]
+            torch._foreach_zero_(gparams)
             g = capi.nb_decoder_weights()
             names = [f[0] for f in capi.nb_decoder_weights._fields_][:17]
             for name, t in zip(names, gparams):
@@ -444,6 +447,9 @@ class Renderer:
             # stream-ordered reuse: the next forward / backward on this stream runs after the kernels just enqueued
             self._pool_give("bwd_ws", ws)
             self._pool_give("save", call.pop("save"))
+            if not call.get("user_raw"):
+                r = call.pop("raw")
+                self._pool_give("raw", r._base if r._base is not None else r)
         grads = list(gvols) + [gp.view_as(t) for gp, t in zip(gparams, params)]
         return [gr if need else None for gr, need in zip(grads, needs)]
 
