@@ -797,14 +797,23 @@ def run_c3(args, rank, world, local_rank):
             p.grad = None
         for v in vols:
             v.grad = None
+        def mem():
+            m_ = torch.cuda.memory_stats(dev)
+            return m_.get("num_device_alloc", 0), m_.get("reserved_bytes.all.current", 0)
         t0 = time.perf_counter()
+        m0 = mem() if dbg else None
         out = ren.get_pixel_value(b["ray_o"], b["ray_d"], b["near"], b["far"], vols, sp_in, b)
         t1 = time.perf_counter()
+        m1 = mem() if dbg else None
         loss = ((out["rgb_map"] - tgt) ** 2).mean()
         if "rgb0" in out:
             loss = loss + ((out["rgb0"] - tgt) ** 2).mean()          # img_loss0, if_nerf_clight.py:29-32
         loss.backward()
         t2 = time.perf_counter()
+        if dbg:
+            m2 = mem()
+            if m2[0] != m0[0]:
+                print("c3 cudaMalloc: forward +%d (%.1f MB), backward +%d (%.1f MB)" % (m1[0] - m0[0], (m1[1] - m0[1]) / 2**20, m2[0] - m1[0], (m2[1] - m1[1]) / 2**20), file=sys.stderr)
         if dbg and t2 - t0 > 0.03:
             import gc
             print("c3 slow step (host): forward %.1f ms, backward %.1f ms, gc %s" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, gc.get_count()), file=sys.stderr)

@@ -158,16 +158,26 @@ __global__ void __launch_bounds__(GT, CTAS_PER_SM) gemm_tf32x3_kernel(const __gr
     const uint32_t idesc = make_idesc_tf32(128, nt);
     constexpr int LBO_A = lbo_bytes(A_ROWS), LBO_B = lbo_bytes(B_ROWS);
 
-    float4 va[TileRegs<A_ROWS>::N], vb[TileRegs<B_ROWS>::N];
-    load_tile<A_ROWS, A_KC>(G.a, G.lda, m0, M, kbeg, kend, va, tid);
-    load_tile<B_ROWS, B_KC>(G.b, G.ldb, n0, G.N, kbeg, kend, vb, tid);
+    // Two register sets: the loads of chunk c + 2 are issued when chunk c has been stored, so they have two MMA batches to
+    // arrive (one set was not enough: ncu showed the CTA stalled on the L2 latency of every chunk, tensor pipe 34 % busy).
+    float4 va0[TileRegs<A_ROWS>::N], vb0[TileRegs<B_ROWS>::N], va1[TileRegs<A_ROWS>::N], vb1[TileRegs<B_ROWS>::N];
+    load_tile<A_ROWS, A_KC>(G.a, G.lda, m0, M, kbeg, kend, va0, tid);
+    load_tile<B_ROWS, B_KC>(G.b, G.ldb, n0, G.N, kbeg, kend, vb0, tid);
+    if (nchunks > 1) {
+        load_tile<A_ROWS, A_KC>(G.a, G.lda, m0, M, kbeg + KCH, kend, va1, tid);
+        load_tile<B_ROWS, B_KC>(G.b, G.ldb, n0, G.N, kbeg + KCH, kend, vb1, tid);
+    }
     uint32_t phase[2] = {0u, 0u};
-    for (int c = 0; c < nchunks; ++c) {
+    auto chunk = [&](float4 (&va)[TileRegs<A_ROWS>::N], float4 (&vb)[TileRegs<B_ROWS>::N], int c) {
         const int s = c & 1;
         unsigned char* st = smem + s * STAGE_BYTES;
         if (c >= 2) { tc::mbar_wait(&bars[s], phase[s]); phase[s] ^= 1u; }       // the MMAs of chunk c - 2 have read this stage
         store_tile<A_ROWS, A_KC>(st, st + A_PLANE, va, tid);
         store_tile<B_ROWS, B_KC>(st + 2 * A_PLANE, st + 2 * A_PLANE + B_PLANE, vb, tid);
+        if (c + 2 < nchunks) {
+            load_tile<A_ROWS, A_KC>(G.a, G.lda, m0, M, kbeg + (c + 2) * KCH, kend, va, tid);
+            load_tile<B_ROWS, B_KC>(G.b, G.ldb, n0, G.N, kbeg + (c + 2) * KCH, kend, vb, tid);
+        }
         tc::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -185,10 +195,10 @@ __global__ void __launch_bounds__(GT, CTAS_PER_SM) gemm_tf32x3_kernel(const __gr
             }
             tc::mma_commit(&bars[s]);
         }
-        if (c + 1 < nchunks) {                           // the next chunk's loads fly while this chunk's MMAs run
-            load_tile<A_ROWS, A_KC>(G.a, G.lda, m0, M, kbeg + (c + 1) * KCH, kend, va, tid);
-            load_tile<B_ROWS, B_KC>(G.b, G.ldb, n0, G.N, kbeg + (c + 1) * KCH, kend, vb, tid);
-        }
+    };
+    for (int c = 0; c < nchunks; c += 2) {
+        chunk(va0, vb0, c);
+        if (c + 1 < nchunks) chunk(va1, vb1, c + 1);
     }
     {
         const int s = (nchunks - 1) & 1;
