@@ -783,6 +783,24 @@ def run_c3(args, rank, world, local_rank):
         import gc
         gc.disable()
     dbg_prev = [None]
+    step_t0 = [None]
+    if dbg == "stack":      # where is the main thread when a step stalls on the host?
+        import traceback
+        main_id = threading.get_ident()
+        dumped = []
+
+        def watch():
+            last = None
+            while True:
+                time.sleep(0.004)
+                t = step_t0[0]
+                if t is not None and t != last and time.perf_counter() - t > 0.02:
+                    last = t
+                    fr = sys._current_frames().get(main_id)
+                    if fr is not None and len(dumped) < 6:
+                        dumped.append("".join(traceback.format_stack(fr)[-7:]))
+                        print("c3 stalled step, main thread at:\n" + dumped[-1], file=sys.stderr)
+        threading.Thread(target=watch, daemon=True).start()
 
     def step(b=batch, tgt=target, sp_in=sp):
         if dbg:      # allocator / gc activity per step (stderr)
@@ -801,6 +819,7 @@ def run_c3(args, rank, world, local_rank):
             m_ = torch.cuda.memory_stats(dev)
             return m_.get("num_device_alloc", 0), m_.get("reserved_bytes.all.current", 0)
         t0 = time.perf_counter()
+        step_t0[0] = t0
         m0 = mem() if dbg else None
         out = ren.get_pixel_value(b["ray_o"], b["ray_d"], b["near"], b["far"], vols, sp_in, b)
         t1 = time.perf_counter()
