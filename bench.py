@@ -786,6 +786,19 @@ def run_c3(args, rank, world, local_rank):
         gc.disable()
     dbg_prev = [None]
     step_t0 = [None]
+    if dbg == "gc":         # duration of every collection of the cyclic collector
+        import gc
+        gc_t = [0.0]
+
+        def on_gc(phase, info):
+            if phase == "start":
+                gc_t[0] = time.perf_counter()
+            else:
+                dt = (time.perf_counter() - gc_t[0]) * 1e3
+                if dt > 2.0:
+                    print("c3 gc: generation %d took %.1f ms, collected %d, uncollectable %d, tracked objects now %d" % (
+                        info["generation"], dt, info["collected"], info["uncollectable"], len(gc.get_objects())), file=sys.stderr)
+        gc.callbacks.append(on_gc)
     if dbg == "stack":      # where is the main thread when a step stalls on the host?
         import traceback
         main_id = threading.get_ident()
