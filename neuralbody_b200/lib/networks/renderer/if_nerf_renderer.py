@@ -202,17 +202,11 @@ class Renderer:
     def _draw_t_rand(self, B, n, S, device):
         """The jitter draw of if_clight_renderer.py:22 (`torch.rand(z_vals.shape).to(upper)`, CPU
         generator), issued per 2048-ray chunk like upstream so the RNG stream is identical."""
-        import os, sys, time
-        t0 = time.perf_counter()
         parts = [torch.rand((B, min(2048, n - i), S)) for i in range(0, n, 2048)]
-        t1 = time.perf_counter()
-        host = torch.cat(parts, dim=1)
-        t2 = time.perf_counter()
-        out = host.to(device).contiguous()
-        t3 = time.perf_counter()
-        if os.environ.get("NB_C3_DEBUG") and t3 - t0 > 0.01:
-            print("t_rand slow: rand %.1f ms, cat %.1f ms, to(device) %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3), file=sys.stderr)
-        return out
+        # (a training chunk is ONE part: no CPU torch.cat, whose OpenMP region is a thread hand-off per step -- on a busy
+        # host such wake-ups were measured at 30-60 ms, ten times the GPU time of the step)
+        host = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
+        return host.to(device).contiguous()
 
     # ------------------------------------------------------------------ fused launch
     def render_rays(self, ray_o, ray_d, near, far, feature_volume, sp_input, t_rand=None, want_raw=False,
