@@ -768,6 +768,9 @@ def run_c3(args, rank, world, local_rank):
         scene[k] = scene[k][:, idx].contiguous()
     prod = Product(args, local_rank, scene, training=True)
     dev, ren, net, cfg = prod.dev, prod.ren, prod.net, prod.cfg
+    # the step's few CPU-side tensor ops (jitter / importance draws, as upstream) stay on this thread, as under torchrun
+    # (OMP_NUM_THREADS=1): an OpenMP hand-off per step costs a scheduler quantum when the host's cores are busy
+    torch.set_num_threads(1)
     ni = args.importance
     cfg.render_importance = ni
     cfg.render_return_weights = True
