@@ -13,7 +13,7 @@ per-GPU work is fixed (262 144 rays per step) => "scaling": "weak".
            all-gathers and the image assembly at N>1) are in the timed region.
 `e2e`    : the same metric through the public API make_renderer(cfg, net).render(batch) with the batch in PINNED HOST
            memory: H2D of rays/near/far/pose per step, prepare_sp_input, weight pack, render, D2H of rgb_map + depth_map
-           (at N>1: of the GATHERED frame, on rank 0) inside the timed region.
+           (at N>1: of the GATHERED frame, on the view's owner rank v % N, each GPU using its own PCIe link) inside the timed region.
 `--impl reference`: the reference's own CPU implementation of the path (the oracle port of /root/reference's
            if_clight_renderer + latent_xyzc + raw2outputs, validated bit-exact against the unmodified reference in the
            build container), all host threads, each step a bounded sample (--ref-rays rays) of the same workload.
@@ -402,11 +402,11 @@ def run_c2(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- e2e through the public API with host buffers: per view H2D of this rank's rays (+ the frame's pose tensors) from
-    # pinned memory, Renderer.render, the gather, and the D2H of the GATHERED frame's rgb + depth on rank 0
+    # pinned memory, Renderer.render, the gather, and the D2H of the GATHERED frame on the view's owner (rank v % N)
     host_local = {k: v.contiguous().pin_memory() for k, v in plan.shard(host, rank).items() if torch.is_tensor(v)}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host_local.values()) * n_views
-    e2e_g = nbdist.FrameGatherer(H * W, world, rank, dev, host=True)
-    d2h_bytes = H * W * nbdist.SLAB_WIDTH * 4 * n_views      # the whole 24 B/ray frame record lands on the host (rank 0)
+    e2e_g = nbdist.FrameGatherer(H * W, world, rank, dev, host=True, host_rank="rotate")
+    d2h_bytes = H * W * nbdist.SLAB_WIDTH * 4 * n_views      # every view's whole 24 B/ray frame record lands on a host (its owner's)
 
     def e2e_step():
         for _ in range(n_views):
@@ -481,7 +481,7 @@ def run_c2(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps,
                 "path": "Renderer.render(batch), batch in pinned host memory" if world == 1 else
-                        "per view: H2D of the rank's rays, prepare_sp_input, render into the slab, all-gather, D2H of the gathered frame on rank 0"},
+                        "per view: H2D of the rank's rays, prepare_sp_input, render into the slab, all-gather, D2H of the gathered frame on its owner (rank v % N: one frame per rank and step)"},
         "multi_gpu_bit_identical": bit_identical,
         "gpu_launches": launches,
         "clocks": clocks,
@@ -608,7 +608,7 @@ def run_c4(args, rank, world, local_rank):
     stats = [int(v) for v in ren.stats.tolist()]
     clocks = sampler.stop() if rank == 0 else None
 
-    e2e_g = nbdist.FrameGatherer(H * W, world, rank, dev, host=True)
+    e2e_g = nbdist.FrameGatherer(H * W, world, rank, dev, host=True, host_rank="rotate")
 
     def e2e_step():
         for RT in path:
@@ -651,7 +651,7 @@ def run_c4(args, rank, world, local_rank):
                 "h2d_bytes_per_step": n_views * 208, "d2h_bytes_per_step": n_views * H * W * nbdist.SLAB_WIDTH * 4,
                 "ms_per_step": e2e_ms / args.steps,
                 "path": "per view: camera (208 B of kernel arguments) -> rays on the device -> render -> gather -> D2H of the "
-                        "24 B/pixel frame record on rank 0"},
+                        "24 B/pixel frame record on the view's owner (rank v % N)"},
         "multi_gpu_bit_identical": bit_identical,
         "gpu_launches": launches, "clocks": clocks, "step_ms": step_ms,
     }

@@ -33,10 +33,18 @@ struct BwdParams {
 constexpr int kBwdMaxSamples = 256;     // coarse + importance samples of a fine pass (64 + 128) fit
 
 // ------------------------------------------------------------------------------------------ 1. composite
-__global__ void composite_bwd_kernel(const BwdParams Q) {
+// One WARP per ray.  The per-sample quantities (z, dist, exp, sigmoids: the expensive part) are computed by all lanes into
+// shared memory; the two recurrences -- transmittance forwards, U_i = sum_{j>i} g_j alpha_j prod_{i<k<j} f_k backwards (no
+// division => safe when 1 - alpha underflows) -- are run by lane 0 in the reference's order; the outputs are written by all
+// lanes.  (The earlier thread-per-ray version kept 1024 threads busy on a 148-SM device: 0.16 ms per 192-sample pass.)
+constexpr int CB_WARPS = 4;
+__global__ void __launch_bounds__(CB_WARPS * 32) composite_bwd_kernel(const BwdParams Q) {
+    __shared__ float s_alpha[CB_WARPS][kBwdMaxSamples], s_f[CB_WARPS][kBwdMaxSamples], s_g[CB_WARPS][kBwdMaxSamples],
+        s_T[CB_WARPS][kBwdMaxSamples], s_U[CB_WARPS][kBwdMaxSamples], s_z[CB_WARPS][kBwdMaxSamples + 1];
     const RenderParams& P = Q.f;
     const int S = P.n_samples;
-    const size_t ri = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t ri = (size_t)blockIdx.x * CB_WARPS + warp;
     if (ri >= (size_t)P.batch * P.n_rays) return;
     const float near = P.near[ri], far = P.far[ri];
     const float dx = P.ray_d[ri * 3], dy = P.ray_d[ri * 3 + 1], dz = P.ray_d[ri * 3 + 2];
@@ -49,31 +57,35 @@ __global__ void composite_bwd_kernel(const BwdParams Q) {
     const float dD = Q.d_depth ? Q.d_depth[ri] : 0.f;
     float dA = Q.d_acc ? Q.d_acc[ri] : 0.f;
     if (P.white_bkgd) dA -= dC[0] + dC[1] + dC[2];            // rgb_map += 1 - acc_map
-    float Tbuf[kBwdMaxSamples];                                // exclusive transmittance (S <= kBwdMaxSamples checked by the host)
-    float T = 1.f;
-    for (int s = 0; s < S; ++s) {
-        Tbuf[s] = T;
-        const float z = z_sample(near, far, P.t_vals, s, S, tr, zu);
-        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr, zu), z) : 1e10f) * nrm;
-        const float alpha = 1.f - expf(-fmaxf(raw[s].w, 0.f) * dist);
-        T *= (1.f - alpha + 1e-10f);
-    }
-    // U_i = sum_{j>i} g_j alpha_j prod_{i<k<j} f_k  (no division => safe when 1 - alpha underflows)
-    float U = 0.f;
-    for (int s = S - 1; s >= 0; --s) {
+    for (int s = lane; s < S; s += 32) s_z[warp][s] = z_sample(near, far, P.t_vals, s, S, tr, zu);
+    __syncwarp();
+    for (int s = lane; s < S; s += 32) {
         const float4 rw = raw[s];
-        const float z = z_sample(near, far, P.t_vals, s, S, tr, zu);
-        const float dist = ((s + 1 < S) ? __fsub_rn(z_sample(near, far, P.t_vals, s + 1, S, tr, zu), z) : 1e10f) * nrm;
-        const float sg = fmaxf(rw.w, 0.f);
-        const float e = expf(-sg * dist);
-        const float alpha = 1.f - e;
-        const float f = 1.f - alpha + 1e-10f;
+        const float z = s_z[warp][s];
+        const float dist = ((s + 1 < S) ? __fsub_rn(s_z[warp][s + 1], z) : 1e10f) * nrm;
+        const float alpha = 1.f - expf(-fmaxf(rw.w, 0.f) * dist);
         const float c0 = 1.f / (1.f + expf(-rw.x)), c1 = 1.f / (1.f + expf(-rw.y)), c2 = 1.f / (1.f + expf(-rw.z));
-        const float g = dC[0] * c0 + dC[1] * c1 + dC[2] * c2 + dD * z + dA;
-        const float Ti = Tbuf[s];
-        const float w = alpha * Ti;
-        const float dalpha = g * Ti - Ti * U;
-        U = g * alpha + f * U;
+        s_alpha[warp][s] = alpha;
+        s_f[warp][s] = 1.f - alpha + 1e-10f;
+        s_g[warp][s] = dC[0] * c0 + dC[1] * c1 + dC[2] * c2 + dD * z + dA;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        float T = 1.f;
+        for (int s = 0; s < S; ++s) { s_T[warp][s] = T; T *= s_f[warp][s]; }       // exclusive transmittance
+        float U = 0.f;
+        for (int s = S - 1; s >= 0; --s) { s_U[warp][s] = U; U = s_g[warp][s] * s_alpha[warp][s] + s_f[warp][s] * U; }
+    }
+    __syncwarp();
+    for (int s = lane; s < S; s += 32) {
+        const float4 rw = raw[s];
+        const float z = s_z[warp][s];
+        const float dist = ((s + 1 < S) ? __fsub_rn(s_z[warp][s + 1], z) : 1e10f) * nrm;
+        const float e = expf(-fmaxf(rw.w, 0.f) * dist);
+        const float c0 = 1.f / (1.f + expf(-rw.x)), c1 = 1.f / (1.f + expf(-rw.y)), c2 = 1.f / (1.f + expf(-rw.z));
+        const float Ti = s_T[warp][s];
+        const float w = s_alpha[warp][s] * Ti;
+        const float dalpha = s_g[warp][s] * Ti - Ti * s_U[warp][s];
         float4 o;
         o.x = w * dC[0] * c0 * (1.f - c0);
         o.y = w * dC[1] * c1 * (1.f - c1);
@@ -398,7 +410,7 @@ void launch_composite_bwd(const RenderParams& p, const float* raw, const float* 
     Q.f = p; Q.raw = raw; Q.d_rgb = d_rgb; Q.d_depth = d_depth; Q.d_acc = d_acc;
     Q.d_raw_out = d_raw_out; Q.d_raw_stride = d_raw_stride;
     const size_t nrays = (size_t)p.batch * p.n_rays;
-    bwd::composite_bwd_kernel<<<(unsigned)((nrays + 127) / 128), 128, 0, stream>>>(Q);
+    bwd::composite_bwd_kernel<<<(unsigned)((nrays + bwd::CB_WARPS - 1) / bwd::CB_WARPS), bwd::CB_WARPS * 32, 0, stream>>>(Q);
 }
 
 int launch_unfold(const nb_decoder_weights& w, const nb_decoder_weights& g, const float* dWcx, const float* dbc, float* T, float* dT,
@@ -488,7 +500,7 @@ extern "C" int nb_render_bwd(const nb_render_bwd_args* a, void* stream) {
     if (npts == 0) return NB_OK;
     const nb_decoder_weights& g = *a->grads;
 
-    bwd::composite_bwd_kernel<<<(unsigned)((nrays + 127) / 128), 128, 0, s>>>(Q);
+    bwd::composite_bwd_kernel<<<(unsigned)((nrays + bwd::CB_WARPS - 1) / bwd::CB_WARPS), bwd::CB_WARPS * 32, 0, s>>>(Q);
 
     const size_t smem = ((size_t)bwd::TP * bwd::LDX + (size_t)bwd::TP * bwd::LDY + (size_t)bwd::KC * kFeat) * 4;
     cudaFuncSetAttribute(bwd::decoder_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

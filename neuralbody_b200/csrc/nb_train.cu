@@ -43,7 +43,10 @@ constexpr int CTAS_PER_SM = KCH <= 16 ? 2 : 1;
 #define NB_TRN_SBO 144
 #endif
 constexpr int SBO = NB_TRN_SBO;
-__host__ __device__ constexpr int lbo_bytes(int rows) { return rows / 8 * SBO + 16; }
+#ifndef NB_TRN_LBO_PAD
+#define NB_TRN_LBO_PAD 16
+#endif
+__host__ __device__ constexpr int lbo_bytes(int rows) { return rows / 8 * SBO + NB_TRN_LBO_PAD; }
 constexpr int A_ROWS = 128, B_ROWS = 256;
 constexpr int A_PLANE = (KCH / 4) * lbo_bytes(A_ROWS);    // 9280 at KCH = 16
 constexpr int B_PLANE = (KCH / 4) * lbo_bytes(B_ROWS);    // 18496

@@ -144,7 +144,9 @@ class FrameGatherer:
         g.drain()                                # frames of the last views are complete after this
 
     `finish` returns the (B, n_rays, 6) device frame of THIS view (valid once the side stream has run; `drain` or
-    `frame_ready(i).synchronize()`); with `host=True` the owning rank also copies it into a pinned host buffer."""
+    `frame_ready(i).synchronize()`); with `host=True` the view's owner also copies it into a pinned host buffer.  The owner is
+    rank `host_rank`, or with `host_rank="rotate"` rank v % world for the v-th view: every GPU then ships 1/world of the frames
+    over its own PCIe link instead of rank 0 shipping all of them (8 x 6.3 MB per step at 8 GPUs: 2 ms of a 9 ms step)."""
 
     def __init__(self, n_rays, world, rank, device, B=1, chunk=256, group=None, host=False, host_rank=0, depth=2):
         self.plan = ShardPlan.get(n_rays, world, chunk, device)
@@ -157,7 +159,8 @@ class FrameGatherer:
         self.gathered = [torch.empty((world, B, per, SLAB_WIDTH), dtype=torch.float32, device=self.device) for _ in range(depth)]
         self.frames = [None] * depth
         self.host = None
-        if host and rank == host_rank:
+        self.host_rank = host_rank
+        if host and (host_rank == "rotate" or rank == host_rank):
             self.host = [torch.empty((B, n_rays, SLAB_WIDTH), dtype=torch.float32, pin_memory=self.cuda) for _ in range(depth)]
         self.done = [torch.cuda.Event() if self.cuda else None for _ in range(depth)]
         self.v = 0
@@ -191,7 +194,8 @@ class FrameGatherer:
             frame = self.plan.assemble(gather_slabs(slab, self.group, out=self.gathered[i]))
         else:
             frame = self.plan.assemble(slab[None])
-        if self.host is not None:
+        owner = self.v % self.world if self.host_rank == "rotate" else self.host_rank
+        if self.host is not None and self.rank == owner:
             self.host[i].copy_(frame, non_blocking=True)
         return frame
 

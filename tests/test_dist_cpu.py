@@ -40,7 +40,7 @@ def _worker(rank, world, port, n_rays, out_dir):
         # the streaming form: double-buffered slabs the render writes into, one gather + un-permute per view
         plan = nbdist.ShardPlan.get(n_rays, world, 8, "cpu")
         local = plan.shard(batch, rank)
-        g = nbdist.FrameGatherer(n_rays, world, rank, "cpu", chunk=8)
+        g = nbdist.FrameGatherer(n_rays, world, rank, "cpu", chunk=8, host=True, host_rank="rotate")
         frames = []
         for view in range(3):
             out = g.begin()
@@ -50,6 +50,8 @@ def _worker(rank, world, port, n_rays, out_dir):
             frames.append(g.finish().clone())
         g.drain()
         torch.save(frames, os.path.join(out_dir, "frames%d.pt" % rank))
+        # rotating owner: view v lands in the host buffer of rank v % world (views 0 and 2 on rank 0, view 1 on rank 1)
+        torch.save(g.host[rank].clone(), os.path.join(out_dir, "host%d.pt" % rank))
         if rank == 0:
             torch.save(render_fn(batch), os.path.join(out_dir, "single.pt"))
     finally:
@@ -71,6 +73,9 @@ def test_ray_sharded_render_equals_single_process(tmp_path, n_rays):
             views = nbdist.slab_views(frame)
             for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
                 assert torch.equal(torch.nan_to_num(views[k]), torch.nan_to_num(single[k])), (r, k)
+        hviews = nbdist.slab_views(torch.load(os.path.join(tmp_path, "host%d.pt" % r)))
+        for k in ("rgb_map", "disp_map", "acc_map", "depth_map"):
+            assert torch.equal(torch.nan_to_num(hviews[k]), torch.nan_to_num(single[k])), ("host", r, k)
 
 
 def test_interleaved_shards_cover_all_rays():
