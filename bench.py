@@ -404,18 +404,23 @@ def run_c2(args, rank, world, local_rank):
     # ---- e2e through the public API with host buffers: per view H2D of this rank's rays (+ the frame's pose tensors) from
     # pinned memory, Renderer.render, the gather, and the D2H of the GATHERED frame on the view's owner (rank v % N)
     host_local = {k: v.contiguous().pin_memory() for k, v in plan.shard(host, rank).items() if torch.is_tensor(v)}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host_local.values()) * n_views
+    RAY_KEYS = ("ray_o", "ray_d", "near", "far")
+    nbytes = lambda keys: sum(host_local[k].numel() * host_local[k].element_size() for k in keys)      # noqa: E731
+    # the N views of a step show ONE frame: its pose tensors cross once per step, each view's rays once per view
+    h2d_bytes = nbytes([k for k in host_local if k not in RAY_KEYS]) + nbytes(RAY_KEYS) * n_views
     e2e_g = nbdist.FrameGatherer(H * W, world, rank, dev, host=True, host_rank="rotate")
     d2h_bytes = H * W * nbdist.SLAB_WIDTH * 4 * n_views      # every view's whole 24 B/ray frame record lands on a host (its owner's)
 
     def e2e_step():
+        frame = {k: v.to(dev, non_blocking=True) for k, v in host_local.items() if k not in RAY_KEYS}
+        sp = ren.prepare_sp_input(frame)                 # once per frame (its .tolist() synchronises, as upstream)
+        vol_e = net.encode_sparse_voxels(sp)
         for _ in range(n_views):
-            batch = {k: v.to(dev, non_blocking=True) for k, v in host_local.items()}
+            rays = {k: host_local[k].to(dev, non_blocking=True) for k in RAY_KEYS}
             out = e2e_g.begin()
-            sp = ren.prepare_sp_input(batch)
-            ren.render_rays(batch["ray_o"], batch["ray_d"], batch["near"], batch["far"], net.encode_sparse_voxels(sp), sp, out=out)
+            ren.render_rays(rays["ray_o"], rays["ray_d"], rays["near"], rays["far"], vol_e, sp, out=out)
             e2e_g.finish()
-        e2e_g.drain()                      # the frames of this step are on the host
+        e2e_g.drain()                      # the frames of this step are on their owners' hosts
 
     import torch.distributed as dist
     if world == 1:
@@ -481,7 +486,7 @@ def run_c2(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                 "ms_per_step": e2e_ms / args.steps,
                 "path": "Renderer.render(batch), batch in pinned host memory" if world == 1 else
-                        "per view: H2D of the rank's rays, prepare_sp_input, render into the slab, all-gather, D2H of the gathered frame on its owner (rank v % N: one frame per rank and step)"},
+                        "per step: H2D of the frame's pose tensors + prepare_sp_input; per view: H2D of the rank's rays, render into the slab, all-gather, D2H of the gathered frame on its owner (rank v % N: one frame per rank and step)"},
         "multi_gpu_bit_identical": bit_identical,
         "gpu_launches": launches,
         "clocks": clocks,
