@@ -31,6 +31,7 @@
 // Results do not depend on the (non-deterministic) order of the blocks in the list: a tile row is evaluated
 // independently of its neighbours.  The list and the raw (rgb logits, sigma) records cross HBM once each way.
 #include "nb_tc_common.cuh"
+#include <type_traits>
 
 namespace nb {
 namespace tcl {
@@ -39,13 +40,9 @@ using tcr::Quad;
 using tcr::Tracer;
 
 constexpr int TP = 128;
-// weight ring: NB_NUM_SLOTS slots of NB_SLOT_KB KB.  32 KB slots take the hi AND lo tiles of a 4-K-step group of an N = 256 layer
-// (12 MMAs per hand-off); 16 KB slots take one plane (8 / 4 MMAs per hand-off).  Measured (profiles/r02_ab_*.txt): in pair
-// mode two 32 KB slots feed the issuer as well as three, and the 32 KB saved buy a 4th layer-0 segment buffer (+2.5 %);
-// 16 KB slots lose 8-13 % to the extra hand-offs.
-#ifndef NB_SLOT_KB
-#define NB_SLOT_KB 32
-#endif
+// weight ring: NB_NUM_SLOTS slots of 32 KB: a slot takes the hi AND lo tiles of a 4-K-step group of an N = 256 layer (12 MMAs
+// per hand-off).  Measured (profiles/r02_ab_decoder_variants.txt): in pair mode two slots feed the issuer as well as three, and
+// the 32 KB saved buy a 4th layer-0 segment buffer (+2.5 %); 16 KB slots (one plane per hand-off) lost 8-13 %.
 #ifndef NB_NUM_SLOTS
 #define NB_NUM_SLOTS 2
 #endif
@@ -53,12 +50,11 @@ constexpr int TP = 128;
 #define NB_SEG_BUFS 4
 #endif
 constexpr int NUM_SLOTS = NB_NUM_SLOTS;
-constexpr int SLOT_BYTES = NB_SLOT_KB * 1024;
+constexpr int SLOT_BYTES = 32 * 1024;
 #ifndef NB_PROD_WAIT_NS
 #define NB_PROD_WAIT_NS 200
 #endif
 constexpr unsigned PROD_WAIT_NS = NB_PROD_WAIT_NS;                 // sleep between the producers' probes for a free segment buffer
-constexpr bool SPLIT_PLANES = SLOT_BYTES < 32768;                  // hi and lo tiles of a group travel in separate slots
 constexpr int CHUNK_BYTES = 2048;
 constexpr int SEG_CHUNKS = 8;
 constexpr int NUM_SEGS = 6;
@@ -84,7 +80,7 @@ constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry
 #define NB_CORNER_BATCH 4
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
-constexpr int L3_SPLIT = SPLIT_PLANES ? 7 : 11;                    // layer-3 K-steps per ring slot (2.25 KB per step and CTA)
+constexpr int L3_SPLIT = 11;                                       // layer-3 K-steps per ring slot (2 KB per step and CTA)
 constexpr int HEAD_FLOATS = kHidden + 4 + 3 * kColor + 4;           // alpha_fc (256 + bias) and rgb_fc (3 x 128 + bias), fp32, resident
 constexpr int HALF_TILE_BYTES = kHalfTile256 * 2;                  // one K-step of an N = 256 layer, this CTA's 128 rows (4 KB)
 constexpr int L3_TILE_BYTES = kHalfTile3 * 2;                      // one K-step of layer 3, this CTA's 64 rows (2 KB)
@@ -117,8 +113,8 @@ constexpr uint32_t TM_R0 = 0, TM_R1 = 256;     // (layer 3 accumulates its 128 c
 // weight-ring pushes of one tile (the loader issues them, the peer's relay forwards their completions): layer 0 of a class with
 // `l0_ksteps` K-steps, layers 1 / 2, layer 3
 __host__ __device__ constexpr int pushes_per_tile(int l0_ksteps, int passes) {
-    const int planes = (SPLIT_PLANES && passes == 3) ? 2 : 1;
-    return ((l0_ksteps + 3) / 4) * planes + 1 + 2 * ((kKsL12 / 4) * planes + 1) + (kStepsL3 + L3_SPLIT - 1) / L3_SPLIT;
+    (void)passes;                                  // the hi and lo tiles of a group share a slot
+    return (l0_ksteps + 3) / 4 + 1 + 2 * (kKsL12 / 4 + 1) + (kStepsL3 + L3_SPLIT - 1) / L3_SPLIT;
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -239,7 +235,8 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
     FrameXf* xf = reinterpret_cast<FrameXf*>(smem + OFF_XF);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // (the shuffle tells ptxas the role dispatch is warp-uniform)
     const int S = P.n_samples;
     constexpr int NUM_SEG_BUFS = (NP == 3) ? SEG_BUFS_3PASS : 2 * SEG_BUFS_3PASS;
     constexpr int SEG_BYTES = SEG_RING_BYTES / NUM_SEG_BUFS;
@@ -498,12 +495,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         const int gs = (nks - g0) < 4 ? (nks - g0) : 4;
                         // this CTA's gs hi tiles (+ gs lo tiles in the 3-pass mode) are contiguous in the stream: one slot, or two
                         const unsigned char* grp = base + 2 * pair_group_offset(g0, (int)crank, nks);
-                        if (SPLIT_PLANES) {
-                            push(grp, gs * HALF_TILE_BYTES);
-                            if (NP == 3) push(grp + gs * HALF_TILE_BYTES, gs * HALF_TILE_BYTES);
-                        } else {
-                            push(grp, (NP == 3 ? 2 : 1) * gs * HALF_TILE_BYTES);
-                        }
+                        push(grp, (NP == 3 ? 2 : 1) * gs * HALF_TILE_BYTES);
                     }
                     push(base + 2 * pair_bias_offset((int)crank, nks), HALF_TILE_BYTES);
                 }
@@ -533,45 +525,49 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 }
             }
         }
-        if (lane == 0 && leader) {
+        if (leader) {
+            // THE WHOLE WARP walks the schedule and waits on the barriers; the MMAs and commits sit in elect_one() blocks (see
+            // nb_tc_ptx.cuh): every value of the loop is warp-uniform, so an MMA costs the warp 1-2 instructions instead of the
+            // ~14 of the single-lane form.  The issuer shares its scheduler with four gathering producer warps, and with the
+            // single-lane form its own instruction stream -- 200+ cycles per MMA while the gather ran, 400 in the rolled layer-3
+            // loop (profiles/r02_trace_timeline_final.txt) -- not the tensor pipe bounded layers 1 and 3.
             uint32_t cnt = 0, hphase = 0, gseg = 0;
-            const uint32_t seg_addr = tc::smem_u32(smem + OFF_SEG), pe_addr = tc::smem_u32(smem + OFF_PE);
-            const uint32_t ones_addr = tc::smem_u32(smem + OFF_ONES), ring_addr = tc::smem_u32(smem + OFF_RING);
-            // M = 256: the pair's two 128-row tiles; N = the whole layer width, each CTA holding half of the B rows
-            constexpr uint32_t ID256 = tc::make_idesc_f16(256, 256), ID3 = tc::make_idesc_f16(256, kN3);
+            constexpr uint32_t FULL = 0xffffffffu;
+            constexpr uint32_t ID256 = tc::make_idesc_f16(256, 256), ID3 = tc::make_idesc_f16(256, kN3);   // M = 256: the pair's two tiles
+            constexpr uint32_t DHI = tc::desc_hi(128);                          // 8-row groups 128 B apart, every operand
+            // low descriptor words (start address | K-chunk stride) of the operand arrays; tiles / K-steps are 16-byte-unit adds
+            const uint32_t seg_lo = tc::desc_lo(tc::smem_u32(smem + OFF_SEG), SEG_CHUNK_STRIDE);
+            const uint32_t pe_lo = tc::desc_lo(tc::smem_u32(smem + OFF_PE), CHUNK_BYTES);
+            const uint32_t ones_lo = tc::desc_lo(tc::smem_u32(smem + OFF_ONES), CHUNK_BYTES);
+            const uint32_t ring256_lo = tc::desc_lo(tc::smem_u32(smem + OFF_RING), 128 * 16);      // 128-row half tiles of an N = 256 layer
+            const uint32_t ring3_lo = tc::desc_lo(tc::smem_u32(smem + OFF_RING), (kN3 / 2) * 16);  // 64-row half tiles of layer 3
+            constexpr uint32_t SLOT_U = SLOT_BYTES >> 4, T256_U = HALF_TILE_BYTES >> 4, T3_U = L3_TILE_BYTES >> 4;
+            constexpr uint32_t SEG_U = (uint32_t)SEG_BYTES >> 4, SEG_LO_U = (SEG_CHUNKS * SEG_CHUNK_STRIDE) >> 4;
+            constexpr uint32_t KS_SEG_U = (2 * SEG_CHUNK_STRIDE) >> 4, KS_A_U = (2 * CHUNK_BYTES) >> 4;
+            static_assert((2 * SEG_CHUNK_STRIDE) % 16 == 0 && SEG_BYTES % 16 == 0 && (SEG_CHUNKS * SEG_CHUNK_STRIDE) % 16 == 0, "descriptor units");
+            const uint32_t tm = __shfl_sync(FULL, tmem, 0);                     // (read from shared memory: tell ptxas it is uniform)
             Tracer tr;
-            tr.init(P.trace, 1);
+            tr.init(lane == 0 ? P.trace : nullptr, 1);
             // The tensor pipe queues only a few instructions, so whatever the issuer does between two MMAs beyond ~the queue's
-            // worth of cycles is a bubble (the trace showed ~750 cycles of barrier round trips per 1536-cycle group).  Hence:
-            // ONE barrier per weight slot, and the barriers of the NEXT group are probed (non-blocking) in the middle of the
-            // current group's MMAs; only a probe that failed is waited for.
+            // worth of cycles is a bubble.  Hence ONE barrier per weight slot, and the barriers of the NEXT group are probed
+            // (non-blocking, made warp-uniform by a vote) right after the current group's MMAs; only a failed probe is waited for.
             bool slot_seen = false;                          // the next slot's phase was already observed complete
             auto probe_slot = [&]() {
-                slot_seen = tc::mbar_test(&bars[BAR_W_FULL + cnt % NUM_SLOTS], (cnt / NUM_SLOTS) & 1);
+                slot_seen = __all_sync(FULL, tc::mbar_test(&bars[BAR_W_FULL + cnt % NUM_SLOTS], (cnt / NUM_SLOTS) & 1));
             };
-            auto wait_slot = [&](uint32_t& slot) {
-                slot = cnt % NUM_SLOTS;
+            auto wait_slot = [&]() {                         // -> the slot's offset in descriptor units
+                const uint32_t slot = cnt % NUM_SLOTS;
                 if (!slot_seen) { tr.ev(40); tc::mbar_wait(&bars[BAR_W_FULL + slot], (cnt / NUM_SLOTS) & 1); tr.ev(42); }
                 slot_seen = false;
                 tc::tc_fence_after();
+                return slot * SLOT_U;
             };
-            auto release_slot = [&](uint32_t slot) {
-                tc::mma_commit_pair(&bars[BAR_W_EMPTY + slot], CMASK);      // both CTAs' loaders reuse the slot
-                ++cnt;
-            };
-            auto a_desc = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * CHUNK_BYTES, CHUNK_BYTES, 128); };
-            auto a_seg = [&](uint32_t base, int ks) { return tc::make_smem_desc(base + ks * 2 * SEG_CHUNK_STRIDE, SEG_CHUNK_STRIDE, 128); };
-            // tile i of a slot holding 128-row half tiles of an N = 256 layer (K-chunks 2 KB apart)
-            auto b256 = [&](uint32_t slot, int i) {
-                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * HALF_TILE_BYTES, 128 * 16, 128);
-            };
-            auto b3 = [&](uint32_t slot, int i) {            // step i of a layer-3 slot (64-row half tiles)
-                return tc::make_smem_desc(ring_addr + slot * SLOT_BYTES + i * L3_TILE_BYTES, (kN3 / 2) * 16, 128);
-            };
+            // (inside an elect block) both CTAs' loaders reuse the slot once the MMAs issued so far are done
+            auto commit_slot = [&]() { tc::mma_commit_pair(&bars[BAR_W_EMPTY + cnt % NUM_SLOTS], CMASK); };
             // the epilogues of BOTH CTAs have converted columns [64 g, 64 g + 64) of the current activation region (K-steps 4g..4g+3)
             uint32_t h_seen = 0;                             // bit g: chunk g's phase was already observed complete
             auto probe_h = [&](int g) {
-                if (tc::mbar_test(&bars[BAR_H_READY + g], (hphase >> g) & 1)) h_seen |= 1u << g;
+                if (__all_sync(FULL, tc::mbar_test(&bars[BAR_H_READY + g], (hphase >> g) & 1))) h_seen |= 1u << g;
             };
             auto wait_h = [&](int g) {
                 if (!((h_seen >> g) & 1)) { tr.ev(44); tc::mbar_wait_cluster(&bars[BAR_H_READY + g], (hphase >> g) & 1); tr.ev(45); }
@@ -579,87 +575,116 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 hphase ^= 1u << g;
                 tc::tc_fence_after();
             };
+            // one layer-0 segment of NKS K-steps: slot = [NKS hi tiles | NKS lo tiles] (3-pass) or the hi tiles alone
+            auto l0_segment = [&](auto nks_c, uint32_t a_hi, uint32_t b, bool first) {
+                constexpr int NKS = decltype(nks_c)::value;
+#pragma unroll
+                for (int ks = 0; ks < NKS; ++ks) {
+                    tc::mma_ss_pair_w(tm + TM_R0, a_hi + ks * KS_SEG_U, b + ks * T256_U, DHI, ID256, ks != 0 || !first);
+                    if (NP == 3) tc::mma_ss_pair_w(tm + TM_R0, a_hi + SEG_LO_U + ks * KS_SEG_U, b + ks * T256_U, DHI, ID256, true);
+                }
+                if (NP == 3) {
+#pragma unroll
+                    for (int ks = 0; ks < NKS; ++ks)
+                        tc::mma_ss_pair_w(tm + TM_R0, a_hi + ks * KS_SEG_U, b + (NKS + ks) * T256_U, DHI, ID256, true);
+                }
+            };
+            // the bias step of an N = 256 layer (a column of ones x [hi(b), lo(b)]) and the layer's accumulator barrier
+            auto bias_and_commit = [&](uint32_t rout, int acc_bar) {
+                const uint32_t b = ring256_lo + wait_slot();
+                if (tc::elect_one()) {
+                    tc::mma_ss_pair_w(tm + rout, ones_lo, b, DHI, ID256, true);
+                    commit_slot();
+                    tc::mma_commit_pair(&bars[BAR_ACC_FULL + acc_bar], CMASK);
+                }
+                ++cnt;
+            };
             // a 256 -> 256 layer: A = activations in region `rin` (TMEM), accumulator = region `rout`
             auto layer256 = [&](uint32_t rin, uint32_t rout, int code) {
-                uint32_t slot;
+#pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     wait_h(g);
                     if (g == 0) tr.ev(30 + code);
-                    wait_slot(slot);                                            // [4 hi tiles | 4 lo tiles], or the hi tiles alone
+                    const uint32_t b = ring256_lo + wait_slot();                // [4 hi tiles | 4 lo tiles], or the hi tiles alone
+                    if (tc::elect_one()) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t a = tmem + rin + 16 * (4 * g + i);
-                        tc::mma_ts_pair(tmem + rout, a, b256(slot, i), ID256, (g | i) != 0);
-                        if (NP == 3) tc::mma_ts_pair(tmem + rout, a + 8, b256(slot, i), ID256, true);
-                    }
-                    if (NP == 3) {
-                        if (SPLIT_PLANES) { release_slot(slot); wait_slot(slot); }      // the lo tiles come in their own slot
-                        else if (g < 3) probe_h(g + 1);                                 // (probes ride under the 8 MMAs just queued)
+                        for (int i = 0; i < 4; ++i) {
+                            const uint32_t a = tm + rin + 16 * (4 * g + i);
+                            tc::mma_ts_pair_w(tm + rout, a, b + i * T256_U, DHI, ID256, (g | i) != 0);
+                            if (NP == 3) tc::mma_ts_pair_w(tm + rout, a + 8, b + i * T256_U, DHI, ID256, true);
+                        }
+                        if (NP == 3) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            tc::mma_ts_pair(tmem + rout, tmem + rin + 16 * (4 * g + i), b256(slot, (SPLIT_PLANES ? 0 : 4) + i), ID256, true);
+                            for (int i = 0; i < 4; ++i)
+                                tc::mma_ts_pair_w(tm + rout, tm + rin + 16 * (4 * g + i), b + (4 + i) * T256_U, DHI, ID256, true);
+                        }
+                        commit_slot();
                     }
-                    release_slot(slot);
+                    ++cnt;
+                    if (g < 3) probe_h(g + 1);                                  // (the probes ride under the MMAs just queued)
                     probe_slot();
                 }
-                wait_slot(slot);
-                tc::mma_ss_pair(tmem + rout, a_desc(ones_addr, 0), b256(slot, 0), ID256, true);
-                release_slot(slot);
-                tc::mma_commit_pair(&bars[BAR_ACC_FULL + (code & 1)], CMASK);
+                bias_and_commit(rout, code & 1);
                 tr.ev(20 + code);
             };
             for (int tbase = tile0; tbase < n_tiles; tbase += gridDim.x) {
-                uint32_t slot;
                 tr.ev(1);
                 // ---- layer 0: A = gathered feature segments (shared memory of each CTA), accumulator R0.  R0 held the previous
                 // tile's h2, whose last reader (its layer 3) was issued before: the tensor pipe executes in issue order.
-                const int nseg = class_segments(tile_ref(tbase).cls);
+                const int nseg = __shfl_sync(FULL, class_segments(tile_ref(tbase).cls), 0);
                 for (int seg = 0; seg < nseg; ++seg, ++gseg) {
                     const uint32_t buf = gseg % NUM_SEG_BUFS;
                     tc::mbar_wait_cluster(&bars[BAR_SEG_FULL + buf], (gseg / NUM_SEG_BUFS) & 1);
                     tc::tc_fence_after();
                     tr.ev(10 + seg);
-                    const uint32_t hi_addr = seg_addr + buf * SEG_BYTES, lo_addr = hi_addr + SEG_CHUNKS * SEG_CHUNK_STRIDE;
-                    const int nks = (seg == NUM_SEGS - 1) ? 2 : 4;
-                    wait_slot(slot);                                            // [nks hi tiles | nks lo tiles], or the hi tiles alone
-                    for (int ks = 0; ks < nks; ++ks) {
-                        tc::mma_ss_pair(tmem + TM_R0, a_seg(hi_addr, ks), b256(slot, ks), ID256, (seg | ks) != 0);
-                        if (NP == 3) tc::mma_ss_pair(tmem + TM_R0, a_seg(lo_addr, ks), b256(slot, ks), ID256, true);
+                    const uint32_t a_hi = seg_lo + buf * SEG_U;                 // (3-pass: the lo plane follows SEG_LO_U units later)
+                    const uint32_t b = ring256_lo + wait_slot();
+                    if (tc::elect_one()) {
+                        if (seg == NUM_SEGS - 1) l0_segment(std::integral_constant<int, 2>{}, a_hi, b, false);
+                        else l0_segment(std::integral_constant<int, 4>{}, a_hi, b, seg == 0);
+                        commit_slot();
+                        tc::mma_commit_pair(&bars[BAR_SEG_EMPTY + buf], CMASK);
                     }
-                    if (NP == 3) {
-                        if (SPLIT_PLANES) { release_slot(slot); wait_slot(slot); }
-                        for (int ks = 0; ks < nks; ++ks)
-                            tc::mma_ss_pair(tmem + TM_R0, a_seg(hi_addr, ks), b256(slot, (SPLIT_PLANES ? 0 : nks) + ks), ID256, true);
-                    }
-                    release_slot(slot);
-                    tc::mma_commit_pair(&bars[BAR_SEG_EMPTY + buf], CMASK);
+                    ++cnt;
                     probe_slot();
                 }
-                wait_slot(slot);
-                tc::mma_ss_pair(tmem + TM_R0, a_desc(ones_addr, 0), b256(slot, 0), ID256, true);
-                release_slot(slot);
-                tc::mma_commit_pair(&bars[BAR_ACC_FULL], CMASK);
+                bias_and_commit(TM_R0, 0);
                 tr.ev(20);
                 layer256(TM_R0, TM_R1, 1);       // layer 1: h0 (R0) -> R1
                 layer256(TM_R1, TM_R0, 2);       // layer 2: h1 (R1) -> R0
                 // ---- layer 3 (the folded colour layer, N = 128): A = h2 (R0) for K-steps 0..15, the per-point tile (shared memory)
                 // for 16..21; accumulator R1[0,128); L3_SPLIT steps per weight slot.  (R1 held h1, last read by layer 2.)
-                for (int k = 0; k < kStepsL3; ++k) {
-                    if (k % L3_SPLIT == 0) {
-                        if (k) { release_slot(slot); }
-                        wait_slot(slot);
+                // Unrolled: one elect block per run of K-steps between two waits.
+                static_assert(L3_SPLIT == 11 && kStepsL3 == 22, "layer-3 issue schedule");
+                uint32_t b3 = ring3_lo + wait_slot();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {            // K-steps 4q..4q+3 need the q-th converted quarter of h2
+                    wait_h(q);
+                    if (q == 0) tr.ev(33);
+                    if (q == 2) {                        // K-steps 8..10 end the first slot
+                        if (tc::elect_one()) {
+#pragma unroll
+                            for (int k = 8; k < 11; ++k) tc::mma_ts_pair_w(tm + TM_R1, tm + TM_R0 + 16 * k, b3 + k * T3_U, DHI, ID3, true);
+                            commit_slot();
+                        }
+                        ++cnt;
+                        b3 = ring3_lo + wait_slot();
+                        if (tc::elect_one()) tc::mma_ts_pair_w(tm + TM_R1, tm + TM_R0 + 16 * 11, b3, DHI, ID3, true);
+                    } else if (tc::elect_one()) {
+#pragma unroll
+                        for (int k = 4 * q; k < 4 * q + 4; ++k)
+                            tc::mma_ts_pair_w(tm + TM_R1, tm + TM_R0 + 16 * k, b3 + (k % L3_SPLIT) * T3_U, DHI, ID3, k != 0);
                     }
-                    if (k < 16 && (k & 3) == 0) {
-                        wait_h(k >> 2);
-                        if (k == 0) tr.ev(33);
-                    }
-                    const int i = k % L3_SPLIT;
-                    if (k < 16) tc::mma_ts_pair(tmem + TM_R1, tmem + TM_R0 + 16 * k, b3(slot, i), ID3, k != 0);
-                    else tc::mma_ss_pair(tmem + TM_R1, a_desc(pe_addr, k - 16), b3(slot, i), ID3, true);
-                    if (k < 12 && (k & 3) == 1) probe_h((k >> 2) + 1);
+                    if (q < 3) probe_h(q + 1);
                 }
-                release_slot(slot);
-                tc::mma_commit_pair(&bars[BAR_ACC_FULL + 1], CMASK);
+                if (tc::elect_one()) {
+#pragma unroll
+                    for (int k = 16; k < kStepsL3; ++k)  // the per-point tile [PE(xyz) | PE(view) | 1 | 1]
+                        tc::mma_ss_pair_w(tm + TM_R1, pe_lo + (k - 16) * KS_A_U, b3 + (k - L3_SPLIT) * T3_U, DHI, ID3, true);
+                    commit_slot();
+                    tc::mma_commit_pair(&bars[BAR_ACC_FULL + 1], CMASK);
+                }
+                ++cnt;
                 probe_slot();
                 tr.ev(23);
             }

@@ -214,6 +214,40 @@ __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask
                  "h"(cta_mask)
                  : "memory");
 }
+// ---- the same instructions for a WARP-UNIFORM issue loop: the whole warp walks the schedule and waits on the barriers, and
+// the MMAs / commits sit in `if (elect_one()) { ... }` blocks.  ptxas recognises elect.sync + branch as "one thread of a
+// converged warp" and then keeps warp-uniform operand values in uniform registers: an MMA is the bare UTCHMMA plus at most one
+// UIADD3 per operand that moves.  Under a plain `if (lane == 0)` the same code is a divergent region, where every
+// uniform-register operand is wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop (~14 SASS instructions per MMA): the
+// issuer's own instruction stream, not the tensor pipe, then bounds the short layers.
+// elect.sync is deterministic for a given member mask (PTX ISA), so the MMAs and the commits that track them come from one lane.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// The shared-memory descriptor travels as its two 32-bit words, so stepping to the next tile of an operand is ONE 32-bit add
+// on the low word (start address >> 4 in bits [0,14): sums of in-range addresses never carry out of the field).
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void mma_ss_pair_w(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi_word, uint32_t idesc,
+                                              bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 ad, bd;\n\tmov.b64 ad, {%1, %3};\n\tmov.b64 bd, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], ad, bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(desc_hi_word), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_ts_pair_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t desc_hi_word, uint32_t idesc,
+                                              bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\tmov.b64 bd, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(desc_hi_word), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
 // shared::cluster address of `local` (a shared::cta address of this CTA) in the CTA of rank `cta`
 __device__ __forceinline__ uint32_t map_to_cta(const void* local, uint32_t cta) {
     uint32_t r;
