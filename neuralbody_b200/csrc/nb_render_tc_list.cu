@@ -17,16 +17,18 @@
 // the 1 MB-per-tile weight stream, not the tensor pipe, bounded the single-CTA version) and reads half of them per MMA.
 //   warps  0..15  producers   trilinear gather of the 352 features into a ring of 64-channel layer-0 operand segments
 //   warps 16..19  epilogue    TMEM accumulator -> relu -> (hi, lo) fp16 operand of the next layer, IN PLACE (see below)
-//   warp  20      MMA issuer  leader: one thread issues every tcgen05.mma for the pair; peer: relays its bulk-copy completions
-//   warp  21      loader      one thread streams this CTA's half of the pre-packed weights through a 3-slot shared-memory ring
+//   warp  20      MMA issuer  leader: the warp walks the schedule, one elected lane issues every tcgen05.mma for the pair (a
+//                             warp-uniform loop: 1-2 SASS instructions per MMA); peer: relays its bulk-copy completions
+//   warp  21      loader      one thread streams this CTA's half of the pre-packed weights through a shared-memory ring
 // (the warp scheduler favours high warp ids, so the latency-critical roles sit above the 16 throughput warps).
 //
 // TMEM (512 columns) is two 256-column regions R0 | R1 that swap roles every layer: layer l accumulates into one region
 // while its A operand (the previous layer's activations) is read from the other.  The epilogue converts an accumulator
 // in place -- the 16 fp32 columns of K-step k become 8 columns of fp16 hi pairs + 8 columns of fp16 lo pairs -- and
-// signals every 64 columns, so the issuer starts layer l+1 on the first converted quarter while the epilogue is still
-// converting the rest: conversion and MMA overlap instead of alternating.  Layer 4 (the 3-wide rgb head) of tile t is
-// issued after the first layer-0 segment of tile t+1, which fills the bubble of its short epilogue.
+// signals after 32, 64, 128, 192 and 256 columns, so the issuer starts layer l+1 on the first converted columns while the
+// epilogue is still converting the rest: conversion and MMA overlap instead of alternating (what stays exposed of an epilogue
+// is the latency of its first hand-over).  h2 is converted to its hi halves only (rounded to nearest): the colour layer is a
+// 1-pass layer, and sigma = alpha_fc . relu(acc) and the 3-wide rgb head are fp32 dot products in the epilogue registers.
 //
 // Results do not depend on the (non-deterministic) order of the blocks in the list: a tile row is evaluated
 // independently of its neighbours.  The list and the raw (rgb logits, sigma) records cross HBM once each way.
@@ -40,17 +42,27 @@ using tcr::Quad;
 using tcr::Tracer;
 
 constexpr int TP = 128;
-// weight ring: NB_NUM_SLOTS slots of 32 KB: a slot takes the hi AND lo tiles of a 4-K-step group of an N = 256 layer (12 MMAs
-// per hand-off).  Measured (profiles/r02_ab_decoder_variants.txt): in pair mode two slots feed the issuer as well as three, and
-// the 32 KB saved buy a 4th layer-0 segment buffer (+2.5 %); 16 KB slots (one plane per hand-off) lost 8-13 %.
+// weight ring: NB_NUM_SLOTS slots of NB_SLOT_KB KB (64 KB in all; a 5th / 6th layer-0 segment buffer would be worth more, but
+// does not fit).  A 32 KB slot takes the hi AND lo tiles of a 4-K-step group of an N = 256 layer (12 MMAs per hand-off); 16 KB
+// slots take one plane each (8 / 4 MMAs per hand-off) and let the loader run three hand-offs ahead instead of one.
+#ifndef NB_SLOT_KB
+#define NB_SLOT_KB 32
+#endif
 #ifndef NB_NUM_SLOTS
-#define NB_NUM_SLOTS 2
+#define NB_NUM_SLOTS (64 / NB_SLOT_KB)
+#endif
+// NB_H_FIRST_SPLIT = 1: the first 64-column quarter of an activation region is handed over in two halves (K-steps 0-1, 2-3), so
+// the next layer starts after 32 converted columns: what is exposed of every epilogue is the latency of its FIRST hand-over.
+#ifndef NB_H_FIRST_SPLIT
+#define NB_H_FIRST_SPLIT 1
 #endif
 #ifndef NB_SEG_BUFS
 #define NB_SEG_BUFS 4
 #endif
 constexpr int NUM_SLOTS = NB_NUM_SLOTS;
-constexpr int SLOT_BYTES = 32 * 1024;
+constexpr int SLOT_BYTES = NB_SLOT_KB * 1024;
+static_assert(SLOT_BYTES == 32768 || SLOT_BYTES == 16384, "weight slot size");
+constexpr bool SPLIT_PLANES = SLOT_BYTES < 32768;                  // hi and lo tiles of a group travel in separate slots
 #ifndef NB_PROD_WAIT_NS
 #define NB_PROD_WAIT_NS 200
 #endif
@@ -80,7 +92,8 @@ constexpr uint32_t ID_MASK = 0x0FFFFFFFu;                          // list entry
 #define NB_CORNER_BATCH 4
 #endif
 constexpr int CORNER_BATCH = NB_CORNER_BATCH;                      // corner loads in flight per thread and batch
-constexpr int L3_SPLIT = 11;                                       // layer-3 K-steps per ring slot (2 KB per step and CTA)
+constexpr int L3_SPLIT = SPLIT_PLANES ? 8 : 11;                    // layer-3 K-steps per ring slot (2 KB per step and CTA)
+constexpr int HSPLIT = NB_H_FIRST_SPLIT ? 1 : 0;                   // extra hand-over barrier for the first half of quarter 0
 constexpr int HEAD_FLOATS = kHidden + 4 + 3 * kColor + 4;           // alpha_fc (256 + bias) and rgb_fc (3 x 128 + bias), fp32, resident
 constexpr int HALF_TILE_BYTES = kHalfTile256 * 2;                  // one K-step of an N = 256 layer, this CTA's 128 rows (4 KB)
 constexpr int L3_TILE_BYTES = kHalfTile3 * 2;                      // one K-step of layer 3, this CTA's 64 rows (2 KB)
@@ -99,8 +112,12 @@ constexpr int OFF_BAR = OFF_SCHED + 64;
 // (leader only): producers / epilogue warps of BOTH CTAs arrive (the peer's remotely).  W_EMPTY / SEG_EMPTY / ACC_FULL: the
 // leader's tcgen05.commit, multicast to both CTAs.
 enum { BAR_W_FULL = 0, BAR_W_EMPTY = NUM_SLOTS, BAR_SEG_FULL = 2 * NUM_SLOTS, BAR_SEG_EMPTY = 2 * NUM_SLOTS + MAX_SEG_BUFS,
-       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS /* x2, see below */, BAR_H_READY = BAR_ACC_FULL + 2 /* x4: one per 64 columns */,
-       NUM_BARS = BAR_H_READY + 4 };
+       BAR_ACC_FULL = 2 * NUM_SLOTS + 2 * MAX_SEG_BUFS /* x2, see below */, BAR_H_READY = BAR_ACC_FULL + 2 /* one per hand-over */,
+       NUM_BARS = BAR_H_READY + 4 + HSPLIT };
+// hand-over barrier of the columns holding K-step k of an activation region: one per 64 columns (4 K-steps); with HSPLIT the
+// first quarter is two hand-overs (K-steps 0-1 -> [0], 2-3 -> [1], then one per quarter)
+__host__ __device__ constexpr int h_bar_of_kstep(int k) { return HSPLIT ? (k < 2 ? 0 : k < 4 ? 1 : (k >> 2) + 1) : (k >> 2); }
+__host__ __device__ constexpr bool h_last_kstep(int k) { return (k & 3) == 3 || (HSPLIT && k == 1); }   // k closes its hand-over
 // ACC_FULL alternates between two barriers (layers 0 / 2 -> [0], layers 1 / 3 -> [1]): the issuer can run a whole layer 0 of
 // the next tile ahead of the epilogue, and with one barrier it could complete two phases before the epilogue looked at the first.
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
@@ -113,8 +130,8 @@ constexpr uint32_t TM_R0 = 0, TM_R1 = 256;     // (layer 3 accumulates its 128 c
 // weight-ring pushes of one tile (the loader issues them, the peer's relay forwards their completions): layer 0 of a class with
 // `l0_ksteps` K-steps, layers 1 / 2, layer 3
 __host__ __device__ constexpr int pushes_per_tile(int l0_ksteps, int passes) {
-    (void)passes;                                  // the hi and lo tiles of a group share a slot
-    return (l0_ksteps + 3) / 4 + 1 + 2 * (kKsL12 / 4 + 1) + (kStepsL3 + L3_SPLIT - 1) / L3_SPLIT;
+    const int planes = (SPLIT_PLANES && passes == 3) ? 2 : 1;
+    return ((l0_ksteps + 3) / 4) * planes + 1 + 2 * ((kKsL12 / 4) * planes + 1) + (kStepsL3 + L3_SPLIT - 1) / L3_SPLIT;
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
         for (int i = 0; i < NUM_SEG_BUFS; ++i) { tc::mbar_init(&bars[BAR_SEG_FULL + i], CLUSTER * PROD_WARPS); tc::mbar_init(&bars[BAR_SEG_EMPTY + i], 1); }
         tc::mbar_init(&bars[BAR_ACC_FULL], 1);
         tc::mbar_init(&bars[BAR_ACC_FULL + 1], 1);
-        for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[BAR_H_READY + i], CLUSTER * EPI_WARPS);
+        for (int i = 0; i < 4 + HSPLIT; ++i) tc::mbar_init(&bars[BAR_H_READY + i], CLUSTER * EPI_WARPS);
         tc::fence_mbar_init();
     }
     const int pwarp = warp - PROD_WARP0, ptid = tid - PROD_WARP0 * 32;       // producer-relative ids
@@ -495,7 +512,12 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         const int gs = (nks - g0) < 4 ? (nks - g0) : 4;
                         // this CTA's gs hi tiles (+ gs lo tiles in the 3-pass mode) are contiguous in the stream: one slot, or two
                         const unsigned char* grp = base + 2 * pair_group_offset(g0, (int)crank, nks);
-                        push(grp, (NP == 3 ? 2 : 1) * gs * HALF_TILE_BYTES);
+                        if (SPLIT_PLANES) {
+                            push(grp, gs * HALF_TILE_BYTES);
+                            if (NP == 3) push(grp + gs * HALF_TILE_BYTES, gs * HALF_TILE_BYTES);
+                        } else {
+                            push(grp, (NP == 3 ? 2 : 1) * gs * HALF_TILE_BYTES);
+                        }
                     }
                     push(base + 2 * pair_bias_offset((int)crank, nks), HALF_TILE_BYTES);
                 }
@@ -575,19 +597,19 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 hphase ^= 1u << g;
                 tc::tc_fence_after();
             };
-            // one layer-0 segment of NKS K-steps: slot = [NKS hi tiles | NKS lo tiles] (3-pass) or the hi tiles alone
-            auto l0_segment = [&](auto nks_c, uint32_t a_hi, uint32_t b, bool first) {
+            // one layer-0 segment of NKS K-steps against its hi weight tiles at `b` (A_hi W_hi, A_lo W_hi) / its lo tiles (A_hi W_lo)
+            auto l0_hi = [&](auto nks_c, uint32_t a_hi, uint32_t b, bool first) {
                 constexpr int NKS = decltype(nks_c)::value;
 #pragma unroll
                 for (int ks = 0; ks < NKS; ++ks) {
                     tc::mma_ss_pair_w(tm + TM_R0, a_hi + ks * KS_SEG_U, b + ks * T256_U, DHI, ID256, ks != 0 || !first);
                     if (NP == 3) tc::mma_ss_pair_w(tm + TM_R0, a_hi + SEG_LO_U + ks * KS_SEG_U, b + ks * T256_U, DHI, ID256, true);
                 }
-                if (NP == 3) {
+            };
+            auto l0_lo = [&](auto nks_c, uint32_t a_hi, uint32_t b) {
+                constexpr int NKS = decltype(nks_c)::value;
 #pragma unroll
-                    for (int ks = 0; ks < NKS; ++ks)
-                        tc::mma_ss_pair_w(tm + TM_R0, a_hi + ks * KS_SEG_U, b + (NKS + ks) * T256_U, DHI, ID256, true);
-                }
+                for (int ks = 0; ks < NKS; ++ks) tc::mma_ss_pair_w(tm + TM_R0, a_hi + ks * KS_SEG_U, b + ks * T256_U, DHI, ID256, true);
             };
             // the bias step of an N = 256 layer (a column of ones x [hi(b), lo(b)]) and the layer's accumulator barrier
             auto bias_and_commit = [&](uint32_t rout, int acc_bar) {
@@ -599,29 +621,41 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 }
                 ++cnt;
             };
+            // K-steps [k0, k1) of a 256 -> 256 layer against the hi weight tiles of its group: A_hi W_hi (+ A_lo W_hi)
+            auto hi_steps = [&](uint32_t rin, uint32_t rout, uint32_t b, int k0, int k1) {
+#pragma unroll
+                for (int k = k0; k < k1; ++k) {
+                    const uint32_t a = tm + rin + 16 * k;
+                    tc::mma_ts_pair_w(tm + rout, a, b + (k & 3) * T256_U, DHI, ID256, k != 0);
+                    if (NP == 3) tc::mma_ts_pair_w(tm + rout, a + 8, b + (k & 3) * T256_U, DHI, ID256, true);
+                }
+            };
             // a 256 -> 256 layer: A = activations in region `rin` (TMEM), accumulator = region `rout`
             auto layer256 = [&](uint32_t rin, uint32_t rout, int code) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
-                    wait_h(g);
+                    wait_h(h_bar_of_kstep(4 * g));
                     if (g == 0) tr.ev(30 + code);
-                    const uint32_t b = ring256_lo + wait_slot();                // [4 hi tiles | 4 lo tiles], or the hi tiles alone
+                    uint32_t b = ring256_lo + wait_slot();                      // [4 hi tiles | 4 lo tiles], or one plane per slot
+                    if (HSPLIT && g == 0) {                                     // quarter 0 arrives in two halves
+                        if (tc::elect_one()) hi_steps(rin, rout, b, 0, 2);
+                        wait_h(1);
+                    }
                     if (tc::elect_one()) {
+                        hi_steps(rin, rout, b, (HSPLIT && g == 0) ? 2 : 4 * g, 4 * g + 4);
+                        if (SPLIT_PLANES || NP != 3) commit_slot();
+                    }
+                    if (g < 3) probe_h(h_bar_of_kstep(4 * g + 4));              // (the probes ride under the MMAs just queued)
+                    if (NP == 3) {
+                        if (SPLIT_PLANES) { ++cnt; b = ring256_lo + wait_slot() - 4 * T256_U; }   // the lo tiles' own slot
+                        if (tc::elect_one()) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t a = tm + rin + 16 * (4 * g + i);
-                            tc::mma_ts_pair_w(tm + rout, a, b + i * T256_U, DHI, ID256, (g | i) != 0);
-                            if (NP == 3) tc::mma_ts_pair_w(tm + rout, a + 8, b + i * T256_U, DHI, ID256, true);
-                        }
-                        if (NP == 3) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
+                            for (int i = 0; i < 4; ++i)                         // A_hi W_lo
                                 tc::mma_ts_pair_w(tm + rout, tm + rin + 16 * (4 * g + i), b + (4 + i) * T256_U, DHI, ID256, true);
+                            commit_slot();
                         }
-                        commit_slot();
                     }
                     ++cnt;
-                    if (g < 3) probe_h(g + 1);                                  // (the probes ride under the MMAs just queued)
                     probe_slot();
                 }
                 bias_and_commit(rout, code & 1);
@@ -638,10 +672,25 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     tc::tc_fence_after();
                     tr.ev(10 + seg);
                     const uint32_t a_hi = seg_lo + buf * SEG_U;                 // (3-pass: the lo plane follows SEG_LO_U units later)
-                    const uint32_t b = ring256_lo + wait_slot();
-                    if (tc::elect_one()) {
-                        if (seg == NUM_SEGS - 1) l0_segment(std::integral_constant<int, 2>{}, a_hi, b, false);
-                        else l0_segment(std::integral_constant<int, 4>{}, a_hi, b, seg == 0);
+                    const bool short_seg = seg == NUM_SEGS - 1;                 // level 0: 32 channels = 2 K-steps
+                    uint32_t b = ring256_lo + wait_slot();
+                    if (SPLIT_PLANES && NP == 3) {                              // hi tiles, then the lo tiles from their own slot
+                        if (tc::elect_one()) {
+                            if (short_seg) l0_hi(std::integral_constant<int, 2>{}, a_hi, b, false);
+                            else l0_hi(std::integral_constant<int, 4>{}, a_hi, b, seg == 0);
+                            commit_slot();
+                        }
+                        ++cnt;
+                        b = ring256_lo + wait_slot();
+                        if (tc::elect_one()) {
+                            if (short_seg) l0_lo(std::integral_constant<int, 2>{}, a_hi, b);
+                            else l0_lo(std::integral_constant<int, 4>{}, a_hi, b);
+                            commit_slot();
+                            tc::mma_commit_pair(&bars[BAR_SEG_EMPTY + buf], CMASK);
+                        }
+                    } else if (tc::elect_one()) {
+                        if (short_seg) { l0_hi(std::integral_constant<int, 2>{}, a_hi, b, false); if (NP == 3) l0_lo(std::integral_constant<int, 2>{}, a_hi, b + 2 * T256_U); }
+                        else { l0_hi(std::integral_constant<int, 4>{}, a_hi, b, seg == 0); if (NP == 3) l0_lo(std::integral_constant<int, 4>{}, a_hi, b + 4 * T256_U); }
                         commit_slot();
                         tc::mma_commit_pair(&bars[BAR_SEG_EMPTY + buf], CMASK);
                     }
@@ -654,37 +703,24 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                 layer256(TM_R1, TM_R0, 2);       // layer 2: h1 (R1) -> R0
                 // ---- layer 3 (the folded colour layer, N = 128): A = h2 (R0) for K-steps 0..15, the per-point tile (shared memory)
                 // for 16..21; accumulator R1[0,128); L3_SPLIT steps per weight slot.  (R1 held h1, last read by layer 2.)
-                // Unrolled: one elect block per run of K-steps between two waits.
-                static_assert(L3_SPLIT == 11 && kStepsL3 == 22, "layer-3 issue schedule");
                 uint32_t b3 = ring3_lo + wait_slot();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {            // K-steps 4q..4q+3 need the q-th converted quarter of h2
-                    wait_h(q);
-                    if (q == 0) tr.ev(33);
-                    if (q == 2) {                        // K-steps 8..10 end the first slot
-                        if (tc::elect_one()) {
-#pragma unroll
-                            for (int k = 8; k < 11; ++k) tc::mma_ts_pair_w(tm + TM_R1, tm + TM_R0 + 16 * k, b3 + k * T3_U, DHI, ID3, true);
-                            commit_slot();
-                        }
-                        ++cnt;
-                        b3 = ring3_lo + wait_slot();
-                        if (tc::elect_one()) tc::mma_ts_pair_w(tm + TM_R1, tm + TM_R0 + 16 * 11, b3, DHI, ID3, true);
-                    } else if (tc::elect_one()) {
-#pragma unroll
-                        for (int k = 4 * q; k < 4 * q + 4; ++k)
-                            tc::mma_ts_pair_w(tm + TM_R1, tm + TM_R0 + 16 * k, b3 + (k % L3_SPLIT) * T3_U, DHI, ID3, k != 0);
+                for (int k = 0; k < kStepsL3; ++k) {     // unrolled: every condition below is a compile-time constant
+                    if (k && k % L3_SPLIT == 0) b3 = ring3_lo + wait_slot();
+                    if (k < 16 && (k == 0 || h_last_kstep(k - 1))) {
+                        wait_h(h_bar_of_kstep(k));
+                        if (k == 0) tr.ev(33);
                     }
-                    if (q < 3) probe_h(q + 1);
+                    const bool slot_ends = k % L3_SPLIT == L3_SPLIT - 1 || k == kStepsL3 - 1;
+                    if (tc::elect_one()) {
+                        if (k < 16) tc::mma_ts_pair_w(tm + TM_R1, tm + TM_R0 + 16 * k, b3 + (k % L3_SPLIT) * T3_U, DHI, ID3, k != 0);
+                        else tc::mma_ss_pair_w(tm + TM_R1, pe_lo + (k - 16) * KS_A_U, b3 + (k % L3_SPLIT) * T3_U, DHI, ID3, true);   // [PE(xyz) | PE(view) | 1 | 1]
+                        if (slot_ends) commit_slot();
+                        if (k == kStepsL3 - 1) tc::mma_commit_pair(&bars[BAR_ACC_FULL + 1], CMASK);
+                    }
+                    if (slot_ends) ++cnt;
+                    if (k < 14 && h_last_kstep(k + 1)) probe_h(h_bar_of_kstep(k + 2));        // the hand-over needed two K-steps from now
                 }
-                if (tc::elect_one()) {
-#pragma unroll
-                    for (int k = 16; k < kStepsL3; ++k)  // the per-point tile [PE(xyz) | PE(view) | 1 | 1]
-                        tc::mma_ss_pair_w(tm + TM_R1, pe_lo + (k - 16) * KS_A_U, b3 + (k - L3_SPLIT) * T3_U, DHI, ID3, true);
-                    commit_slot();
-                    tc::mma_commit_pair(&bars[BAR_ACC_FULL + 1], CMASK);
-                }
-                ++cnt;
                 probe_slot();
                 tr.ev(23);
             }
@@ -721,7 +757,7 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                         sig = fmaf(fmaxf(__uint_as_float(v[4 * q + 3]), 0.f), w4.w, sig);
                     }
                 }
-                if (NP == 3) {
+                if (NP == 3 && !sigma_too) {
                     uint32_t l[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -734,21 +770,24 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
                     tc::tmem_st8(base + 16 * k, h);
                     tc::tmem_st8(base + 16 * k + 8, l);
                 } else {
+                    // 1-pass mode, and h2 in every mode: layer 3 (the colour path) multiplies the hi halves only, so h2 is
+                    // rounded to nearest and its lo columns are left alone (the conversion is the epilogue's critical path)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) h[i] = tc::cvt_relu_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
                     tc::tmem_st8(base + 16 * k, h);
                 }
             };
             auto chunk_done = [&](int k) {
-                if ((k & 3) == 3) {
+                if (h_last_kstep(k)) {
                     tc::tmem_st_wait();
                     tc::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) arrive_at_leader(BAR_H_READY + (k >> 2));     // one arrival per warp, 4 + 4 warps of the pair
+                    if (lane == 0) arrive_at_leader(BAR_H_READY + h_bar_of_kstep(k));   // one arrival per warp, 4 + 4 warps of the pair
                 }
             };
             tc::tmem_ld16(base, va);
             tc::tmem_ld_wait(va);
+#pragma unroll
             for (int k = 0; k < 16; k += 2) {
                 tc::tmem_ld16(base + 16 * (k + 1), vb);
                 convert_store(va, k);
