@@ -64,8 +64,12 @@ constexpr int SLOT_BYTES = NB_SLOT_KB * 1024;
 static_assert(SLOT_BYTES == 32768 || SLOT_BYTES == 16384, "weight slot size");
 constexpr bool SPLIT_PLANES = SLOT_BYTES < 32768;                  // hi and lo tiles of a group travel in separate slots
 #ifndef NB_PROD_WAIT_NS
-#define NB_PROD_WAIT_NS 200
+#define NB_PROD_WAIT_NS 100
 #endif
+#ifndef NB_GATHER_AHEAD
+#define NB_GATHER_AHEAD 1
+#endif
+constexpr bool GATHER_AHEAD = NB_GATHER_AHEAD;                     // producers gather a segment into registers BEFORE they wait for its buffer
 constexpr unsigned PROD_WAIT_NS = NB_PROD_WAIT_NS;                 // sleep between the producers' probes for a free segment buffer
 constexpr int CHUNK_BYTES = 2048;
 constexpr int SEG_CHUNKS = 8;
@@ -376,12 +380,19 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
             int cur_lvl = -1;
             for (int seg = 0; seg < nseg; ++seg, ++gseg) {
                 const uint32_t buf = gseg % NUM_SEG_BUFS;
-                tc::mbar_wait_backoff(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1, PROD_WAIT_NS);
-                tr.ev(10 + seg);
+                // The gather itself needs no buffer: a segment is gathered and converted INTO REGISTERS first (16 packed words per
+                // thread), and only the 8 shared-memory stores wait for the ring slot.  With four buffers for six segments the
+                // last two of a tile used to start their L2-latency-bound gather (6-7 K cycles) only when the issuer had consumed
+                // segments 0 / 1 -- 3.4 K cycles of every 14 K-cycle layer 0 were exposed (profiles/r02_trace_timeline_h_split.txt)
+                // while the producers sat idle for 6 K cycles before.  This way the ring is one segment deeper than its buffers.
+                if (!GATHER_AHEAD) { tc::mbar_wait_backoff(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1, PROD_WAIT_NS); tr.ev(10 + seg); }
                 // this thread's (row, channel quad) slot of the hi plane; the lo plane follows SEG_CHUNKS chunk strides later
                 const uint32_t dst = seg_base + buf * SEG_BYTES + so0;
                 const int nunits = (seg == NUM_SEGS - 1) ? 1 : 2;
-                for (int uu = 0; uu < nunits; ++uu) {
+                uint2 hi_w[2][PTS_PER_GROUP], lo_w[2][PTS_PER_GROUP];      // [unit][row]: 4 channels as fp16 (hi, lo) pairs
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu) {
+                    if (uu >= nunits) continue;
                     const int unit = 2 * seg + uu;              // coarse level first (nb_layout.h feat_tc_to_orig)
                     int lvl, c0;
                     if (unit < 4) { lvl = 3; c0 = unit * 32; }
@@ -454,22 +465,27 @@ __global__ void __launch_bounds__(NT, 1) render_tc_list_kernel(const __grid_cons
 #pragma unroll
                     for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
                         const float (&a)[4] = acc[pp];
-                        const uint32_t so = dst + (uint32_t)(uu * 4 * SEG_CHUNK_STRIDE + pp * 16);   // K-major core-matrix layout
                         if (NP == 3) {
                             // (hi, lo) split with a truncated hi: the residual is exact and costs one LOP3 + half an FADD2 a value
-                            uint2 hi, lo;
-                            hi.x = tc::cvt_rz_f16x2(a[0], a[1]); hi.y = tc::cvt_rz_f16x2(a[2], a[3]);
+                            hi_w[uu][pp].x = tc::cvt_rz_f16x2(a[0], a[1]); hi_w[uu][pp].y = tc::cvt_rz_f16x2(a[2], a[3]);
                             float r0, r1, r2, r3;
                             tc::trunc_residual2(a[0], a[1], r0, r1);
                             tc::trunc_residual2(a[2], a[3], r2, r3);
-                            lo.x = tc::cvt_f16x2(r0, r1); lo.y = tc::cvt_f16x2(r2, r3);
-                            tcr::sts_v2(so, hi);
-                            tcr::sts_v2(so + SEG_CHUNKS * SEG_CHUNK_STRIDE, lo);
+                            lo_w[uu][pp].x = tc::cvt_f16x2(r0, r1); lo_w[uu][pp].y = tc::cvt_f16x2(r2, r3);
                         } else {
-                            uint2 hi;
-                            hi.x = tc::cvt_f16x2(a[0], a[1]); hi.y = tc::cvt_f16x2(a[2], a[3]);
-                            tcr::sts_v2(so, hi);
+                            hi_w[uu][pp].x = tc::cvt_f16x2(a[0], a[1]); hi_w[uu][pp].y = tc::cvt_f16x2(a[2], a[3]);
                         }
+                    }
+                }
+                if (GATHER_AHEAD) { tc::mbar_wait_backoff(&bars[BAR_SEG_EMPTY + buf], ((gseg / NUM_SEG_BUFS) & 1) ^ 1, PROD_WAIT_NS); tr.ev(10 + seg); }
+#pragma unroll
+                for (int uu = 0; uu < 2; ++uu) {
+                    if (uu >= nunits) continue;
+#pragma unroll
+                    for (int pp = 0; pp < PTS_PER_GROUP; ++pp) {
+                        const uint32_t so = dst + (uint32_t)(uu * 4 * SEG_CHUNK_STRIDE + pp * 16);   // K-major core-matrix layout
+                        tcr::sts_v2(so, hi_w[uu][pp]);
+                        if (NP == 3) tcr::sts_v2(so + SEG_CHUNKS * SEG_CHUNK_STRIDE, lo_w[uu][pp]);
                     }
                 }
                 tc::fence_proxy_async();
