@@ -1,20 +1,21 @@
 #!/bin/bash
-# Round-2 closing evidence on one GPU (tight budget): full GPU test suite, the default bench line, c5, two producer-wait
-# variants, the ncu launch list, one ncu --set full capture of the decoder (raw page exported here), the in-kernel timeline.
-tag=${1:-r2d}
+# Closing evidence on one GPU (about two minutes of box time): full GPU test suite, the default bench line, c5, optional
+# library variants (neuralbody_b200/libnb_<variant>.so), the ncu launch list, one ncu --set full capture of the decoder
+# (raw page exported on the box), the in-kernel timeline.      usage: tools/gpu_closing_evidence.sh tag [variant ...]
+tag=${1:-closing}; shift
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests -m gpu -q --timeout 200 > gpurun_out/${tag}_pytest.log 2>&1
 echo "pytest rc=$? $(tail -1 gpurun_out/${tag}_pytest.log)"
 timeout 300 python bench.py > gpurun_out/${tag}_bench_c2.json 2> gpurun_out/${tag}_bench_c2.err
 echo "bench c2 rc=$?"; tail -c 600 gpurun_out/${tag}_bench_c2.json | head -c 300; echo
-for v in w50 w100; do
+for v in "$@"; do
   NB_LIB_PATH=$PWD/neuralbody_b200/libnb_${v}.so timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_${v}.json 2> gpurun_out/${tag}_${v}.err
 done
 timeout 300 python bench.py --config c5 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_c5.json 2> gpurun_out/${tag}_bench_c5.err
 echo "bench c5 rc=$?"
 python - <<PY
 import json
-for v in ("bench_c2", "w50", "w100", "bench_c5"):
+for v in ["bench_c2", "bench_c5"] + "$*".split():
     try:
         d = json.loads(open("gpurun_out/${tag}_%s.json" % v).read().strip().splitlines()[-1])
         r = d["roofline"]
